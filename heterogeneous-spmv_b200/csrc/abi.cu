@@ -1,0 +1,1044 @@
+// C ABI of libhspmv.so (declared in include/hspmv.h): matrix handles, upload, Band-k build,
+// kernel selection and launch, device-event timing.  Host index work lives in bandk.cpp,
+// partition.cpp, io.cpp, heuristics.cpp; kernels in kernels.cuh / merge.cuh / gen.cuh.
+#include "gen.cuh"
+#include "host_index.h"
+#include "kernels.cuh"
+#include "merge.cuh"
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <initializer_list>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+using hspmv::u32;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(HSPMV_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));       \
+  } while (0)
+
+constexpr int64_t PAD = 16; // tail padding (elements) of every device array
+
+struct DeviceProps {
+  int device = -1, sms = 0, cc = 0;
+  int64_t l2 = 0, hbm = 0;
+  size_t max_smem_optin = 0;
+  int max_persist_l2 = 0, max_window = 0;
+};
+
+int query_props(DeviceProps &p) {
+  int dev;
+  CU(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, dev));
+  p.device = dev;
+  p.sms = prop.multiProcessorCount;
+  p.cc = prop.major * 10 + prop.minor;
+  p.l2 = prop.l2CacheSize;
+  p.hbm = (int64_t)prop.totalGlobalMem;
+  p.max_smem_optin = prop.sharedMemPerBlockOptin;
+  p.max_persist_l2 = prop.persistingL2CacheMaxSize;
+  p.max_window = prop.accessPolicyMaxWindowSize;
+  return HSPMV_OK;
+}
+
+} // namespace
+
+struct hspmv_matrix {
+  int dtype = HSPMV_F64;
+  int64_t m = 0, n = 0, nnz = 0;
+  int k = 1;
+  int64_t n_sr = 0, n_ssr = 0;
+  DeviceProps dev;
+
+  int *d_rp = nullptr, *d_ci = nullptr;
+  void *d_val = nullptr, *d_x = nullptr, *d_y = nullptr, *d_tmp = nullptr;
+  u32 *d_sr = nullptr, *d_ssr = nullptr, *d_sr_e = nullptr, *d_perm = nullptr;
+
+  // CSR_VECTOR bins
+  bool bins_ready = false;
+  int *d_bin_rows = nullptr;
+  int64_t bin_ptr[hspmv::NUM_BINS + 1] = {0};
+  int64_t stats[10] = {0};
+  bool stats_ready = false;
+
+  // CSR_MERGE
+  int64_t merge_tile = 0, merge_tiles = 0;
+  int merge_ctas = 0;
+  int *d_tile_row = nullptr, *d_carry_row = nullptr;
+  void *d_carry_val = nullptr;
+
+  // host copies (kept on request; needed for Band-k)
+  std::vector<int32_t> h_rp, h_ci;
+  std::vector<unsigned char> h_val;
+  std::vector<u32> h_perm, h_sr, h_ssr;
+
+  int64_t opt[16] = {0};
+  cudaStream_t stream = nullptr; // handle's own stream (timed runs, set_x/get_y)
+  void *d_flush = nullptr;
+  size_t flush_bytes = 0;
+  bool l2_window_set = false;
+  std::string last_kernel;
+
+  size_t vsize() const { return dtype == HSPMV_F64 ? 8 : 4; }
+};
+
+namespace {
+
+void free_device(hspmv_matrix *A) {
+  void *ptrs[] = {A->d_rp, A->d_ci, A->d_val, A->d_x, A->d_y, A->d_tmp, A->d_sr, A->d_ssr,
+                  A->d_sr_e, A->d_perm, A->d_bin_rows, A->d_tile_row, A->d_carry_row,
+                  A->d_carry_val, A->d_flush};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+}
+
+int alloc_vectors(hspmv_matrix *A) {
+  const size_t vs = A->vsize();
+  const int64_t big = (A->n > A->m ? A->n : A->m) + PAD;
+  CU(cudaMalloc(&A->d_x, (size_t)(A->n + PAD) * vs));
+  CU(cudaMalloc(&A->d_y, (size_t)(A->m + PAD) * vs));
+  CU(cudaMalloc(&A->d_tmp, (size_t)big * vs));
+  CU(cudaMemset(A->d_x, 0, (size_t)(A->n + PAD) * vs));
+  CU(cudaMemset(A->d_y, 0, (size_t)(A->m + PAD) * vs));
+  return HSPMV_OK;
+}
+
+int alloc_matrix_arrays(hspmv_matrix *A) {
+  const size_t vs = A->vsize();
+  CU(cudaMalloc(&A->d_rp, (size_t)(A->m + 1 + PAD) * 4));
+  CU(cudaMalloc(&A->d_ci, (size_t)(A->nnz + PAD) * 4));
+  CU(cudaMalloc(&A->d_val, (size_t)(A->nnz + PAD) * vs));
+  // the pads are read by aligned quads / TMA windows that straddle the end: keep them defined
+  CU(cudaMemset((char *)A->d_rp + (size_t)(A->m + 1) * 4, 0, PAD * 4));
+  CU(cudaMemset((char *)A->d_ci + (size_t)A->nnz * 4, 0, PAD * 4));
+  CU(cudaMemset((char *)A->d_val + (size_t)A->nnz * vs, 0, PAD * vs));
+  return HSPMV_OK;
+}
+
+int new_handle(hspmv_matrix **out, int dtype, int64_t m, int64_t n, int64_t nnz) {
+  if (!out) return fail(HSPMV_EINVAL, "null handle pointer");
+  if (dtype != HSPMV_F32 && dtype != HSPMV_F64) return fail(HSPMV_EINVAL, "dtype must be HSPMV_F32 or HSPMV_F64");
+  if (m < 0 || n < 0 || nnz < 0 || nnz > 2147483647LL - PAD || m > 2147483647LL - PAD)
+    return fail(HSPMV_EINVAL, "sizes out of the 32-bit index range of the file formats");
+  hspmv_matrix *A = new hspmv_matrix();
+  A->dtype = dtype;
+  A->m = m;
+  A->n = n;
+  A->nnz = nnz;
+  int rc = query_props(A->dev);
+  if (rc) {
+    delete A;
+    return rc;
+  }
+  if (A->dev.cc < 100) {
+    delete A;
+    return fail(HSPMV_ECUDA, "libhspmv needs an sm_100 (Blackwell) device; there is no fallback path");
+  }
+  cudaError_t e = cudaStreamCreateWithFlags(&A->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete A;
+    return fail(HSPMV_ECUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+  }
+  *out = A;
+  return HSPMV_OK;
+}
+
+int grid_for(int64_t items, int threads, int cap) {
+  int64_t g = (items + threads - 1) / threads;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (int)g;
+}
+
+#define LAUNCHED() g_launches.fetch_add(1, std::memory_order_relaxed)
+
+// ---- bins ---------------------------------------------------------------------------
+int ensure_host_rp(hspmv_matrix *A, std::vector<int32_t> &rp) {
+  if (!A->h_rp.empty()) {
+    rp = A->h_rp;
+    return HSPMV_OK;
+  }
+  rp.resize((size_t)A->m + 1);
+  CU(cudaMemcpy(rp.data(), A->d_rp, (size_t)(A->m + 1) * 4, cudaMemcpyDeviceToHost));
+  return HSPMV_OK;
+}
+
+int ensure_stats(hspmv_matrix *A) {
+  if (A->stats_ready) return HSPMV_OK;
+  std::vector<int32_t> rp;
+  int rc = ensure_host_rp(A, rp);
+  if (rc) return rc;
+  hspmv::row_stats(A->m, rp.data(), A->stats);
+  A->stats_ready = true;
+  return HSPMV_OK;
+}
+
+int ensure_bins(hspmv_matrix *A) {
+  if (A->bins_ready) return HSPMV_OK;
+  std::vector<int32_t> rp, rows;
+  int rc = ensure_host_rp(A, rp);
+  if (rc) return rc;
+  hspmv::bin_rows(A->m, rp.data(), rows, A->bin_ptr);
+  CU(cudaMalloc(&A->d_bin_rows, (size_t)(A->m + 1) * 4));
+  if (A->m) CU(cudaMemcpy(A->d_bin_rows, rows.data(), (size_t)A->m * 4, cudaMemcpyHostToDevice));
+  A->bins_ready = true;
+  return HSPMV_OK;
+}
+
+// ---- launches -------------------------------------------------------------------------
+template <typename T, int VEC>
+void launch_vector(hspmv_matrix *A, bool list, const int *rows, int64_t n_rows, int64_t row_base,
+                   const T *x, T *y, cudaStream_t st) {
+  if (n_rows <= 0) return;
+  const int threads = 256;
+  const int64_t groups_per_cta = threads / VEC;
+  int64_t want = (n_rows + groups_per_cta - 1) / groups_per_cta;
+  const int64_t cap = (int64_t)A->dev.sms * 64; // grid-stride beyond this
+  int grid = (int)(want < cap ? want : cap);
+  if (list)
+    hspmv::csr_vector_kernel<T, VEC, true><<<grid, threads, 0, st>>>(
+        n_rows, rows, 0, A->d_rp, A->d_ci, (const T *)A->d_val, x, y);
+  else
+    hspmv::csr_vector_kernel<T, VEC, false><<<grid, threads, 0, st>>>(
+        n_rows, nullptr, row_base, A->d_rp, A->d_ci, (const T *)A->d_val, x, y);
+  LAUNCHED();
+}
+
+template <typename T>
+void launch_vector_vec(hspmv_matrix *A, int vec, bool list, const int *rows, int64_t n_rows,
+                       int64_t row_base, const T *x, T *y, cudaStream_t st) {
+  switch (vec) {
+  case 1: launch_vector<T, 1>(A, list, rows, n_rows, row_base, x, y, st); break;
+  case 2: launch_vector<T, 2>(A, list, rows, n_rows, row_base, x, y, st); break;
+  case 4: launch_vector<T, 4>(A, list, rows, n_rows, row_base, x, y, st); break;
+  case 8: launch_vector<T, 8>(A, list, rows, n_rows, row_base, x, y, st); break;
+  case 16: launch_vector<T, 16>(A, list, rows, n_rows, row_base, x, y, st); break;
+  default: launch_vector<T, 32>(A, list, rows, n_rows, row_base, x, y, st); break;
+  }
+}
+
+int pow2_floor_clamped(int64_t v) {
+  int p = 1;
+  while (p < 32 && (int64_t)p * 2 <= v) p <<= 1;
+  return p;
+}
+
+// CSR_VECTOR: one contiguous launch when every row fits the chosen lane count in a few steps,
+// otherwise one launch per non-empty bin.
+template <typename T>
+int run_csr_vector(hspmv_matrix *A, const T *x, T *y, cudaStream_t st) {
+  int rc = ensure_stats(A);
+  if (rc) return rc;
+  const int64_t max_len = A->stats[8];
+  const double mean = A->m ? (double)A->nnz / (double)A->m : 0.0;
+  int vec = (int)A->opt[HSPMV_OPT_VEC];
+  if (vec <= 0) { // lanes * 4 entries per step should cover the mean row (+3 for misalignment)
+    vec = 1;
+    while (vec < 32 && vec * 4 < mean + 3) vec <<= 1;
+  }
+  const bool regular = max_len <= (int64_t)vec * 4 * 8 || A->opt[HSPMV_OPT_VEC] > 0;
+  char name[96];
+  if (regular) {
+    launch_vector_vec<T>(A, vec, false, nullptr, A->m, 0, x, y, st);
+    std::snprintf(name, sizeof(name), "csr_vector<%s,vec=%d> contiguous", sizeof(T) == 8 ? "f64" : "f32", vec);
+    A->last_kernel = name;
+    return HSPMV_OK;
+  }
+  rc = ensure_bins(A);
+  if (rc) return rc;
+  static const int bin_vec[hspmv::NUM_BINS] = {1, 1, 2, 4, 8, 16, 32, 32};
+  int launches = 0;
+  for (int b = 0; b < hspmv::NUM_BINS; ++b) {
+    const int64_t cnt = A->bin_ptr[b + 1] - A->bin_ptr[b];
+    if (!cnt) continue;
+    const int *rows = A->d_bin_rows + A->bin_ptr[b];
+    if (b == 0) {
+      hspmv::zero_rows_kernel<T><<<grid_for(cnt, 256, A->dev.sms * 8), 256, 0, st>>>(cnt, rows, y);
+      LAUNCHED();
+    } else if (b == hspmv::NUM_BINS - 1) {
+      hspmv::csr_blockrow_kernel<T><<<(int)(cnt < A->dev.sms * 8 ? cnt : A->dev.sms * 8), 256, 0, st>>>(
+          cnt, rows, A->d_rp, A->d_ci, (const T *)A->d_val, x, y);
+      LAUNCHED();
+    } else {
+      launch_vector_vec<T>(A, bin_vec[b], true, rows, cnt, 0, x, y, st);
+    }
+    ++launches;
+  }
+  std::snprintf(name, sizeof(name), "csr_vector<%s> binned (%d launches)", sizeof(T) == 8 ? "f64" : "f32", launches);
+  A->last_kernel = name;
+  return HSPMV_OK;
+}
+
+template <typename T, int VEC>
+int launch_csrk(hspmv_matrix *A, const hspmv::CsrkParams<T> &p, int grid, int warps, size_t smem,
+                cudaStream_t st) {
+  auto kern = hspmv::csrk_tma_kernel<T, VEC>;
+  static size_t configured[64] = {0}; // per device: opt-in shared memory already granted
+  size_t &have = configured[A->dev.device & 63];
+  if (smem > have) {
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    have = smem;
+  }
+  kern<<<grid, warps * 32, smem, st>>>(p);
+  LAUNCHED();
+  return HSPMV_OK;
+}
+
+// CSRK (k = 2,3 after hspmv_build_csrk / hspmv_create_csrk) and CSR_STREAM (k = 1, fixed-row tiles)
+template <typename T>
+int run_csrk(hspmv_matrix *A, bool stream_mode, const T *x, T *y, cudaStream_t st) {
+  if (!stream_mode && A->k < 2) return fail(HSPMV_ESTATE, "HSPMV_ALGO_CSRK needs hspmv_build_csrk or hspmv_create_csrk first");
+  const double mean = A->m ? (double)A->nnz / (double)A->m : 1.0;
+  int vec = (int)A->opt[HSPMV_OPT_VEC];
+  if (vec <= 0) vec = mean <= 12 ? 1 : mean <= 48 ? 2 : mean <= 96 ? 4 : mean <= 192 ? 8 : mean <= 384 ? 16 : 32;
+  int warps = (int)A->opt[HSPMV_OPT_WARPS];
+  if (warps <= 0) warps = 8;
+  if (warps > 16) warps = 16;
+  int stages = (int)A->opt[HSPMV_OPT_STAGES];
+  if (stages <= 0) stages = 2;
+
+  hspmv::CsrkParams<T> p;
+  p.m = A->m;
+  p.rp = A->d_rp;
+  p.ci = A->d_ci;
+  p.val = (const T *)A->d_val;
+  p.x = x;
+  p.y = y;
+  p.ssr_ptr = A->d_ssr;
+  p.sr_ptr = A->d_sr;
+  p.sr_e = A->d_sr_e;
+  p.n_ssr = A->n_ssr;
+  p.stages = stages;
+  p.rows_per_tile = 0;
+
+  int64_t work_items; // what the grid is spread over
+  int64_t typical_rows, typical_nnz;
+  if (stream_mode) {
+    int rpt = (int)A->opt[HSPMV_OPT_ROWS_PER_TILE];
+    if (rpt <= 0) { // ~768 nonzeros per tile, whole passes of the warp
+      const int per_pass = 32 / vec;
+      rpt = (int)(768.0 / (mean > 1 ? mean : 1.0) + 0.5);
+      rpt = ((rpt + per_pass - 1) / per_pass) * per_pass;
+      if (rpt < per_pass) rpt = per_pass;
+    }
+    p.k = 1;
+    p.rows_per_tile = rpt;
+    p.n_sr = (A->m + rpt - 1) / rpt;
+    work_items = (p.n_sr + warps - 1) / warps;
+    typical_rows = rpt;
+    typical_nnz = (int64_t)(rpt * mean);
+  } else {
+    p.k = A->k;
+    p.n_sr = A->n_sr;
+    work_items = A->k == 3 ? A->n_ssr : (A->n_sr + warps - 1) / warps;
+    typical_rows = A->n_sr ? (A->m + A->n_sr - 1) / A->n_sr : 1;
+    typical_nnz = A->n_sr ? (A->nnz + A->n_sr - 1) / A->n_sr : 1;
+  }
+
+  // stage capacity: explicit option, else 1.5x the typical super-row, within shared memory
+  int cap_nnz = (int)A->opt[HSPMV_OPT_STAGE_NNZ];
+  if (cap_nnz <= 0) cap_nnz = (int)((typical_nnz * 3 / 2 + 64 + 3) & ~(int64_t)3);
+  int cap_rows = (int)((typical_rows * 2 + 32 + 3) & ~(int64_t)3);
+  if (cap_nnz < 64) cap_nnz = 64;
+  const size_t budget = A->dev.max_smem_optin - 1024;
+  auto total = [&](int cn, int cr) {
+    return (((size_t)warps * stages * 8 + 127) & ~(size_t)127) +
+           (size_t)warps * stages * hspmv::csrk_stage_bytes(cn, cr, sizeof(T));
+  };
+  while (total(cap_nnz, cap_rows) > budget && cap_nnz > 64) cap_nnz = (cap_nnz * 3 / 4) & ~3;
+  while (total(cap_nnz, cap_rows) > budget && cap_rows > 8) cap_rows = (cap_rows / 2) & ~3;
+  if (total(cap_nnz, cap_rows) > budget) return fail(HSPMV_EINVAL, "warps*stages does not fit shared memory");
+  cap_nnz &= ~3;
+  cap_rows &= ~3;
+  p.cap_nnz = cap_nnz;
+  p.cap_rows = cap_rows;
+  const size_t smem = total(cap_nnz, cap_rows);
+
+  int ctas_per_sm = (int)A->opt[HSPMV_OPT_CTAS_PER_SM];
+  if (ctas_per_sm <= 0) {
+    ctas_per_sm = (int)((A->dev.max_smem_optin + 1024) / (smem + 1024));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    if (ctas_per_sm * warps > 32) ctas_per_sm = 32 / warps > 0 ? 32 / warps : 1;
+  }
+  int64_t grid = (int64_t)A->dev.sms * ctas_per_sm;
+  if (grid > work_items) grid = work_items;
+  if (grid < 1) grid = 1;
+
+  int rc;
+  switch (vec) {
+  case 1: rc = launch_csrk<T, 1>(A, p, (int)grid, warps, smem, st); break;
+  case 2: rc = launch_csrk<T, 2>(A, p, (int)grid, warps, smem, st); break;
+  case 4: rc = launch_csrk<T, 4>(A, p, (int)grid, warps, smem, st); break;
+  case 8: rc = launch_csrk<T, 8>(A, p, (int)grid, warps, smem, st); break;
+  case 16: rc = launch_csrk<T, 16>(A, p, (int)grid, warps, smem, st); break;
+  default: rc = launch_csrk<T, 32>(A, p, (int)grid, warps, smem, st); vec = 32; break;
+  }
+  if (rc) return rc;
+  char name[160];
+  std::snprintf(name, sizeof(name), "csrk_tma<%s,vec=%d> k=%d grid=%d warps=%d stages=%d cap_nnz=%d cap_rows=%d%s",
+                sizeof(T) == 8 ? "f64" : "f32", vec, p.k, (int)grid, warps, stages, cap_nnz, cap_rows,
+                stream_mode ? " (CSR stream tiles)" : "");
+  A->last_kernel = name;
+  return HSPMV_OK;
+}
+
+template <typename T>
+int run_csr_merge(hspmv_matrix *A, const T *x, T *y, cudaStream_t st) {
+  int64_t tile = A->opt[HSPMV_OPT_MERGE_TILE];
+  if (tile <= 0) tile = 4096;
+  tile &= ~(int64_t)3;
+  int ctas_per_sm = (int)A->opt[HSPMV_OPT_CTAS_PER_SM];
+  if (ctas_per_sm <= 0) ctas_per_sm = 4;
+  if (A->nnz == 0) {
+    CU(cudaMemsetAsync(y, 0, (size_t)A->m * sizeof(T), st));
+    A->last_kernel = "memset (empty matrix)";
+    return HSPMV_OK;
+  }
+  const int64_t n_tiles = (A->nnz + tile - 1) / tile;
+  int64_t ctas = (int64_t)A->dev.sms * ctas_per_sm;
+  if (ctas > n_tiles) ctas = n_tiles;
+  if (A->merge_tile != tile || A->merge_ctas != (int)ctas) {
+    if (A->d_tile_row) cudaFree(A->d_tile_row);
+    if (A->d_carry_row) cudaFree(A->d_carry_row);
+    if (A->d_carry_val) cudaFree(A->d_carry_val);
+    A->d_tile_row = A->d_carry_row = nullptr;
+    A->d_carry_val = nullptr;
+    CU(cudaMalloc(&A->d_tile_row, (size_t)(n_tiles + 1) * 4));
+    CU(cudaMalloc(&A->d_carry_row, (size_t)ctas * 4));
+    CU(cudaMalloc(&A->d_carry_val, (size_t)ctas * 8));
+    hspmv::tile_rows_kernel<<<grid_for(n_tiles + 1, 256, A->dev.sms * 8), 256, 0, st>>>(
+        A->m, A->d_rp, tile, n_tiles, A->d_tile_row);
+    LAUNCHED();
+    A->merge_tile = tile;
+    A->merge_tiles = n_tiles;
+    A->merge_ctas = (int)ctas;
+  }
+  const size_t smem = (size_t)tile * sizeof(T);
+  auto kern = hspmv::csr_merge_kernel<T, 256>;
+  static size_t configured[64] = {0};
+  size_t &have = configured[A->dev.device & 63];
+  if (smem > have) {
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    have = smem;
+  }
+  kern<<<(int)ctas, 256, smem, st>>>(A->m, A->nnz, (int)tile, n_tiles, A->d_tile_row, A->d_rp, A->d_ci,
+                                     (const T *)A->d_val, x, y, A->d_carry_row, (T *)A->d_carry_val);
+  LAUNCHED();
+  hspmv::merge_fixup_kernel<T><<<1, 32, 0, st>>>((int)ctas, A->d_carry_row, (const T *)A->d_carry_val, y);
+  LAUNCHED();
+  char name[96];
+  std::snprintf(name, sizeof(name), "csr_merge<%s> tile=%d ctas=%d + fixup", sizeof(T) == 8 ? "f64" : "f32",
+                (int)tile, (int)ctas);
+  A->last_kernel = name;
+  return HSPMV_OK;
+}
+
+int apply_l2_window(hspmv_matrix *A, const void *x, cudaStream_t st) {
+  if (!A->opt[HSPMV_OPT_L2_PERSIST_X] || A->dev.max_persist_l2 <= 0) return HSPMV_OK;
+  size_t bytes = (size_t)A->n * A->vsize();
+  size_t persist = bytes < (size_t)A->dev.max_persist_l2 ? bytes : (size_t)A->dev.max_persist_l2;
+  if (!A->l2_window_set) {
+    CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist));
+    A->l2_window_set = true;
+  }
+  cudaStreamAttrValue attr;
+  std::memset(&attr, 0, sizeof(attr));
+  size_t win = bytes < (size_t)A->dev.max_window ? bytes : (size_t)A->dev.max_window;
+  attr.accessPolicyWindow.base_ptr = const_cast<void *>(x);
+  attr.accessPolicyWindow.num_bytes = win;
+  attr.accessPolicyWindow.hitRatio = win ? (float)((double)persist / (double)win > 1.0 ? 1.0 : (double)persist / (double)win) : 0.f;
+  attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  CU(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
+  return HSPMV_OK;
+}
+
+template <typename T>
+int dispatch(hspmv_matrix *A, int algo, const void *dx, void *dy, cudaStream_t st) {
+  const T *x = (const T *)(dx ? dx : A->d_x);
+  T *y = (T *)(dy ? dy : A->d_y);
+  if (A->m == 0) return HSPMV_OK;
+  int rc = apply_l2_window(A, x, st);
+  if (rc) return rc;
+  if (algo == HSPMV_ALGO_AUTO) {
+    if (A->k >= 2) {
+      algo = HSPMV_ALGO_CSRK;
+    } else {
+      rc = ensure_stats(A);
+      if (rc) return rc;
+      const double mean = A->m ? (double)A->nnz / (double)A->m : 0.0;
+      // regular short rows: the TMA tile engine; skewed row lengths: nnz-balanced merge
+      algo = (A->stats[8] <= 8 * (mean + 1) + 64) ? HSPMV_ALGO_CSR_STREAM : HSPMV_ALGO_CSR_MERGE;
+    }
+  }
+  switch (algo) {
+  case HSPMV_ALGO_CSR_VECTOR: rc = run_csr_vector<T>(A, x, y, st); break;
+  case HSPMV_ALGO_CSR_STREAM: rc = run_csrk<T>(A, true, x, y, st); break;
+  case HSPMV_ALGO_CSR_MERGE: rc = run_csr_merge<T>(A, x, y, st); break;
+  case HSPMV_ALGO_CSRK: rc = run_csrk<T>(A, false, x, y, st); break;
+  default: return fail(HSPMV_EINVAL, "unknown algo");
+  }
+  if (rc) return rc;
+  CU(cudaGetLastError());
+  return HSPMV_OK;
+}
+
+int do_spmv(hspmv_matrix *A, int algo, const void *dx, void *dy, cudaStream_t st) {
+  return A->dtype == HSPMV_F64 ? dispatch<double>(A, algo, dx, dy, st) : dispatch<float>(A, algo, dx, dy, st);
+}
+
+int upload_csrk_maps(hspmv_matrix *A) {
+  for (u32 **p : {&A->d_sr, &A->d_ssr, &A->d_sr_e, &A->d_perm})
+    if (*p) {
+      cudaFree(*p);
+      *p = nullptr;
+    }
+  CU(cudaMalloc(&A->d_sr, (size_t)(A->n_sr + 1 + PAD) * 4));
+  CU(cudaMemset(A->d_sr, 0, (size_t)(A->n_sr + 1 + PAD) * 4));
+  CU(cudaMemcpy(A->d_sr, A->h_sr.data(), (size_t)(A->n_sr + 1) * 4, cudaMemcpyHostToDevice));
+  CU(cudaMalloc(&A->d_sr_e, (size_t)(A->n_sr + 1 + PAD) * 4));
+  hspmv::sr_offsets_kernel<<<grid_for(A->n_sr + 1, 256, A->dev.sms * 8), 256, 0, A->stream>>>(A->n_sr, A->d_sr, A->d_rp, A->d_sr_e);
+  LAUNCHED();
+  if (A->k == 3) {
+    CU(cudaMalloc(&A->d_ssr, (size_t)(A->n_ssr + 1 + PAD) * 4));
+    CU(cudaMemset(A->d_ssr, 0, (size_t)(A->n_ssr + 1 + PAD) * 4));
+    CU(cudaMemcpy(A->d_ssr, A->h_ssr.data(), (size_t)(A->n_ssr + 1) * 4, cudaMemcpyHostToDevice));
+  }
+  if (!A->h_perm.empty()) {
+    CU(cudaMalloc(&A->d_perm, (size_t)(A->m + PAD) * 4));
+    CU(cudaMemcpy(A->d_perm, A->h_perm.data(), (size_t)A->m * 4, cudaMemcpyHostToDevice));
+  }
+  CU(cudaStreamSynchronize(A->stream));
+  return HSPMV_OK;
+}
+
+} // namespace
+
+// =============================================================================================
+extern "C" {
+
+int hspmv_version(void) { return 100; }
+const char *hspmv_last_error(void) { return g_err.c_str(); }
+
+int hspmv_device_count(int *count) {
+  if (!count) return fail(HSPMV_EINVAL, "null");
+  CU(cudaGetDeviceCount(count));
+  return HSPMV_OK;
+}
+int hspmv_set_device(int device) {
+  CU(cudaSetDevice(device));
+  return HSPMV_OK;
+}
+int hspmv_device_info(int *sm_count, int64_t *l2_bytes, int64_t *hbm_bytes, int *cc) {
+  DeviceProps p;
+  int rc = query_props(p);
+  if (rc) return rc;
+  if (sm_count) *sm_count = p.sms;
+  if (l2_bytes) *l2_bytes = p.l2;
+  if (hbm_bytes) *hbm_bytes = p.hbm;
+  if (cc) *cc = p.cc;
+  return HSPMV_OK;
+}
+int64_t hspmv_launch_count(void) { return g_launches.load(); }
+
+// ---- files ----------------------------------------------------------------------------
+int hspmv_read_csr_text(const char *path, int index_base, int dtype, int64_t *m, int64_t *n,
+                        int64_t *nnz, int32_t **row_ptr, int32_t **col_idx, void **val) {
+  std::string err;
+  int rc = hspmv::read_csr_text(path, index_base, dtype, m, n, nnz, row_ptr, col_idx, val, err);
+  return rc ? fail(rc, err) : rc;
+}
+int hspmv_write_csr_text(const char *path, int index_base, int dtype, int64_t m, int64_t n,
+                         int64_t nnz, const int32_t *row_ptr, const int32_t *col_idx, const void *val) {
+  std::string err;
+  int rc = hspmv::write_csr_text(path, index_base, dtype, m, n, nnz, row_ptr, col_idx, val, err);
+  return rc ? fail(rc, err) : rc;
+}
+int hspmv_read_csr3_text(const char *path, int dtype, int64_t *n_ssr, int64_t *n_sr, int64_t *m,
+                         int64_t *n, int64_t *nnz, uint32_t **ssr_ptr, uint32_t **sr_ptr,
+                         uint32_t **row_ptr, uint32_t **col_idx, void **val) {
+  std::string err;
+  int rc = hspmv::read_csr3_text(path, dtype, n_ssr, n_sr, m, n, nnz, ssr_ptr, sr_ptr, row_ptr, col_idx, val, err);
+  return rc ? fail(rc, err) : rc;
+}
+int hspmv_write_csr3_text(const char *path, int dtype, int64_t n_ssr, int64_t n_sr, int64_t m,
+                          int64_t n, int64_t nnz, const uint32_t *ssr_ptr, const uint32_t *sr_ptr,
+                          const uint32_t *row_ptr, const uint32_t *col_idx, const void *val) {
+  std::string err;
+  int rc = hspmv::write_csr3_text(path, dtype, n_ssr, n_sr, m, n, nnz, ssr_ptr, sr_ptr, row_ptr, col_idx, val, err);
+  return rc ? fail(rc, err) : rc;
+}
+void hspmv_free_host(void *p) { std::free(p); }
+
+// ---- handles --------------------------------------------------------------------------
+int hspmv_create_csr(hspmv_matrix **out, int64_t m, int64_t n, int64_t nnz, const int32_t *row_ptr,
+                     const int32_t *col_idx, const void *val, int dtype, int index_base, int keep_host) {
+  if (!row_ptr || (nnz > 0 && (!col_idx || !val))) return fail(HSPMV_EINVAL, "null CSR array");
+  if ((int64_t)row_ptr[m] - index_base != nnz) return fail(HSPMV_EINVAL, "row_ptr[m] != nnz");
+  hspmv_matrix *A = nullptr;
+  int rc = new_handle(&A, dtype, m, n, nnz);
+  if (rc) return rc;
+  const size_t vs = A->vsize();
+  // host copy (also the place where a 1-based file becomes 0-based)
+  A->h_rp.resize((size_t)m + 1);
+  A->h_ci.resize((size_t)nnz);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i <= m; ++i) A->h_rp[(size_t)i] = row_ptr[i] - index_base;
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < nnz; ++i) A->h_ci[(size_t)i] = col_idx[i] - index_base;
+  for (int64_t i = 0; i < m; ++i)
+    if (A->h_rp[(size_t)i] > A->h_rp[(size_t)i + 1] || A->h_rp[(size_t)i] < 0) {
+      hspmv_destroy(A);
+      return fail(HSPMV_EINVAL, "row_ptr is not monotone");
+    }
+  bool bad_col = false;
+#pragma omp parallel for schedule(static) reduction(|| : bad_col)
+  for (int64_t i = 0; i < nnz; ++i) bad_col = bad_col || A->h_ci[(size_t)i] < 0 || A->h_ci[(size_t)i] >= n;
+  if (bad_col) {
+    hspmv_destroy(A);
+    return fail(HSPMV_EINVAL, "column index out of range (wrong index_base?)");
+  }
+  if ((rc = alloc_matrix_arrays(A)) || (rc = alloc_vectors(A))) {
+    hspmv_destroy(A);
+    return rc;
+  }
+  cudaError_t e = cudaMemcpy(A->d_rp, A->h_rp.data(), (size_t)(m + 1) * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && nnz) e = cudaMemcpy(A->d_ci, A->h_ci.data(), (size_t)nnz * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && nnz) e = cudaMemcpy(A->d_val, val, (size_t)nnz * vs, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    hspmv_destroy(A);
+    return fail(HSPMV_ECUDA, std::string("upload: ") + cudaGetErrorString(e));
+  }
+  if (keep_host) {
+    A->h_val.assign((const unsigned char *)val, (const unsigned char *)val + (size_t)nnz * vs);
+  } else {
+    std::vector<int32_t>().swap(A->h_ci);
+  }
+  hspmv::row_stats(m, A->h_rp.data(), A->stats);
+  A->stats_ready = true;
+  *out = A;
+  return HSPMV_OK;
+}
+
+int hspmv_create_csrk(hspmv_matrix **out, int64_t n_ssr, int64_t n_sr, int64_t m, int64_t n,
+                      int64_t nnz, const uint32_t *ssr_ptr, const uint32_t *sr_ptr,
+                      const uint32_t *row_ptr, const uint32_t *col_idx, const void *val, int dtype) {
+  if (!sr_ptr || n_sr <= 0) return fail(HSPMV_EINVAL, "sr_ptr required");
+  if (sr_ptr[0] != 0 || sr_ptr[n_sr] != (uint32_t)m) return fail(HSPMV_EINVAL, "sr_ptr does not cover the rows");
+  if (ssr_ptr && (ssr_ptr[0] != 0 || ssr_ptr[n_ssr] != (uint32_t)n_sr)) return fail(HSPMV_EINVAL, "ssr_ptr does not cover the super-rows");
+  hspmv_matrix *A = nullptr;
+  int rc = hspmv_create_csr(&A, m, n, nnz, (const int32_t *)row_ptr, (const int32_t *)col_idx, val, dtype, 0, 0);
+  if (rc) return rc;
+  A->k = ssr_ptr ? 3 : 2;
+  A->n_sr = n_sr;
+  A->n_ssr = ssr_ptr ? n_ssr : 0;
+  A->h_sr.assign(sr_ptr, sr_ptr + n_sr + 1);
+  if (ssr_ptr) A->h_ssr.assign(ssr_ptr, ssr_ptr + n_ssr + 1);
+  rc = upload_csrk_maps(A); // no permutation known: x / y are taken in the file's (reordered) order
+  if (rc) {
+    hspmv_destroy(A);
+    return rc;
+  }
+  *out = A;
+  return HSPMV_OK;
+}
+
+int hspmv_create_stencil(hspmv_matrix **out, int kind, int64_t g, int dtype, int mode, int64_t row_lo,
+                         int64_t row_hi, int64_t col_shift, int64_t n_cols) {
+  if ((kind != 27 && kind != 5) || g < 1) return fail(HSPMV_EINVAL, "kind must be 27 or 5");
+  const int64_t n_all = kind == 27 ? g * g * g : g * g;
+  if (row_hi < 0) row_hi = n_all;
+  if (row_lo < 0 || row_lo > row_hi || row_hi > n_all) return fail(HSPMV_EINVAL, "bad row range");
+  if (n_cols <= 0) n_cols = n_all - col_shift;
+  const int64_t before_lo = kind == 27 ? hspmv::stencil27_before(row_lo, g) : hspmv::laplace5_before(row_lo, g);
+  const int64_t before_hi = kind == 27 ? hspmv::stencil27_before(row_hi, g) : hspmv::laplace5_before(row_hi, g);
+  hspmv_matrix *A = nullptr;
+  int rc = new_handle(&A, dtype, row_hi - row_lo, n_cols, before_hi - before_lo);
+  if (rc) return rc;
+  if ((rc = alloc_matrix_arrays(A)) || (rc = alloc_vectors(A))) {
+    hspmv_destroy(A);
+    return rc;
+  }
+  const int grid = grid_for(A->m + 1, 256, A->dev.sms * 16);
+  if (kind == 27) {
+    if (dtype == HSPMV_F64)
+      hspmv::stencil27_kernel<double><<<grid, 256, 0, A->stream>>>(g, row_lo, row_hi, col_shift, mode, A->d_rp, A->d_ci, (double *)A->d_val);
+    else
+      hspmv::stencil27_kernel<float><<<grid, 256, 0, A->stream>>>(g, row_lo, row_hi, col_shift, mode, A->d_rp, A->d_ci, (float *)A->d_val);
+  } else {
+    if (dtype == HSPMV_F64)
+      hspmv::laplace5_kernel<double><<<grid, 256, 0, A->stream>>>(g, row_lo, row_hi, col_shift, mode, A->d_rp, A->d_ci, (double *)A->d_val);
+    else
+      hspmv::laplace5_kernel<float><<<grid, 256, 0, A->stream>>>(g, row_lo, row_hi, col_shift, mode, A->d_rp, A->d_ci, (float *)A->d_val);
+  }
+  LAUNCHED();
+  cudaError_t e = cudaStreamSynchronize(A->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    hspmv_destroy(A);
+    return fail(HSPMV_ECUDA, std::string("stencil generator: ") + cudaGetErrorString(e));
+  }
+  // closed-form statistics (no host copy of row_ptr for the 64 M-row configuration)
+  for (int i = 0; i < 10; ++i) A->stats[i] = 0;
+  A->stats[8] = kind == 27 ? (g >= 3 ? 27 : g == 2 ? 8 : 1) : (g >= 3 ? 5 : g == 2 ? 3 : 1);
+  A->stats[hspmv::bin_of_len(A->stats[8])] = A->m; // every row is within the same vector bin class
+  A->stats_ready = true;
+  *out = A;
+  return HSPMV_OK;
+}
+
+int hspmv_destroy(hspmv_matrix *A) {
+  if (!A) return HSPMV_OK;
+  free_device(A);
+  if (A->stream) cudaStreamDestroy(A->stream);
+  delete A;
+  return HSPMV_OK;
+}
+
+int hspmv_matrix_info(const hspmv_matrix *A, int64_t *m, int64_t *n, int64_t *nnz, int *dtype, int *k,
+                      int64_t *n_sr, int64_t *n_ssr) {
+  if (!A) return fail(HSPMV_EINVAL, "null handle");
+  if (m) *m = A->m;
+  if (n) *n = A->n;
+  if (nnz) *nnz = A->nnz;
+  if (dtype) *dtype = A->dtype;
+  if (k) *k = A->k;
+  if (n_sr) *n_sr = A->n_sr;
+  if (n_ssr) *n_ssr = A->n_ssr;
+  return HSPMV_OK;
+}
+
+int hspmv_download_csr(const hspmv_matrix *A, int32_t *row_ptr, int32_t *col_idx, void *val) {
+  if (!A) return fail(HSPMV_EINVAL, "null handle");
+  if (row_ptr) CU(cudaMemcpy(row_ptr, A->d_rp, (size_t)(A->m + 1) * 4, cudaMemcpyDeviceToHost));
+  if (col_idx && A->nnz) CU(cudaMemcpy(col_idx, A->d_ci, (size_t)A->nnz * 4, cudaMemcpyDeviceToHost));
+  if (val && A->nnz) CU(cudaMemcpy(val, A->d_val, (size_t)A->nnz * A->vsize(), cudaMemcpyDeviceToHost));
+  return HSPMV_OK;
+}
+
+int hspmv_row_stats(const hspmv_matrix *A, int64_t out[10]) {
+  if (!A || !out) return fail(HSPMV_EINVAL, "null");
+  int rc = ensure_stats(const_cast<hspmv_matrix *>(A));
+  if (rc) return rc;
+  for (int i = 0; i < 10; ++i) out[i] = A->stats[i];
+  return HSPMV_OK;
+}
+
+// ---- Band-k -----------------------------------------------------------------------------
+int hspmv_bandk_host(int64_t n, int64_t nnz, const uint32_t *row_ptr, const uint32_t *col_idx, int k,
+                     const int *sup_row_sizes, uint32_t *perm, uint32_t *sr_ptr, int64_t *n_sr,
+                     uint32_t *ssr_ptr, int64_t *n_ssr) {
+  std::vector<u32> p, sr, ssr;
+  int rc = hspmv::bandk_build(n, nnz, row_ptr, col_idx, k, sup_row_sizes, p, sr, ssr);
+  if (rc) return fail(rc, rc == HSPMV_EUNSUPPORTED
+                              ? "Band-k: a coarse vertex has no upper/diagonal entry (matrix must be structurally symmetric with a stored diagonal)"
+                              : "Band-k: bad arguments");
+  if (perm) std::memcpy(perm, p.data(), p.size() * 4);
+  if (sr_ptr) std::memcpy(sr_ptr, sr.data(), sr.size() * 4);
+  if (n_sr) *n_sr = (int64_t)sr.size() - 1;
+  if (k == 3 && ssr_ptr) std::memcpy(ssr_ptr, ssr.data(), ssr.size() * 4);
+  if (n_ssr) *n_ssr = k == 3 ? (int64_t)ssr.size() - 1 : 0;
+  return HSPMV_OK;
+}
+
+int hspmv_reorder_host(int64_t n, int64_t nnz, const uint32_t *perm, const uint32_t *row_ptr,
+                       const uint32_t *col_idx, const void *val, int dtype, uint32_t *row_ptr_out,
+                       uint32_t *col_idx_out, void *val_out) {
+  (void)nnz;
+  if (!perm || !row_ptr || !col_idx || !val || !row_ptr_out || !col_idx_out || !val_out)
+    return fail(HSPMV_EINVAL, "null");
+  if (dtype == HSPMV_F64)
+    hspmv::reorder_f64(n, perm, row_ptr, col_idx, (const double *)val, row_ptr_out, col_idx_out, (double *)val_out);
+  else
+    hspmv::reorder_f32(n, perm, row_ptr, col_idx, (const float *)val, row_ptr_out, col_idx_out, (float *)val_out);
+  return HSPMV_OK;
+}
+
+int hspmv_build_csrk(hspmv_matrix *A, int k, const int *sup_row_sizes) {
+  if (!A) return fail(HSPMV_EINVAL, "null handle");
+  if (A->m != A->n) return fail(HSPMV_EINVAL, "Band-k needs a square matrix");
+  if (A->k != 1) return fail(HSPMV_ESTATE, "matrix is already in CSR-k form");
+  const size_t vs = A->vsize();
+  // host copy of the CSR arrays: kept at creation, or fetched back from HBM
+  if (A->h_rp.empty()) {
+    A->h_rp.resize((size_t)A->m + 1);
+    CU(cudaMemcpy(A->h_rp.data(), A->d_rp, (size_t)(A->m + 1) * 4, cudaMemcpyDeviceToHost));
+  }
+  if (A->h_ci.size() != (size_t)A->nnz) {
+    A->h_ci.resize((size_t)A->nnz);
+    if (A->nnz) CU(cudaMemcpy(A->h_ci.data(), A->d_ci, (size_t)A->nnz * 4, cudaMemcpyDeviceToHost));
+  }
+  if (A->h_val.size() != (size_t)A->nnz * vs) {
+    A->h_val.resize((size_t)A->nnz * vs);
+    if (A->nnz) CU(cudaMemcpy(A->h_val.data(), A->d_val, (size_t)A->nnz * vs, cudaMemcpyDeviceToHost));
+  }
+  std::vector<u32> perm, sr, ssr;
+  int rc = hspmv::bandk_build(A->m, A->nnz, (const u32 *)A->h_rp.data(), (const u32 *)A->h_ci.data(), k,
+                              sup_row_sizes, perm, sr, ssr);
+  if (rc) return fail(rc, rc == HSPMV_EUNSUPPORTED
+                              ? "Band-k: a coarse vertex has no upper/diagonal entry (matrix must be structurally symmetric with a stored diagonal)"
+                              : "Band-k: bad arguments (k must be 2 or 3)");
+  if (sr.back() != (u32)A->m) return fail(HSPMV_EUNSUPPORTED, "Band-k: trailing empty rows are not covered by a super-row");
+  // A' = P A P^T on the host, then one upload of the REORDERED arrays
+  std::vector<int32_t> rp2((size_t)A->m + 1), ci2((size_t)A->nnz);
+  std::vector<unsigned char> val2((size_t)A->nnz * vs);
+  if (A->dtype == HSPMV_F64)
+    hspmv::reorder_f64(A->m, perm.data(), (const u32 *)A->h_rp.data(), (const u32 *)A->h_ci.data(),
+                       (const double *)A->h_val.data(), (u32 *)rp2.data(), (u32 *)ci2.data(), (double *)val2.data());
+  else
+    hspmv::reorder_f32(A->m, perm.data(), (const u32 *)A->h_rp.data(), (const u32 *)A->h_ci.data(),
+                       (const float *)A->h_val.data(), (u32 *)rp2.data(), (u32 *)ci2.data(), (float *)val2.data());
+  A->h_rp.swap(rp2);
+  A->h_ci.swap(ci2);
+  A->h_val.swap(val2);
+  CU(cudaMemcpy(A->d_rp, A->h_rp.data(), (size_t)(A->m + 1) * 4, cudaMemcpyHostToDevice));
+  if (A->nnz) {
+    CU(cudaMemcpy(A->d_ci, A->h_ci.data(), (size_t)A->nnz * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(A->d_val, A->h_val.data(), (size_t)A->nnz * vs, cudaMemcpyHostToDevice));
+  }
+  A->k = k;
+  A->h_perm.swap(perm);
+  A->h_sr.swap(sr);
+  A->h_ssr.swap(ssr);
+  A->n_sr = (int64_t)A->h_sr.size() - 1;
+  A->n_ssr = k == 3 ? (int64_t)A->h_ssr.size() - 1 : 0;
+  A->bins_ready = false;
+  A->merge_tile = 0;
+  hspmv::row_stats(A->m, A->h_rp.data(), A->stats);
+  return upload_csrk_maps(A);
+}
+
+int hspmv_csrk_get(const hspmv_matrix *A, uint32_t *perm, uint32_t *sr_ptr, uint32_t *ssr_ptr) {
+  if (!A) return fail(HSPMV_EINVAL, "null handle");
+  if (A->k < 2) return fail(HSPMV_ESTATE, "not in CSR-k form");
+  if (perm) {
+    if (A->h_perm.empty()) return fail(HSPMV_ESTATE, "no permutation (matrix came from a .csr3 file)");
+    std::memcpy(perm, A->h_perm.data(), A->h_perm.size() * 4);
+  }
+  if (sr_ptr) std::memcpy(sr_ptr, A->h_sr.data(), A->h_sr.size() * 4);
+  if (ssr_ptr && A->k == 3) std::memcpy(ssr_ptr, A->h_ssr.data(), A->h_ssr.size() * 4);
+  return HSPMV_OK;
+}
+
+int hspmv_auto_params(int64_t nnz, int64_t n_rows, int arch, int sizes[2], int *veclevel, int *block_dim_y) {
+  int rc = hspmv::auto_params(nnz, n_rows, arch, sizes, veclevel, block_dim_y);
+  return rc ? fail(rc, "auto_params: bad arguments") : rc;
+}
+
+// ---- vectors ----------------------------------------------------------------------------
+int hspmv_set_x(hspmv_matrix *A, const void *x_host) {
+  if (!A || !x_host) return fail(HSPMV_EINVAL, "null");
+  const size_t vs = A->vsize();
+  if (A->d_perm) {
+    CU(cudaMemcpyAsync(A->d_tmp, x_host, (size_t)A->n * vs, cudaMemcpyHostToDevice, A->stream));
+    const int grid = grid_for(A->n, 256, A->dev.sms * 16);
+    if (A->dtype == HSPMV_F64)
+      hspmv::gather_kernel<double><<<grid, 256, 0, A->stream>>>(A->n, A->d_perm, (const double *)A->d_tmp, (double *)A->d_x);
+    else
+      hspmv::gather_kernel<float><<<grid, 256, 0, A->stream>>>(A->n, A->d_perm, (const float *)A->d_tmp, (float *)A->d_x);
+    LAUNCHED();
+  } else {
+    CU(cudaMemcpyAsync(A->d_x, x_host, (size_t)A->n * vs, cudaMemcpyHostToDevice, A->stream));
+  }
+  CU(cudaStreamSynchronize(A->stream));
+  return HSPMV_OK;
+}
+
+int hspmv_get_y(hspmv_matrix *A, void *y_host, int original_order) {
+  if (!A || !y_host) return fail(HSPMV_EINVAL, "null");
+  const size_t vs = A->vsize();
+  if (original_order && A->d_perm) {
+    const int grid = grid_for(A->m, 256, A->dev.sms * 16);
+    if (A->dtype == HSPMV_F64)
+      hspmv::scatter_kernel<double><<<grid, 256, 0, A->stream>>>(A->m, A->d_perm, (const double *)A->d_y, (double *)A->d_tmp);
+    else
+      hspmv::scatter_kernel<float><<<grid, 256, 0, A->stream>>>(A->m, A->d_perm, (const float *)A->d_y, (float *)A->d_tmp);
+    LAUNCHED();
+    CU(cudaMemcpyAsync(y_host, A->d_tmp, (size_t)A->m * vs, cudaMemcpyDeviceToHost, A->stream));
+  } else {
+    CU(cudaMemcpyAsync(y_host, A->d_y, (size_t)A->m * vs, cudaMemcpyDeviceToHost, A->stream));
+  }
+  CU(cudaStreamSynchronize(A->stream));
+  return HSPMV_OK;
+}
+
+void *hspmv_x_device(hspmv_matrix *A) { return A ? A->d_x : nullptr; }
+void *hspmv_y_device(hspmv_matrix *A) { return A ? A->d_y : nullptr; }
+
+int hspmv_fill_x_synthetic(hspmv_matrix *A, int64_t global_offset) {
+  if (!A) return fail(HSPMV_EINVAL, "null handle");
+  const int grid = grid_for(A->n, 256, A->dev.sms * 16);
+  if (A->dtype == HSPMV_F64)
+    hspmv::vector_x_kernel<double><<<grid, 256, 0, A->stream>>>(A->n, global_offset, (double *)A->d_x);
+  else
+    hspmv::vector_x_kernel<float><<<grid, 256, 0, A->stream>>>(A->n, global_offset, (float *)A->d_x);
+  LAUNCHED();
+  CU(cudaStreamSynchronize(A->stream));
+  return HSPMV_OK;
+}
+
+// ---- hot path ---------------------------------------------------------------------------
+int hspmv_set_option(hspmv_matrix *A, int option, int64_t value) {
+  if (!A || option < 1 || option > 15) return fail(HSPMV_EINVAL, "bad option");
+  if (option == HSPMV_OPT_VEC && value != 0 && (value < 1 || value > 32 || (value & (value - 1))))
+    return fail(HSPMV_EINVAL, "HSPMV_OPT_VEC must be 0 or a power of two <= 32");
+  A->opt[option] = value;
+  return HSPMV_OK;
+}
+
+int hspmv_spmv(hspmv_matrix *A, int algo, const void *d_x, void *d_y, void *stream) {
+  if (!A) return fail(HSPMV_EINVAL, "null handle");
+  return do_spmv(A, algo, d_x, d_y, (cudaStream_t)stream);
+}
+
+int hspmv_spmv_timed(hspmv_matrix *A, int algo, int warmup, int iters, int flush_l2, float *ms_out) {
+  if (!A || iters < 1 || !ms_out) return fail(HSPMV_EINVAL, "bad arguments");
+  if (flush_l2 && !A->d_flush) {
+    A->flush_bytes = (size_t)A->dev.l2 * 2;
+    CU(cudaMalloc(&A->d_flush, A->flush_bytes));
+  }
+  for (int i = 0; i < warmup; ++i) {
+    int rc = do_spmv(A, algo, nullptr, nullptr, A->stream);
+    if (rc) return rc;
+  }
+  std::vector<cudaEvent_t> ev((size_t)iters * 2);
+  for (auto &e : ev) CU(cudaEventCreate(&e));
+  for (int i = 0; i < iters; ++i) {
+    if (flush_l2) CU(cudaMemsetAsync(A->d_flush, i & 0xff, A->flush_bytes, A->stream));
+    CU(cudaEventRecord(ev[(size_t)2 * i], A->stream));
+    int rc = do_spmv(A, algo, nullptr, nullptr, A->stream);
+    if (rc) return rc;
+    CU(cudaEventRecord(ev[(size_t)2 * i + 1], A->stream));
+  }
+  CU(cudaStreamSynchronize(A->stream));
+  for (int i = 0; i < iters; ++i) CU(cudaEventElapsedTime(&ms_out[i], ev[(size_t)2 * i], ev[(size_t)2 * i + 1]));
+  for (auto &e : ev) cudaEventDestroy(e);
+  return HSPMV_OK;
+}
+
+int hspmv_spmv_host(hspmv_matrix *A, int algo, const void *x_host, void *y_host) {
+  int rc = hspmv_set_x(A, x_host);
+  if (rc) return rc;
+  rc = do_spmv(A, algo, nullptr, nullptr, A->stream);
+  if (rc) return rc;
+  return hspmv_get_y(A, y_host, 1);
+}
+
+const char *hspmv_last_kernel(const hspmv_matrix *A) { return A ? A->last_kernel.c_str() : ""; }
+
+// ---- spmv.h compatibility ------------------------------------------------------------------
+namespace {
+typedef std::tuple<const void *, const void *, const void *, int, int, int> CacheKey;
+std::map<CacheKey, hspmv_matrix *> g_cache;
+std::mutex g_cache_mu;
+
+int compat_spmv(int dtype, int m, int n, int nnz, const int *rs, const int *ci, const void *val,
+                const void *x, void *y) {
+  std::lock_guard<std::mutex> lock(g_cache_mu);
+  CacheKey key(rs, ci, val, m, nnz, dtype);
+  hspmv_matrix *A = nullptr;
+  auto it = g_cache.find(key);
+  if (it == g_cache.end()) {
+    // the reference's omp_spmv indexes x with column ids < m for its square inputs; n is unused there
+    int rc = hspmv_create_csr(&A, m, n > 0 ? n : m, nnz, rs, ci, val, dtype, 0, 0);
+    if (rc) return rc;
+    g_cache[key] = A;
+  } else {
+    A = it->second;
+  }
+  return hspmv_spmv_host(A, HSPMV_ALGO_AUTO, x, y);
+}
+} // namespace
+
+int hspmv_omp_spmv_f64(int m, int n, int nnz, const int *row_start, const int *col_idx, const double *val,
+                       const double *x, double *y) {
+  return compat_spmv(HSPMV_F64, m, n, nnz, row_start, col_idx, val, x, y);
+}
+int hspmv_omp_spmv_f32(int m, int n, int nnz, const int *row_start, const int *col_idx, const float *val,
+                       const float *x, float *y) {
+  return compat_spmv(HSPMV_F32, m, n, nnz, row_start, col_idx, val, x, y);
+}
+void hspmv_omp_spmv_cache_clear(void) {
+  std::lock_guard<std::mutex> lock(g_cache_mu);
+  for (auto &kv : g_cache) hspmv_destroy(kv.second);
+  g_cache.clear();
+}
+
+// ---- multi-GPU index work ----------------------------------------------------------------
+int hspmv_partition_rows(int64_t m, const int32_t *row_ptr, int n_parts, const uint32_t *align_ptr,
+                         int64_t n_align, int64_t *row_lo) {
+  int rc = hspmv::partition_rows(m, row_ptr, n_parts, align_ptr, n_align, row_lo);
+  return rc ? fail(rc, "partition_rows: bad arguments") : rc;
+}
+int hspmv_block_col_range(const int32_t *row_ptr, const int32_t *col_idx, int64_t row_lo, int64_t row_hi,
+                          int64_t *col_min, int64_t *col_max) {
+  int rc = hspmv::block_col_range(row_ptr, col_idx, row_lo, row_hi, col_min, col_max);
+  return rc ? fail(rc, "block_col_range: bad arguments") : rc;
+}
+int hspmv_col_range_device(const hspmv_matrix *A, int64_t *col_min, int64_t *col_max) {
+  if (!A || !col_min || !col_max) return fail(HSPMV_EINVAL, "null");
+  int *d = nullptr;
+  CU(cudaMalloc(&d, 8));
+  int init[2] = {INT32_MAX, -1};
+  CU(cudaMemcpy(d, init, 8, cudaMemcpyHostToDevice));
+  if (A->nnz) {
+    hspmv::col_minmax_kernel<<<grid_for(A->nnz, 256, A->dev.sms * 16), 256, 0, A->stream>>>(A->nnz, A->d_ci, d, d + 1);
+    LAUNCHED();
+  }
+  int res[2];
+  CU(cudaStreamSynchronize(A->stream));
+  CU(cudaMemcpy(res, d, 8, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  *col_min = A->nnz ? res[0] : 0;
+  *col_max = A->nnz ? res[1] : -1;
+  return HSPMV_OK;
+}
+
+// tile table of the CSR_MERGE path, host restatement (for the bit-exactness tests)
+int hspmv_merge_tile_rows_host(int64_t m, const int32_t *row_ptr, int64_t tile, int32_t *tile_row) {
+  if (!row_ptr || !tile_row || tile <= 0) return fail(HSPMV_EINVAL, "bad arguments");
+  std::vector<int32_t> t;
+  hspmv::tile_rows(m, row_ptr, tile, t);
+  std::memcpy(tile_row, t.data(), t.size() * 4);
+  return HSPMV_OK;
+}
+// device tile table of a handle (after a CSR_MERGE launch), copied back for diffing
+int hspmv_merge_tile_rows_device(const hspmv_matrix *A, int64_t *tile, int64_t *n_tiles, int32_t *tile_row) {
+  if (!A || !A->d_tile_row) return fail(HSPMV_ESTATE, "no CSR_MERGE launch on this handle yet");
+  if (tile) *tile = A->merge_tile;
+  if (n_tiles) *n_tiles = A->merge_tiles;
+  if (tile_row) CU(cudaMemcpy(tile_row, A->d_tile_row, (size_t)(A->merge_tiles + 1) * 4, cudaMemcpyDeviceToHost));
+  return HSPMV_OK;
+}
+// row bins of the CSR_VECTOR path, host (for the bit-exactness tests): rows[m], bin_ptr[9]
+int hspmv_bin_rows_host(int64_t m, const int32_t *row_ptr, int32_t *rows, int64_t *bin_ptr) {
+  if (!row_ptr || !rows || !bin_ptr) return fail(HSPMV_EINVAL, "null");
+  std::vector<int32_t> r;
+  int64_t bp[hspmv::NUM_BINS + 1];
+  hspmv::bin_rows(m, row_ptr, r, bp);
+  if (m) std::memcpy(rows, r.data(), (size_t)m * 4);
+  std::memcpy(bin_ptr, bp, sizeof(bp));
+  return HSPMV_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,394 @@
+// Band-k / CSR-k builder (host side of hspmv_build_csrk, hspmv_bandk_host, hspmv_reorder_host).
+//
+// Produces, bit for bit, the index structures of the reference's HAND-coarsening path:
+//   BAND_k::preprocessingForSpMV  spmv-csrk/csrk.cpp:841-1067
+//   BAND_k::handCoarsen           :1243-1437      BAND_k::uncoarsenTheGraph :1148-1224
+//   rcm_reordering_g              :2289-2374      findPseudoPeripheralVertex :2377-2421
+//   findRootedLevelStructures     :2426-2475      renumberGraphUsingReorderedVertices :3012-3115
+//   CSRk_Graph::reorderA          :548-676
+// but is organised differently so that it scales to the 1.7 G-nnz configuration:
+//   * the coarse graph is assembled without the reference's 2*nnz-entry scratch list and its
+//     serial dedup: each coarse vertex's UPPER neighbours (same or later group) are collected,
+//     sorted and run-length encoded in parallel, and the lower half is obtained by transposing
+//     the strict upper half (the reference inserts the mirrored entry explicitly at
+//     csrk.cpp:1350-1354; after its per-vertex sort the two constructions are identical:
+//     entries < v come only from mirrors, entries >= v only from v's own rows);
+//   * BFS bookkeeping uses epoch stamps instead of clearing and restoring a mask;
+//   * reorderA sorts each row in a per-thread scratch buffer instead of an nnz-sized pair array.
+// The one place where the result depends on library behaviour -- the order in which
+// std::sort leaves equal-multiplicity neighbours (csrk.cpp:2345-2346, comparator :65-67) -- is
+// reproduced by calling std::sort on the same {deg,id} element layout with the same predicate.
+#include "host_index.h"
+
+#include <algorithm>
+#include <cstring>
+#include <utility>
+#include <vector>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace hspmv {
+
+namespace {
+
+struct Coarse {
+  int64_t n = 0;
+  std::vector<u32> rp, adj, mult;
+};
+
+// Greedy contiguous grouping (csrk.cpp:1278-1292): a group is closed by the vertex that makes
+// the running nnz reach the threshold; the next vertex opens a new group.
+void group_rows(const u32 *rp, int64_t n, u32 T, std::vector<u32> &start, std::vector<u32> &grp) {
+  grp.resize((size_t)n);
+  start.clear();
+  start.push_back(0);
+  u32 acc = 0, g = 0;
+  for (int64_t v = 0; v < n; ++v) {
+    const u32 len = rp[v + 1] - rp[v];
+    if (acc < T) {
+      acc += len;
+    } else {
+      ++g;
+      acc = len;
+      start.push_back((u32)v);
+    }
+    grp[(size_t)v] = g;
+  }
+  if (acc > 0) start.push_back((u32)n);
+}
+
+int build_coarse(const u32 *rp, const u32 *adj, const std::vector<u32> &start,
+                 const std::vector<u32> &grp, Coarse &out) {
+  const int64_t nc = (int64_t)start.size() - 1;
+  out.n = nc;
+  std::vector<u32> up_cnt((size_t)nc + 1, 0);
+  int nthreads = 1;
+#ifdef _OPENMP
+  nthreads = omp_get_max_threads();
+#endif
+  std::vector<std::vector<u32>> buf_adj((size_t)nthreads), buf_mult((size_t)nthreads);
+  std::vector<int64_t> first_cv((size_t)nthreads + 1, nc);
+
+#pragma omp parallel num_threads(nthreads)
+  {
+    int tid = 0, nt = 1;
+#ifdef _OPENMP
+    tid = omp_get_thread_num();
+    nt = omp_get_num_threads();
+#endif
+    const int64_t lo = nc * tid / nt, hi = nc * (tid + 1) / nt;
+    first_cv[(size_t)tid] = lo;
+    std::vector<u32> scratch;
+    std::vector<u32> &oa = buf_adj[(size_t)tid], &om = buf_mult[(size_t)tid];
+    for (int64_t cv = lo; cv < hi; ++cv) {
+      scratch.clear();
+      const u32 gs = start[(size_t)cv];
+      for (u32 u = gs; u < start[(size_t)cv + 1]; ++u)
+        for (u32 j = rp[u]; j < rp[u + 1]; ++j)
+          if (adj[j] >= gs) scratch.push_back(grp[adj[j]]);
+      std::sort(scratch.begin(), scratch.end());
+      u32 distinct = 0;
+      for (size_t i = 0; i < scratch.size();) {
+        size_t j = i + 1;
+        while (j < scratch.size() && scratch[j] == scratch[i]) ++j;
+        oa.push_back(scratch[i]);
+        om.push_back((u32)(j - i));
+        ++distinct;
+        i = j;
+      }
+      up_cnt[(size_t)cv] = distinct;
+    }
+  }
+
+  // stitch the per-thread upper lists into one CSR (threads own contiguous vertex ranges)
+  std::vector<u32> up_rp((size_t)nc + 1, 0);
+  for (int64_t v = 0; v < nc; ++v) up_rp[(size_t)v + 1] = up_rp[(size_t)v] + up_cnt[(size_t)v];
+  std::vector<u32> up_adj(up_rp[(size_t)nc]), up_mult(up_rp[(size_t)nc]);
+  for (int t = 0; t < nthreads; ++t) {
+    if (buf_adj[(size_t)t].empty()) continue;
+    const u32 dst = up_rp[(size_t)first_cv[(size_t)t]];
+    std::memcpy(&up_adj[dst], buf_adj[(size_t)t].data(), buf_adj[(size_t)t].size() * sizeof(u32));
+    std::memcpy(&up_mult[dst], buf_mult[(size_t)t].data(), buf_mult[(size_t)t].size() * sizeof(u32));
+    std::vector<u32>().swap(buf_adj[(size_t)t]);
+    std::vector<u32>().swap(buf_mult[(size_t)t]);
+  }
+
+  // transpose of the strict upper part = lower part; filling in increasing source order
+  // leaves every lower list sorted ascending
+  std::vector<u32> low_cnt((size_t)nc + 1, 0);
+  for (int64_t v = 0; v < nc; ++v)
+    for (u32 e = up_rp[(size_t)v]; e < up_rp[(size_t)v + 1]; ++e)
+      if (up_adj[e] != (u32)v) ++low_cnt[up_adj[e]];
+
+  out.rp.assign((size_t)nc + 1, 0);
+  for (int64_t v = 0; v < nc; ++v) {
+    const u32 tot = low_cnt[(size_t)v] + up_cnt[(size_t)v];
+    if (tot == 0) return HSPMV_EUNSUPPORTED; // reference reads out of bounds here (Q8)
+    out.rp[(size_t)v + 1] = out.rp[(size_t)v] + tot;
+  }
+  out.adj.resize(out.rp[(size_t)nc]);
+  out.mult.resize(out.rp[(size_t)nc]);
+  std::vector<u32> cursor(out.rp.begin(), out.rp.end() - 1);
+  for (int64_t v = 0; v < nc; ++v)
+    for (u32 e = up_rp[(size_t)v]; e < up_rp[(size_t)v + 1]; ++e) {
+      const u32 t = up_adj[e];
+      if (t != (u32)v) {
+        out.adj[cursor[t]] = (u32)v;
+        out.mult[cursor[t]] = up_mult[e];
+        ++cursor[t];
+      }
+    }
+  for (int64_t v = 0; v < nc; ++v) {
+    const u32 n_up = up_cnt[(size_t)v];
+    std::memcpy(&out.adj[cursor[(size_t)v]], &up_adj[up_rp[(size_t)v]], n_up * sizeof(u32));
+    std::memcpy(&out.mult[cursor[(size_t)v]], &up_mult[up_rp[(size_t)v]], n_up * sizeof(u32));
+  }
+  return HSPMV_OK;
+}
+
+// ---- RCM on the coarse graph ---------------------------------------------------------
+struct Rcm {
+  const Coarse &g;
+  std::vector<unsigned char> open; // 1 = not yet numbered ("mask" in the reference)
+  std::vector<u32> stamp;          // BFS visit epoch
+  u32 epoch = 0;
+  std::vector<int> order, lvl_ptr;
+
+  explicit Rcm(const Coarse &gr) : g(gr), open((size_t)gr.n, 1), stamp((size_t)gr.n, 0) {}
+
+  // rooted level structure over the open vertices (csrk.cpp:2426-2475)
+  int levels_from(int root) {
+    ++epoch;
+    order.clear();
+    lvl_ptr.clear();
+    order.push_back(root);
+    stamp[(size_t)root] = epoch;
+    size_t begin = 0, end = 0;
+    int levels = 0;
+    for (;;) {
+      begin = end;
+      lvl_ptr.push_back((int)begin);
+      end = order.size();
+      for (size_t i = begin; i < end; ++i) {
+        const int v = order[i];
+        for (u32 e = g.rp[(size_t)v]; e < g.rp[(size_t)v + 1]; ++e) {
+          const u32 w = g.adj[e];
+          if (open[w] && stamp[w] != epoch) {
+            stamp[w] = epoch;
+            order.push_back((int)w);
+          }
+        }
+      }
+      ++levels;
+      if (order.size() == end) break;
+    }
+    lvl_ptr.push_back((int)end);
+    return levels;
+  }
+
+  // George-Liu pseudo-peripheral vertex (csrk.cpp:2377-2421)
+  int peripheral(int root) {
+    int levels = levels_from(root);
+    const int cc = lvl_ptr[(size_t)levels];
+    if (levels == 1 || levels == cc) return root;
+    for (;;) {
+      const int j1 = lvl_ptr[(size_t)levels - 1];
+      int best = cc;
+      root = order[(size_t)j1];
+      for (int j = j1; j < cc; ++j) {
+        const int v = order[(size_t)j];
+        int d = 0;
+        for (u32 e = g.rp[(size_t)v]; e < g.rp[(size_t)v + 1]; ++e) d += open[g.adj[e]] ? 1 : 0;
+        if (d < best) {
+          best = d;
+          root = v;
+        }
+      }
+      const int nl = levels_from(root);
+      if (nl <= levels || levels >= cc) return root;
+      levels = nl;
+    }
+  }
+};
+
+struct DegId { // layout of rev_deg_id_pair, csrk.h:477-490
+  unsigned deg;
+  unsigned id;
+};
+inline bool heavier_first(DegId a, DegId b) { return a.deg > b.deg; } // csrk.cpp:65-67
+
+void rcm_order(const Coarse &g, std::vector<u32> &new2old, std::vector<u32> &old2new) {
+  Rcm s(g);
+  new2old.assign((size_t)g.n, 0);
+  old2new.assign((size_t)g.n, 0);
+  std::vector<int> queue;
+  std::vector<DegId> cand;
+  int64_t done = 0;
+  for (int64_t seed = 0; seed < g.n && done < g.n; ++seed) {
+    if (!s.open[(size_t)seed]) continue;
+    const int root = s.peripheral((int)seed);
+    queue.clear();
+    queue.push_back(root);
+    const int64_t first = done;
+    for (size_t head = 0; head < queue.size(); ++head) {
+      const int p = queue[head];
+      if (!s.open[(size_t)p]) continue; // vertices are marked at dequeue, so duplicates occur
+      s.open[(size_t)p] = 0;
+      new2old[(size_t)done++] = (u32)p;
+      cand.clear();
+      for (u32 e = g.rp[(size_t)p]; e < g.rp[(size_t)p + 1]; ++e)
+        if (s.open[g.adj[e]]) {
+          DegId d;
+          d.deg = g.mult[e];
+          d.id = g.adj[e];
+          cand.push_back(d);
+        }
+      std::sort(cand.begin(), cand.end(), heavier_first);
+      for (size_t i = 0; i < cand.size(); ++i) queue.push_back((int)cand[i].id);
+    }
+    std::reverse(new2old.begin() + first, new2old.begin() + done);
+    for (int64_t i = first; i < done; ++i) old2new[new2old[(size_t)i]] = (u32)i;
+  }
+}
+
+// relabel + sort adjacency by new id (csrk.cpp:3012-3115)
+void relabel(Coarse &g, const std::vector<u32> &new2old, const std::vector<u32> &old2new) {
+  Coarse src;
+  src.rp.swap(g.rp);
+  src.adj.swap(g.adj);
+  src.mult.swap(g.mult);
+  g.rp.assign((size_t)g.n + 1, 0);
+  for (int64_t i = 0; i < g.n; ++i) {
+    const u32 o = new2old[(size_t)i];
+    g.rp[(size_t)i + 1] = g.rp[(size_t)i] + (src.rp[o + 1] - src.rp[o]);
+  }
+  g.adj.resize(src.adj.size());
+  g.mult.resize(src.mult.size());
+#pragma omp parallel
+  {
+    std::vector<std::pair<u32, u32>> row;
+#pragma omp for schedule(static)
+    for (int64_t i = 0; i < g.n; ++i) {
+      const u32 o = new2old[(size_t)i];
+      row.clear();
+      for (u32 e = src.rp[o]; e < src.rp[o + 1]; ++e)
+        row.push_back(std::make_pair(old2new[src.adj[e]], src.mult[e]));
+      std::sort(row.begin(), row.end()); // ids are distinct after dedup
+      for (size_t t = 0; t < row.size(); ++t) {
+        g.adj[g.rp[(size_t)i] + t] = row[t].first;
+        g.mult[g.rp[(size_t)i] + t] = row[t].second;
+      }
+    }
+  }
+}
+
+// csrk.cpp:1148-1224: group starts rewritten in permuted order; finer permutation composed
+void expand_level(std::vector<u32> &map, const std::vector<u32> &perm_coarse,
+                  std::vector<u32> &perm_fine) {
+  const size_t nc = perm_coarse.size();
+  std::vector<u32> new_map(nc + 1, 0), composed(perm_fine.size());
+  for (size_t j = 0; j < nc; ++j) {
+    const u32 o = perm_coarse[j];
+    new_map[j + 1] = new_map[j] + (map[o + 1] - map[o]);
+  }
+#pragma omp parallel for schedule(static)
+  for (int64_t j = 0; j < (int64_t)nc; ++j) {
+    const u32 o = perm_coarse[(size_t)j];
+    u32 dst = new_map[(size_t)j];
+    for (u32 t = map[o]; t < map[o + 1]; ++t) composed[dst++] = perm_fine[t];
+  }
+  map.swap(new_map);
+  perm_fine.swap(composed);
+}
+
+} // namespace
+
+int bandk_build(int64_t n, int64_t nnz, const u32 *rp, const u32 *adj, int k, const int *sizes,
+                std::vector<u32> &perm, std::vector<u32> &sr_ptr, std::vector<u32> &ssr_ptr) {
+  if (k < 2 || k > 3 || n <= 0 || !rp || !adj || !sizes) return HSPMV_EINVAL;
+  if (rp[n] != (u32)nnz) return HSPMV_EINVAL;
+
+  std::vector<std::vector<u32>> perms((size_t)k), maps((size_t)k);
+  Coarse level[3];
+
+  const u32 *cur_rp = rp, *cur_adj = adj;
+  int64_t cur_n = n, cur_nnz = nnz;
+  for (int lvl = 1; lvl < k; ++lvl) {
+    // csrk.cpp:896-897: unsigned * long / long, truncated to int, compared as unsigned
+    const int T = (int)((long)(unsigned)sizes[lvl - 1] * (long)cur_nnz / (long)cur_n);
+    std::vector<u32> grp;
+    group_rows(cur_rp, cur_n, (u32)T, maps[(size_t)lvl], grp);
+    int rc = build_coarse(cur_rp, cur_adj, maps[(size_t)lvl], grp, level[lvl]);
+    if (rc) return rc;
+    std::vector<u32> o2n;
+    rcm_order(level[lvl], perms[(size_t)lvl], o2n);
+    if (lvl + 1 < k) { // the next level coarsens the renumbered graph
+      relabel(level[lvl], perms[(size_t)lvl], o2n);
+      cur_rp = level[lvl].rp.data();
+      cur_adj = level[lvl].adj.data();
+      cur_n = level[lvl].n;
+      cur_nnz = (int64_t)level[lvl].adj.size();
+    }
+  }
+
+  // level-(k-1) ... level-1: rewrite the maps, compose down to rows (csrk.cpp:1015-1034)
+  if (k == 3) expand_level(maps[2], perms[2], perms[1]);
+  perms[0].resize((size_t)n);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) perms[0][(size_t)i] = (u32)i;
+  expand_level(maps[1], perms[1], perms[0]);
+
+  perm.swap(perms[0]);
+  sr_ptr.swap(maps[1]);
+  if (k == 3)
+    ssr_ptr.swap(maps[2]);
+  else
+    ssr_ptr.clear();
+  return HSPMV_OK;
+}
+
+template <typename T>
+static void reorder_impl(int64_t n, const u32 *perm, const u32 *rp, const u32 *ci, const T *v,
+                         u32 *rp2, u32 *ci2, T *v2) {
+  std::vector<u32> fwd((size_t)n);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) fwd[perm[i]] = (u32)i;
+  rp2[0] = 0;
+  for (int64_t i = 0; i < n; ++i) rp2[i + 1] = rp2[i] + (rp[perm[i] + 1] - rp[perm[i]]);
+#pragma omp parallel
+  {
+    std::vector<std::pair<u32, u32>> row; // (new column, old position)
+#pragma omp for schedule(dynamic, 1024)
+    for (int64_t i = 0; i < n; ++i) {
+      const u32 o = perm[i];
+      const u32 len = rp[o + 1] - rp[o];
+      row.resize(len);
+      bool sorted = true;
+      for (u32 t = 0; t < len; ++t) {
+        row[t].first = fwd[ci[rp[o] + t]];
+        row[t].second = rp[o] + t;
+        if (t && row[t].first < row[t - 1].first) sorted = false;
+      }
+      if (!sorted) // columns of a row are unique, so any sort gives the reference's order
+        std::sort(row.begin(), row.end());
+      const u32 dst = rp2[i];
+      for (u32 t = 0; t < len; ++t) {
+        ci2[dst + t] = row[t].first;
+        v2[dst + t] = v[row[t].second];
+      }
+    }
+  }
+}
+
+void reorder_f32(int64_t n, const u32 *perm, const u32 *rp, const u32 *ci, const float *v,
+                 u32 *rp2, u32 *ci2, float *v2) {
+  reorder_impl<float>(n, perm, rp, ci, v, rp2, ci2, v2);
+}
+void reorder_f64(int64_t n, const u32 *perm, const u32 *rp, const u32 *ci, const double *v,
+                 u32 *rp2, u32 *ci2, double *v2) {
+  reorder_impl<double>(n, perm, rp, ci, v, rp2, ci2, v2);
+}
+
+} // namespace hspmv

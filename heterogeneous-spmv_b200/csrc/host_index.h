@@ -1,0 +1,63 @@
+// Host-side index work shared by the C ABI (abi.cu) and the converters: Band-k builder,
+// text I/O, partitioning, binning, size heuristics.  No CUDA in here.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/hspmv.h"
+
+namespace hspmv {
+
+typedef uint32_t u32;
+
+// ---- bandk.cpp
+int bandk_build(int64_t n, int64_t nnz, const u32 *rp, const u32 *adj, int k, const int *sizes,
+                std::vector<u32> &perm, std::vector<u32> &sr_ptr, std::vector<u32> &ssr_ptr);
+void reorder_f32(int64_t n, const u32 *perm, const u32 *rp, const u32 *ci, const float *v,
+                 u32 *rp2, u32 *ci2, float *v2);
+void reorder_f64(int64_t n, const u32 *perm, const u32 *rp, const u32 *ci, const double *v,
+                 u32 *rp2, u32 *ci2, double *v2);
+
+// ---- io.cpp
+int read_csr_text(const char *path, int base, int dtype, int64_t *m, int64_t *n, int64_t *nnz,
+                  int32_t **rp, int32_t **ci, void **val, std::string &err);
+int write_csr_text(const char *path, int base, int dtype, int64_t m, int64_t n, int64_t nnz,
+                   const int32_t *rp, const int32_t *ci, const void *val, std::string &err);
+int read_csr3_text(const char *path, int dtype, int64_t *n_ssr, int64_t *n_sr, int64_t *m,
+                   int64_t *n, int64_t *nnz, u32 **ssr, u32 **sr, u32 **rp, u32 **ci, void **val,
+                   std::string &err);
+int write_csr3_text(const char *path, int dtype, int64_t n_ssr, int64_t n_sr, int64_t m,
+                    int64_t n, int64_t nnz, const u32 *ssr, const u32 *sr, const u32 *rp,
+                    const u32 *ci, const void *val, std::string &err);
+
+// ---- partition.cpp
+int partition_rows(int64_t m, const int32_t *rp, int n_parts, const u32 *align_ptr,
+                   int64_t n_align, int64_t *row_lo);
+int block_col_range(const int32_t *rp, const int32_t *ci, int64_t row_lo, int64_t row_hi,
+                    int64_t *cmin, int64_t *cmax);
+// Row-length bins of the CSR_VECTOR path.  bin_of_len() is THE rule (oracle/partition_oracle.py
+// restates it): 0 empty, 1: len<=4, 2: <=8, 3: <=16, 4: <=32, 5: <=64, 6: <=BLOCK_ROW_THRESHOLD,
+// 7: longer (one CTA per row).
+enum { NUM_BINS = 8, BLOCK_ROW_THRESHOLD = 4096 };
+inline int bin_of_len(int64_t len) {
+  if (len <= 0) return 0;
+  if (len <= 4) return 1;
+  if (len <= 8) return 2;
+  if (len <= 16) return 3;
+  if (len <= 32) return 4;
+  if (len <= 64) return 5;
+  if (len <= BLOCK_ROW_THRESHOLD) return 6;
+  return 7;
+}
+void row_stats(int64_t m, const int32_t *rp, int64_t out[10]);
+// rows of each bin in ascending order, concatenated; bin_ptr[NUM_BINS+1]
+void bin_rows(int64_t m, const int32_t *rp, std::vector<int32_t> &rows, int64_t bin_ptr[NUM_BINS + 1]);
+// merge-path tile table: tile_row[t] = last row r with rp[r] <= t*tile (t = 0..n_tiles), i.e. the
+// row that owns nonzero t*tile; tile_row[n_tiles] = m
+void tile_rows(int64_t m, const int32_t *rp, int64_t tile, std::vector<int32_t> &tile_row);
+
+// ---- heuristics.cpp
+int auto_params(int64_t nnz, int64_t n_rows, int arch, int sizes[2], int *veclevel, int *block_dim_y);
+
+} // namespace hspmv

@@ -1,0 +1,475 @@
+// sm_100a SpMV kernels.  All HBM-bound: no tensor cores (SpMV is not a dense contraction).
+//
+//   csr_vector_kernel   row-length-binned CSR: VEC lanes per row (1..32), 4 nonzeros per lane
+//                       per step through 128-bit loads, warp-shuffle reduction.
+//                       Replaces cuda_spmv, cuda-spmv-csr/spmv.cu:117-182 (thread per row).
+//   csr_blockrow_kernel one CTA per very long row (last bin).
+//   csrk_tma_kernel     CSR-k: super-super-row -> CTA, super-row -> warp, row -> VEC lanes.
+//                       Each warp owns a private ring of shared-memory stages; one elected lane
+//                       brings the next super-row's row_ptr / col / val segments in with TMA
+//                       bulk copies (cp.async.bulk + mbarrier complete_tx) while the warp
+//                       consumes the current one.  No CTA-wide barrier in the main loop.
+//                       Replaces cuSpMV_2 / cuSpMV_3 / cuSpMV_3_vec,
+//                       cuda-spmv-csrk/cuda/csrk.cu:320-391 / 244-319 / 184-242.
+//                       With k == 1 the same engine runs plain CSR on fixed-row tiles.
+//   csr_merge_kernel    nnz-balanced split for power-law matrices (see merge.cuh).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace hspmv {
+
+// ------------------------------------------------------------------------------------------
+// small PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (bytes % 16 == 0,
+// both addresses 16 B aligned).  SASS: UBLKCP.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes,
+                                         uint32_t bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
+
+// streaming 128-bit loads of the matrix arrays: read once, keep them out of L1
+__device__ __forceinline__ int4 ld_stream(const int4 *p) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float4 ld_stream(const float4 *p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double2 ld_stream(const double2 *p) {
+  double2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
+               : "=d"(r.x), "=d"(r.y)
+               : "l"(p));
+  return r;
+}
+
+// four consecutive values starting at a 4-aligned element index
+template <typename T> struct Quad {
+  T v[4];
+};
+__device__ __forceinline__ Quad<float> load_quad(const float *base, int64_t idx) {
+  float4 t = ld_stream(reinterpret_cast<const float4 *>(base + idx));
+  Quad<float> q;
+  q.v[0] = t.x; q.v[1] = t.y; q.v[2] = t.z; q.v[3] = t.w;
+  return q;
+}
+__device__ __forceinline__ Quad<double> load_quad(const double *base, int64_t idx) {
+  double2 a = ld_stream(reinterpret_cast<const double2 *>(base + idx));
+  double2 b = ld_stream(reinterpret_cast<const double2 *>(base + idx + 2));
+  Quad<double> q;
+  q.v[0] = a.x; q.v[1] = a.y; q.v[2] = b.x; q.v[3] = b.y;
+  return q;
+}
+
+template <typename T, int VEC> __device__ __forceinline__ T group_sum(T v) {
+#pragma unroll
+  for (int o = VEC >> 1; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o, VEC);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// CSR, VEC lanes per row, 128-bit loads
+// ------------------------------------------------------------------------------------------
+// rows: either the contiguous range [row_base, row_base + n_rows) or row_list[0..n_rows).
+// The column / value arrays are padded by >= 4 entries past nnz, so the aligned quads that
+// straddle a row's ends are always in bounds; out-of-row lanes are masked by select, never
+// multiplied by zero (x may hold Inf/NaN in entries the row does not reference).
+template <typename T, int VEC, bool LIST>
+__global__ void __launch_bounds__(256)
+csr_vector_kernel(int64_t n_rows, const int *__restrict__ row_list, int64_t row_base,
+                  const int *__restrict__ rp, const int *__restrict__ ci,
+                  const T *__restrict__ val, const T *__restrict__ x, T *__restrict__ y) {
+  const int lane = threadIdx.x & (VEC - 1);
+  const int64_t n_groups = (int64_t)gridDim.x * blockDim.x / VEC;
+  // warp-uniform trip count: every lane of a warp stays in the loop until the warp's first
+  // group runs out of rows, so the full-mask shuffles below are always convergent
+  for (int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) / VEC; g0 < n_rows;
+       g0 += n_groups) {
+    const int64_t g = g0 + (threadIdx.x & 31) / VEC;
+    const bool active = g < n_rows;
+    int64_t r = 0, e0 = 0, e1 = 0;
+    if (active) {
+      r = LIST ? (int64_t)row_list[g] : row_base + g;
+      e0 = rp[r];
+      e1 = rp[r + 1];
+    }
+    T acc = 0;
+    for (int64_t b = (e0 & ~(int64_t)3) + 4 * lane; b < e1; b += 4 * VEC) {
+      const int4 c = ld_stream(reinterpret_cast<const int4 *>(ci + b));
+      const Quad<T> q = load_quad(val, b);
+      const T x0 = __ldg(x + c.x), x1 = __ldg(x + c.y), x2 = __ldg(x + c.z), x3 = __ldg(x + c.w);
+      if (b >= e0 && b + 3 < e1) {
+        acc += q.v[0] * x0;
+        acc += q.v[1] * x1;
+        acc += q.v[2] * x2;
+        acc += q.v[3] * x3;
+      } else {
+        if (b >= e0 && b < e1) acc += q.v[0] * x0;
+        if (b + 1 >= e0 && b + 1 < e1) acc += q.v[1] * x1;
+        if (b + 2 >= e0 && b + 2 < e1) acc += q.v[2] * x2;
+        if (b + 3 >= e0 && b + 3 < e1) acc += q.v[3] * x3;
+      }
+    }
+    acc = group_sum<T, VEC>(acc);
+    if (active && lane == 0) y[r] = acc;
+  }
+}
+
+// one CTA per long row
+template <typename T>
+__global__ void __launch_bounds__(256)
+csr_blockrow_kernel(int64_t n_rows, const int *__restrict__ row_list,
+                    const int *__restrict__ rp, const int *__restrict__ ci,
+                    const T *__restrict__ val, const T *__restrict__ x, T *__restrict__ y) {
+  __shared__ T partial[8];
+  for (int64_t g = blockIdx.x; g < n_rows; g += gridDim.x) {
+    const int64_t r = row_list[g];
+    const int64_t e0 = rp[r], e1 = rp[r + 1];
+    T acc = 0;
+    for (int64_t b = (e0 & ~(int64_t)3) + 4 * (int64_t)threadIdx.x; b < e1; b += 4 * 256) {
+      const int4 c = ld_stream(reinterpret_cast<const int4 *>(ci + b));
+      const Quad<T> q = load_quad(val, b);
+      if (b >= e0 && b < e1) acc += q.v[0] * __ldg(x + c.x);
+      if (b + 1 >= e0 && b + 1 < e1) acc += q.v[1] * __ldg(x + c.y);
+      if (b + 2 >= e0 && b + 2 < e1) acc += q.v[2] * __ldg(x + c.z);
+      if (b + 3 >= e0 && b + 3 < e1) acc += q.v[3] * __ldg(x + c.w);
+    }
+    acc = group_sum<T, 32>(acc);
+    if ((threadIdx.x & 31) == 0) partial[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      T s = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += partial[w];
+      y[r] = s;
+    }
+    __syncthreads();
+  }
+}
+
+// rows with no stored entry: y = 0 (only launched when the matrix has such rows and the
+// main kernel works from row lists)
+template <typename T>
+__global__ void zero_rows_kernel(int64_t n_rows, const int *__restrict__ row_list,
+                                 T *__restrict__ y) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows;
+       i += (int64_t)gridDim.x * blockDim.x)
+    y[row_list[i]] = 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// CSR-k, TMA-staged super-rows
+// ------------------------------------------------------------------------------------------
+template <typename T> struct CsrkParams {
+  int k;              // 1: implicit tiles of rows_per_tile rows, 2: sr_ptr, 3: ssr_ptr + sr_ptr
+  int64_t m;          // rows
+  int64_t n_sr;       // super-rows (k == 1: number of tiles)
+  int64_t n_ssr;      // super-super-rows (k == 3)
+  const uint32_t *ssr_ptr; // [n_ssr+1]
+  const uint32_t *sr_ptr;  // [n_sr+1]
+  const uint32_t *sr_e;    // [n_sr+1] = rp[sr_ptr[s]]: device-only helper, saves one dependent load
+  const int *rp;
+  const int *ci;
+  const T *val;
+  const T *x;
+  T *y;
+  int rows_per_tile;  // k == 1
+  int stages;         // ring depth per warp
+  int cap_nnz;        // stage capacity in nonzeros (multiple of 4)
+  int cap_rows;       // stage capacity in rows (multiple of 4)
+};
+
+// sequence of super-rows a warp processes
+struct SrCursor {
+  int64_t cur, end, step;     // k < 3: cur, cur+step, ... < end
+  int64_t s, s_step, n_ssr;   // k == 3: CTA walks super-super-rows s, s+s_step, ...
+  const uint32_t *ssr_ptr;
+  int w, W;
+  bool three;
+  __device__ __forceinline__ bool next(int64_t &sr) {
+    if (!three) {
+      if (cur >= end) return false;
+      sr = cur;
+      cur += step;
+      return true;
+    }
+    for (;;) {
+      if (cur < end) {
+        sr = cur;
+        cur += W;
+        return true;
+      }
+      s += s_step;
+      if (s >= n_ssr) return false;
+      cur = (int64_t)__ldg(ssr_ptr + s) + w;
+      end = (int64_t)__ldg(ssr_ptr + s + 1);
+    }
+  }
+};
+
+struct SrMeta {
+  int r0, r1;     // rows
+  int e0, e1;     // nonzeros
+};
+
+__host__ __device__ inline size_t csrk_stage_bytes(int cap_nnz, int cap_rows, size_t vsize) {
+  // meta (16 B) | row_ptr window | col window | val window ; every piece a multiple of 16 B
+  return 16 + (size_t)(cap_rows + 8) * 4 + (size_t)(cap_nnz + 8) * 4 + (size_t)(cap_nnz + 8) * vsize;
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ void csrk_rows(int r0, int r1, const int *__restrict__ rp_w, int rbase,
+                                          const int *__restrict__ ci_w, const T *__restrict__ val_w,
+                                          int64_t ebase, const T *__restrict__ x, T *__restrict__ y,
+                                          int lane) {
+  const int sub = lane & (VEC - 1);
+  const int gid = lane / VEC;
+  // warp-uniform trip count (full-mask shuffles inside)
+  for (int rb = r0; rb < r1; rb += 32 / VEC) {
+    const int r = rb + gid;
+    const bool active = r < r1;
+    int64_t rs = 0, re = 0;
+    if (active) {
+      rs = rp_w[r - rbase];
+      re = rp_w[r + 1 - rbase];
+    }
+    T acc = 0;
+#pragma unroll 4
+    for (int64_t j = rs + sub; j < re; j += VEC)
+      acc += val_w[j - ebase] * __ldg(x + ci_w[j - ebase]);
+    acc = group_sum<T, VEC>(acc);
+    if (active && sub == 0) y[r] = acc;
+  }
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(512, 1) csrk_tma_kernel(const CsrkParams<T> p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int w = threadIdx.x >> 5;
+  const int W = blockDim.x >> 5;
+  const int S = p.stages;
+  const size_t stage_bytes = csrk_stage_bytes(p.cap_nnz, p.cap_rows, sizeof(T));
+  // layout: [W*S mbarriers][warp 0: S stages][warp 1: S stages]...
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw) + (size_t)w * S;
+  unsigned char *ring = smem_raw + (((size_t)W * S * 8 + 127) & ~(size_t)127) + (size_t)w * S * stage_bytes;
+
+  if (lane == 0) {
+    for (int s = 0; s < S; ++s) mbar_init(smem_u32(bars + s), 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  __syncwarp();
+
+  SrCursor cur;
+  cur.three = (p.k == 3);
+  cur.w = w;
+  cur.W = W;
+  cur.ssr_ptr = p.ssr_ptr;
+  cur.n_ssr = p.n_ssr;
+  if (cur.three) {
+    cur.s = (int64_t)blockIdx.x - gridDim.x; // first next() advances to blockIdx.x
+    cur.s_step = gridDim.x;
+    cur.cur = 0;
+    cur.end = 0;
+    cur.step = 0;
+  } else {
+    cur.cur = (int64_t)blockIdx.x * W + w;
+    cur.step = (int64_t)gridDim.x * W;
+    cur.end = p.n_sr;
+    cur.s = cur.s_step = 0;
+  }
+
+  const uint64_t policy = l2_policy_evict_first();
+
+  auto load_meta = [&](int64_t sr) -> SrMeta {
+    SrMeta mt;
+    if (p.k == 1) {
+      const int64_t r0 = sr * p.rows_per_tile;
+      const int64_t r1 = (r0 + p.rows_per_tile < p.m) ? r0 + p.rows_per_tile : p.m;
+      mt.r0 = (int)r0;
+      mt.r1 = (int)r1;
+      mt.e0 = __ldg(p.rp + r0);
+      mt.e1 = __ldg(p.rp + r1);
+    } else {
+      mt.r0 = (int)__ldg(p.sr_ptr + sr);
+      mt.r1 = (int)__ldg(p.sr_ptr + sr + 1);
+      mt.e0 = (int)__ldg(p.sr_e + sr);
+      mt.e1 = (int)__ldg(p.sr_e + sr + 1);
+    }
+    return mt;
+  };
+
+  // post the TMA copies (or an empty arrival for an oversized super-row) for `mt` into stage st
+  auto issue = [&](const SrMeta &mt, int st) {
+    if (lane == 0) {
+      unsigned char *base = ring + (size_t)st * stage_bytes;
+      const int rows = mt.r1 - mt.r0, cnt = mt.e1 - mt.e0;
+      const bool staged = rows <= p.cap_rows && cnt <= p.cap_nnz && cnt > 0;
+      int *meta = reinterpret_cast<int *>(base);
+      meta[0] = mt.r0;
+      meta[1] = mt.r1;
+      meta[2] = mt.e0;
+      meta[3] = staged ? mt.e1 : -mt.e1 - 1; // negative: not staged, read from global
+      const uint32_t bar = smem_u32(bars + st);
+      if (staged) {
+        const int rb = mt.r0 & ~3, rt = (mt.r1 + 1 + 3) & ~3; // row_ptr entries r0..r1
+        const int64_t eb = mt.e0 & ~3, et = ((int64_t)mt.e1 + 3) & ~(int64_t)3;
+        const uint32_t rp_bytes = (uint32_t)(rt - rb) * 4u;
+        const uint32_t ci_bytes = (uint32_t)(et - eb) * 4u;
+        const uint32_t va_bytes = (uint32_t)(et - eb) * (uint32_t)sizeof(T);
+        unsigned char *rp_w = base + 16;
+        unsigned char *ci_w = rp_w + (size_t)(p.cap_rows + 8) * 4;
+        unsigned char *va_w = ci_w + (size_t)(p.cap_nnz + 8) * 4;
+        fence_proxy_async(); // earlier generic-proxy reads of this stage vs. the async writes
+        mbar_arrive_expect_tx(bar, rp_bytes + ci_bytes + va_bytes);
+        bulk_g2s(smem_u32(rp_w), p.rp + rb, rp_bytes, bar, policy);
+        bulk_g2s(smem_u32(ci_w), p.ci + eb, ci_bytes, bar, policy);
+        bulk_g2s(smem_u32(va_w), p.val + eb, va_bytes, bar, policy);
+      } else {
+        mbar_arrive(bar);
+      }
+    }
+  };
+
+  // ---- prologue: fill the ring
+  int64_t sr;
+  int filled = 0;
+  for (; filled < S; ++filled) {
+    if (!cur.next(sr)) break;
+    issue(load_meta(sr), filled);
+  }
+  bool have_next = cur.next(sr);
+  SrMeta next_meta;
+  next_meta.r0 = next_meta.r1 = next_meta.e0 = next_meta.e1 = 0;
+  if (have_next) next_meta = load_meta(sr); // in flight while the first stage is consumed
+
+  // ---- main loop
+  int st = 0;
+  uint32_t parity = 0;
+  for (int live = filled; live > 0;) {
+    const uint32_t bar = smem_u32(bars + st);
+    mbar_wait(bar, parity);
+    unsigned char *base = ring + (size_t)st * stage_bytes;
+    const int *meta = reinterpret_cast<const int *>(base);
+    const int r0 = meta[0], r1 = meta[1], e0 = meta[2], e1m = meta[3];
+    if (e1m >= 0) {
+      const int *rp_w = reinterpret_cast<const int *>(base + 16);
+      const int *ci_w = rp_w + (p.cap_rows + 8);
+      const T *va_w = reinterpret_cast<const T *>(reinterpret_cast<const unsigned char *>(ci_w) +
+                                                   (size_t)(p.cap_nnz + 8) * 4);
+      csrk_rows<T, VEC>(r0, r1, rp_w, r0 & ~3, ci_w, va_w, (int64_t)(e0 & ~3), p.x, p.y, lane);
+    } else {
+      csrk_rows<T, VEC>(r0, r1, p.rp, 0, p.ci, p.val, 0, p.x, p.y, lane);
+    }
+    __syncwarp();
+    --live;
+    if (have_next) {
+      issue(next_meta, st);
+      ++live;
+      have_next = cur.next(sr);
+      if (have_next) next_meta = load_meta(sr);
+    }
+    if (++st == S) {
+      st = 0;
+      parity ^= 1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// vector helpers
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void gather_kernel(int64_t n, const uint32_t *__restrict__ perm,
+                              const T *__restrict__ src, T *__restrict__ dst) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = src[perm[i]];
+}
+template <typename T>
+__global__ void scatter_kernel(int64_t n, const uint32_t *__restrict__ perm,
+                               const T *__restrict__ src, T *__restrict__ dst) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    dst[perm[i]] = src[i];
+}
+// sr_e[s] = rp[sr_ptr[s]]
+__global__ void sr_offsets_kernel(int64_t n_sr, const uint32_t *__restrict__ sr_ptr,
+                                  const int *__restrict__ rp, uint32_t *__restrict__ sr_e) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n_sr;
+       i += (int64_t)gridDim.x * blockDim.x)
+    sr_e[i] = (uint32_t)rp[sr_ptr[i]];
+}
+__global__ void col_minmax_kernel(int64_t nnz, const int *__restrict__ ci, int *out_min,
+                                  int *out_max) {
+  int lo = INT32_MAX, hi = -1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = ci[i];
+    lo = min(lo, c);
+    hi = max(hi, c);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_down_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_down_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(out_min, lo);
+    atomicMax(out_max, hi);
+  }
+}
+
+} // namespace hspmv

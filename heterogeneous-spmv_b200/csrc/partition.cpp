@@ -1,0 +1,83 @@
+// Integer index work that feeds the kernels and the multi-GPU layer: nnz-balanced row blocks,
+// column ranges (halo discovery), row-length bins, merge-path tile table.  All of it must be
+// bit-exact against oracle/partition_oracle.py, which restates the same rules in numpy
+// (the reference has no multi-GPU or binning code to compare with -- SURVEY.md 8e).
+#include "host_index.h"
+
+#include <algorithm>
+
+namespace hspmv {
+
+int partition_rows(int64_t m, const int32_t *rp, int n_parts, const u32 *align_ptr,
+                   int64_t n_align, int64_t *row_lo) {
+  if (m < 0 || !rp || n_parts < 1 || !row_lo) return HSPMV_EINVAL;
+  const int64_t nnz = rp[m];
+  row_lo[0] = 0;
+  for (int p = 1; p < n_parts; ++p) {
+    const int64_t target = (int64_t)(((__int128)nnz * p) / n_parts);
+    // first row r with rp[r] >= target
+    int64_t r = std::lower_bound(rp, rp + m + 1, (int32_t)target) - rp;
+    if (r > m) r = m;
+    if (align_ptr) { // snap up to the next group boundary (super-row or super-super-row start)
+      const u32 *b = std::lower_bound(align_ptr, align_ptr + n_align + 1, (u32)r);
+      r = (b == align_ptr + n_align + 1) ? m : (int64_t)*b;
+    }
+    row_lo[p] = std::max(r, row_lo[p - 1]);
+  }
+  row_lo[n_parts] = m;
+  return HSPMV_OK;
+}
+
+int block_col_range(const int32_t *rp, const int32_t *ci, int64_t row_lo, int64_t row_hi,
+                    int64_t *cmin, int64_t *cmax) {
+  if (!rp || !ci || !cmin || !cmax || row_hi < row_lo) return HSPMV_EINVAL;
+  int32_t lo = INT32_MAX, hi = -1;
+  const int64_t e0 = rp[row_lo], e1 = rp[row_hi];
+#pragma omp parallel for reduction(min : lo) reduction(max : hi) schedule(static)
+  for (int64_t e = e0; e < e1; ++e) {
+    lo = std::min(lo, ci[e]);
+    hi = std::max(hi, ci[e]);
+  }
+  *cmin = (e1 > e0) ? lo : 0;
+  *cmax = (e1 > e0) ? hi : -1;
+  return HSPMV_OK;
+}
+
+void row_stats(int64_t m, const int32_t *rp, int64_t out[10]) {
+  for (int i = 0; i < 10; ++i) out[i] = 0;
+  int64_t mx = 0;
+  for (int64_t r = 0; r < m; ++r) {
+    const int64_t len = (int64_t)rp[r + 1] - rp[r];
+    ++out[bin_of_len(len)];
+    mx = std::max(mx, len);
+  }
+  out[8] = mx;
+  out[9] = out[0];
+}
+
+void bin_rows(int64_t m, const int32_t *rp, std::vector<int32_t> &rows, int64_t bin_ptr[NUM_BINS + 1]) {
+  int64_t cnt[NUM_BINS] = {0};
+  for (int64_t r = 0; r < m; ++r) ++cnt[bin_of_len((int64_t)rp[r + 1] - rp[r])];
+  bin_ptr[0] = 0;
+  for (int b = 0; b < NUM_BINS; ++b) bin_ptr[b + 1] = bin_ptr[b] + cnt[b];
+  rows.resize((size_t)m);
+  int64_t cur[NUM_BINS];
+  for (int b = 0; b < NUM_BINS; ++b) cur[b] = bin_ptr[b];
+  for (int64_t r = 0; r < m; ++r) rows[(size_t)cur[bin_of_len((int64_t)rp[r + 1] - rp[r])]++] = (int32_t)r;
+}
+
+void tile_rows(int64_t m, const int32_t *rp, int64_t tile, std::vector<int32_t> &tile_row) {
+  const int64_t nnz = rp[m];
+  const int64_t n_tiles = (nnz + tile - 1) / tile;
+  tile_row.resize((size_t)n_tiles + 1);
+#pragma omp parallel for schedule(static)
+  for (int64_t t = 0; t < n_tiles; ++t) {
+    const int64_t e = t * tile;
+    // last row r with rp[r] <= e  (the row that owns nonzero e)
+    const int32_t *u = std::upper_bound(rp, rp + m + 1, (int32_t)e);
+    tile_row[(size_t)t] = (int32_t)((u - rp) - 1);
+  }
+  tile_row[(size_t)n_tiles] = (int32_t)m;
+}
+
+} // namespace hspmv

@@ -1,0 +1,225 @@
+/* hspmv.h -- C ABI of the B200-native SpMV engine (libhspmv.so).
+ *
+ * This is the drop-in boundary for the y = A*x hot path of computablee/heterogeneous-spmv.
+ * The reference has no FFI layer; its "operator API" is the set of C/C++ entry points its
+ * drivers call.  Every function below names the reference interface
+ * it replaces (file:line relative to the reference tree).  Plain pointers and sizes only;
+ * no C++ or torch types; int status returns (0 = HSPMV_OK); opaque handles; host buffers are
+ * caller-owned, device buffers are library-owned unless a function says otherwise.
+ *
+ * Threading: one handle per host thread.  All launches go to the stream passed in (or the
+ * handle's own stream when NULL is passed where noted).  There is NO CPU fallback: every
+ * compute entry point returns HSPMV_ECUDA when no sm_100 device is usable.
+ *
+ * include/spmv.h and include/csrk.h are source-compatible mirrors of the reference's
+ * spmv-csr/spmv.h and spmv-csrk/csrk.h built on top of this ABI.
+ */
+#ifndef HSPMV_H
+#define HSPMV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hspmv_matrix hspmv_matrix; /* opaque */
+
+enum { HSPMV_F32 = 0, HSPMV_F64 = 1 };
+
+enum {
+  HSPMV_OK = 0,
+  HSPMV_EINVAL = 1,       /* bad argument */
+  HSPMV_ECUDA = 2,        /* CUDA runtime error / no usable device */
+  HSPMV_EIO = 3,          /* file could not be opened / parsed */
+  HSPMV_ENOMEM = 4,
+  HSPMV_EUNSUPPORTED = 5, /* e.g. Band-k on a matrix with a coarse vertex without upper entries (Q8) */
+  HSPMV_ESTATE = 6        /* call order: e.g. CSR-k kernel before hspmv_build_csrk */
+};
+
+/* Kernel selection.  AUTO picks from the row-length statistics gathered at creation. */
+enum {
+  HSPMV_ALGO_AUTO = 0,
+  HSPMV_ALGO_CSR_VECTOR = 1, /* row-length binned: sub-warp vector-per-row (2..32 lanes), block-per-row */
+  HSPMV_ALGO_CSR_STREAM = 2, /* fixed-row tiles staged by TMA bulk copies (CSR-k engine, virtual super-rows) */
+  HSPMV_ALGO_CSR_MERGE = 3,  /* nnz-balanced split with carry fix-up (power-law matrices) */
+  HSPMV_ALGO_CSRK = 4        /* SSR -> CTA, SR -> warp, row -> lane(s), TMA-staged super-rows (needs build_csrk) */
+};
+
+/* Tunables for hspmv_set_option (all optional; defaults come from the auto-tuner). */
+enum {
+  HSPMV_OPT_VEC = 1,          /* lanes per row: 1,2,4,8,16,32; 0 = auto */
+  HSPMV_OPT_WARPS = 2,        /* warps per CTA for the TMA kernels */
+  HSPMV_OPT_STAGES = 3,       /* TMA ring depth per warp */
+  HSPMV_OPT_STAGE_NNZ = 4,    /* capacity of one stage in nonzeros */
+  HSPMV_OPT_CTAS_PER_SM = 5,  /* persistent grid = SMs * this */
+  HSPMV_OPT_ROWS_PER_TILE = 6,/* CSR_STREAM: rows per warp tile */
+  HSPMV_OPT_L2_PERSIST_X = 7, /* 1: put x under a persisting L2 access-policy window */
+  HSPMV_OPT_MERGE_TILE = 8,   /* CSR_MERGE: nonzeros per CTA tile */
+  HSPMV_OPT_THREADS = 9       /* CSR_VECTOR / CSR_MERGE block size */
+};
+
+/* ---- runtime ---------------------------------------------------------------------- */
+int hspmv_version(void);
+/* last error text of the calling thread ("" if none) */
+const char *hspmv_last_error(void);
+int hspmv_device_count(int *count);
+int hspmv_set_device(int device);
+/* sm count, L2 bytes, total HBM bytes, cc major*10+minor of the current device */
+int hspmv_device_info(int *sm_count, int64_t *l2_bytes, int64_t *hbm_bytes, int *cc);
+/* number of kernels this library has launched in the calling process (bench.py gpu_launches) */
+int64_t hspmv_launch_count(void);
+
+/* ---- file formats ----------------------------------------------------------------- */
+/* Replaces my_read_csr: spmv-csr/spmv.c:11-57 (index_base 0), spmv-csrk/spmv.cpp:32-79 and
+ * cuda-spmv-csrk/cuda/spmv.cu:46-93 (index_base 1: 1 is subtracted from every index),
+ * cuda-spmv-csr/spmv.cu:11-73.  Grammar: "m n nnz", (m+1) row pointers, nnz column indices,
+ * nnz values, whitespace separated.  dtype selects float or double storage of *val.
+ * Arrays are allocated by the library (free with hspmv_free_host). */
+int hspmv_read_csr_text(const char *path, int index_base, int dtype, int64_t *m, int64_t *n,
+                        int64_t *nnz, int32_t **row_ptr, int32_t **col_idx, void **val);
+/* Writes the layout of helpers/converter.m:42-48 (also reformat-csr-to-csr3/spmv.cpp:38-62). */
+int hspmv_write_csr_text(const char *path, int index_base, int dtype, int64_t m, int64_t n,
+                         int64_t nnz, const int32_t *row_ptr, const int32_t *col_idx,
+                         const void *val);
+/* `.csr3` reader; replaces reformat-csr-to-csr3/stats.c:10-79.  Header "nSSR nSR M N NNZ",
+ * then ssr_ptr, sr_ptr, row_ptr, col (all 0-based, %u), val (%.6f). */
+int hspmv_read_csr3_text(const char *path, int dtype, int64_t *n_ssr, int64_t *n_sr, int64_t *m,
+                         int64_t *n, int64_t *nnz, uint32_t **ssr_ptr, uint32_t **sr_ptr,
+                         uint32_t **row_ptr, uint32_t **col_idx, void **val);
+/* `.csr3` writer; replaces my_write_csr, reformat-csr-to-csr3/spmv-auto.cpp:30-65. */
+int hspmv_write_csr3_text(const char *path, int dtype, int64_t n_ssr, int64_t n_sr, int64_t m,
+                          int64_t n, int64_t nnz, const uint32_t *ssr_ptr, const uint32_t *sr_ptr,
+                          const uint32_t *row_ptr, const uint32_t *col_idx, const void *val);
+void hspmv_free_host(void *p);
+
+/* ---- matrix handles --------------------------------------------------------------- */
+/* Upload once into device-resident, 256 B-aligned, tail-padded arrays.  Replaces the upload in
+ * cuda-spmv-csr/spmv.cu:28-30,66-71 and the CSRk_Graph ctor cuda-spmv-csrk/cuda/csrk.cu:532-588
+ * (which, like this, copies the caller's arrays: spmv-csrk/csrk.cpp:392-408).
+ * keep_host != 0 keeps a host copy inside the handle (needed by hspmv_build_csrk). */
+int hspmv_create_csr(hspmv_matrix **out, int64_t m, int64_t n, int64_t nnz,
+                     const int32_t *row_ptr, const int32_t *col_idx, const void *val, int dtype,
+                     int index_base, int keep_host);
+/* From `.csr3` arrays (matrix already Band-k reordered); k = 3, or k = 2 when ssr_ptr == NULL. */
+int hspmv_create_csrk(hspmv_matrix **out, int64_t n_ssr, int64_t n_sr, int64_t m, int64_t n,
+                      int64_t nnz, const uint32_t *ssr_ptr, const uint32_t *sr_ptr,
+                      const uint32_t *row_ptr, const uint32_t *col_idx, const void *val,
+                      int dtype);
+/* Synthetic matrices generated directly in HBM (the shapes of BASELINE.json configs; same
+ * closed forms as generators.py): rows [row_lo,row_hi) of the g^3 27-point stencil (kind 27)
+ * or the g^2 5-point Laplacian (kind 5), natural order; row_ptr rebased to 0; column ids
+ * shifted by -col_shift (multi-GPU localisation).  mode 0 = classic values, 1 = varied. */
+int hspmv_create_stencil(hspmv_matrix **out, int kind, int64_t g, int dtype, int mode,
+                         int64_t row_lo, int64_t row_hi, int64_t col_shift, int64_t n_cols);
+int hspmv_destroy(hspmv_matrix *A);
+
+/* m, n, nnz, dtype, k (1 = plain CSR), #super-rows, #super-super-rows; any pointer may be NULL */
+int hspmv_matrix_info(const hspmv_matrix *A, int64_t *m, int64_t *n, int64_t *nnz, int *dtype,
+                      int *k, int64_t *n_sr, int64_t *n_ssr);
+/* Device -> host copy of the (possibly Band-k reordered) CSR arrays, for bit-exact diffing. */
+int hspmv_download_csr(const hspmv_matrix *A, int32_t *row_ptr, int32_t *col_idx, void *val);
+/* Row-length statistics and the bins the CSR_VECTOR path uses: out[0..7] = rows per bin
+ * (empty, <=4, <=8, <=16, <=32, <=64, <=128 [vec 32 loops], >block_row_threshold),
+ * out[8] = max row length, out[9] = number of empty rows. */
+int hspmv_row_stats(const hspmv_matrix *A, int64_t out[10]);
+
+/* ---- Band-k / CSR-k --------------------------------------------------------------- */
+/* Replaces CSRk_Graph::putInCSRkFormat (spmv-csrk/csrk.cpp:681-706 = BAND_k::
+ * preprocessingForSpMV :841-1067 + reorderA :548-676) and the device upload of the maps
+ * (cuda-spmv-csrk/cuda/csrk.cu:848-866).  k in {2,3}; sup_row_sizes[0] controls level 1 (rows
+ * per super-row, nnz-weighted), [1] level 2 -- same order as the reference argv (Q9).
+ * Unlike the reference CUDA path (quirk Q3) the REORDERED matrix is what gets uploaded. */
+int hspmv_build_csrk(hspmv_matrix *A, int k, const int *sup_row_sizes);
+/* Host copies for bit-exact diffing; any pointer may be NULL.  perm[m] (new row -> old row,
+ * CSRk_Graph::getPermutation csrk.h:325), sr_ptr[n_sr+1], ssr_ptr[n_ssr+1]. */
+int hspmv_csrk_get(const hspmv_matrix *A, uint32_t *perm, uint32_t *sr_ptr, uint32_t *ssr_ptr);
+
+/* The same index work without a device (host only; used by tests and by converters). */
+int hspmv_bandk_host(int64_t n, int64_t nnz, const uint32_t *row_ptr, const uint32_t *col_idx,
+                     int k, const int *sup_row_sizes, uint32_t *perm, uint32_t *sr_ptr,
+                     int64_t *n_sr, uint32_t *ssr_ptr, int64_t *n_ssr);
+int hspmv_reorder_host(int64_t n, int64_t nnz, const uint32_t *perm, const uint32_t *row_ptr,
+                       const uint32_t *col_idx, const void *val, int dtype, uint32_t *row_ptr_out,
+                       uint32_t *col_idx_out, void *val_out);
+
+/* Size / launch-shape heuristics.  arch: 0 = Volta formula (spmv-auto-volta.cu:130-159 and
+ * reformat-csr-to-csr3/spmv-auto.cpp:154-173), 1 = Ampere (spmv-auto-ampere.cu:130-158),
+ * 2 = MI100 (hip/spmv-auto-mi100.cu:132-133), 3 = B200 retune (this library).
+ * Outputs sizes[0] ("ssrs"), sizes[1] ("srs"), veclevel (0 = scalar kernel), block_dim_y. */
+int hspmv_auto_params(int64_t nnz, int64_t n_rows, int arch, int sizes[2], int *veclevel,
+                      int *block_dim_y);
+
+/* ---- vectors ---------------------------------------------------------------------- */
+/* Replaces CSRk_Graph::setX (csrk.h:327-335, csrk.cu:91-101): x_test[i] = x[perm[i]] when the
+ * matrix is in CSR-k order, then H2D.  x has n entries of the matrix dtype. */
+int hspmv_set_x(hspmv_matrix *A, const void *x_host);
+/* Replaces getY (csrk.cu:109-112) / the D2H at cuda-spmv-csr/spmv.cu:270.  original_order != 0
+ * undoes the Band-k row permutation (y_out[perm[i]] = y[i]); 0 returns the kernel's order,
+ * which is what spmv-csrk/spmv.cpp:203 compares against y_csrser[perm[i]]. */
+int hspmv_get_y(hspmv_matrix *A, void *y_host, int original_order);
+/* Library-owned device vectors of the handle (x in kernel order, n entries; y, m entries). */
+void *hspmv_x_device(hspmv_matrix *A);
+void *hspmv_y_device(hspmv_matrix *A);
+/* x_i = 1 + ((global_offset + i) mod 97)/128 written straight into the handle's device x
+ * (generators.py:vector_x; the non-constant x the parity tests use instead of the reference's
+ * x = 1, which is blind to permutation errors -- SURVEY.md section 4). */
+int hspmv_fill_x_synthetic(hspmv_matrix *A, int64_t global_offset);
+
+/* ---- the hot path ----------------------------------------------------------------- */
+int hspmv_set_option(hspmv_matrix *A, int option, int64_t value);
+/* Enqueue y = A*x on `stream` (a cudaStream_t cast to void*; NULL = the legacy default
+ * stream).  d_x / d_y are device pointers in kernel order; NULL selects the handle's own
+ * vectors.  Replaces the launches at cuda-spmv-csr/spmv.cu:243, cuda-spmv-csrk/cuda/spmv.cu:
+ * 186-198, spmv-auto-ampere.cu:205-217 and the CPU loops omp_spmv (spmv-csr/spmv.c:92-114)
+ * and CSRk_Graph::SpMV (spmv-csrk/csrk.cpp:149-330). */
+int hspmv_spmv(hspmv_matrix *A, int algo, const void *d_x, void *d_y, void *stream);
+/* N timed launches after `warmup` untimed ones; ms_out[i] = device time of launch i from
+ * CUDA events on the launching stream.  flush_l2 != 0 overwrites an L2-sized scratch buffer
+ * before every launch (outside the event pair).  Replaces the host-timer loops at
+ * cuda-spmv-csr/spmv.cu:240-260 / spmv-auto-ampere.cu:205-230. */
+int hspmv_spmv_timed(hspmv_matrix *A, int algo, int warmup, int iters, int flush_l2,
+                     float *ms_out);
+/* End-to-end plugin call with HOST buffers: set_x (permute + H2D) -> kernel -> get_y (D2H,
+ * original row order), synchronous.  This is setX + SpMV + getY of the reference drivers. */
+int hspmv_spmv_host(hspmv_matrix *A, int algo, const void *x_host, void *y_host);
+/* Name of the kernel variant the last hspmv_spmv on this handle launched (for reports). */
+const char *hspmv_last_kernel(const hspmv_matrix *A);
+
+/* Source-compatible replacements for spmv-csr/spmv.h:11-12 (double) and the float body in
+ * spmv-csr/spmv.c:92-114: host CSR in, host y out.  The matrix is uploaded on first use and
+ * cached by (row_start, col_idx, val, nnz) identity, so repeated calls in a timing loop
+ * only move x and y. */
+int hspmv_omp_spmv_f64(int m, int n, int nnz, const int *row_start, const int *col_idx,
+                       const double *val, const double *x, double *y);
+int hspmv_omp_spmv_f32(int m, int n, int nnz, const int *row_start, const int *col_idx,
+                       const float *val, const float *x, float *y);
+void hspmv_omp_spmv_cache_clear(void);
+
+/* ---- multi-GPU index work (host; bit-exact vs oracle/partition_oracle.py) ---------- */
+/* nnz-balanced contiguous row blocks: row_lo[p] = first row r with row_ptr[r] >= p*nnz/P
+ * (row_lo[0] = 0, row_lo[P] = m).  If align_ptr != NULL (sr_ptr or the composed ssr->row map,
+ * n_align+1 entries) each cut is moved up to the next group boundary. */
+int hspmv_partition_rows(int64_t m, const int32_t *row_ptr, int n_parts, const uint32_t *align_ptr,
+                         int64_t n_align, int64_t *row_lo);
+/* For the row block [row_lo,row_hi): smallest and largest column index referenced. */
+int hspmv_block_col_range(const int32_t *row_ptr, const int32_t *col_idx, int64_t row_lo,
+                          int64_t row_hi, int64_t *col_min, int64_t *col_max);
+/* Device variant for matrices that only exist in HBM (generated or already uploaded). */
+int hspmv_col_range_device(const hspmv_matrix *A, int64_t *col_min, int64_t *col_max);
+
+
+/* ---- kernel-side index tables, exposed for the bit-exactness tests ------------------ */
+/* CSR_MERGE tile table: tile_row[t] = last row r with row_ptr[r] <= t*tile, t = 0..n_tiles
+ * (n_tiles = ceil(nnz/tile)); tile_row[n_tiles] = m.  Host rule and the device copy. */
+int hspmv_merge_tile_rows_host(int64_t m, const int32_t *row_ptr, int64_t tile, int32_t *tile_row);
+int hspmv_merge_tile_rows_device(const hspmv_matrix *A, int64_t *tile, int64_t *n_tiles,
+                                 int32_t *tile_row);
+/* CSR_VECTOR bins: rows[m] grouped by bin in ascending row order, bin_ptr[9]. */
+int hspmv_bin_rows_host(int64_t m, const int32_t *row_ptr, int32_t *rows, int64_t *bin_ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HSPMV_H */
