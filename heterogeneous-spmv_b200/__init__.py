@@ -335,6 +335,11 @@ class Matrix:
         assert len(x) == self.info()["n"]
         _check(lib().hspmv_set_x(self.h, _p(x)))
 
+    def set_y(self, y):
+        y = np.ascontiguousarray(y, dtype=self.dtype)
+        assert len(y) == self.info()["m"]
+        _check(lib().hspmv_set_y(self.h, _p(y)))
+
     def fill_x_synthetic(self, offset=0):
         _check(lib().hspmv_fill_x_synthetic(self.h, C.c_int64(offset)))
 
@@ -437,6 +442,7 @@ class CSRk_Graph:
 
     def setY(self, y):
         self._y = y
+        self.A.set_y(y)
 
     def SpMV(self, y=None):
         """SpMV() launches on the device-resident vectors (CUDA flavour, csrk.cuh:347).

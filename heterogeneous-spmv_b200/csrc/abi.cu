@@ -882,6 +882,13 @@ int hspmv_get_y(hspmv_matrix *A, void *y_host, int original_order) {
   return HSPMV_OK;
 }
 
+int hspmv_set_y(hspmv_matrix *A, const void *y_host) {
+  if (!A || !y_host) return fail(HSPMV_EINVAL, "null");
+  CU(cudaMemcpyAsync(A->d_y, y_host, (size_t)A->m * A->vsize(), cudaMemcpyHostToDevice, A->stream));
+  CU(cudaStreamSynchronize(A->stream));
+  return HSPMV_OK;
+}
+
 void *hspmv_x_device(hspmv_matrix *A) { return A ? A->d_x : nullptr; }
 void *hspmv_y_device(hspmv_matrix *A) { return A ? A->d_y : nullptr; }
 

@@ -159,6 +159,9 @@ int hspmv_set_x(hspmv_matrix *A, const void *x_host);
  * undoes the Band-k row permutation (y_out[perm[i]] = y[i]); 0 returns the kernel's order,
  * which is what spmv-csrk/spmv.cpp:203 compares against y_csrser[perm[i]]. */
 int hspmv_get_y(hspmv_matrix *A, void *y_host, int original_order);
+/* Replaces CSRk_Graph::setY (cuda-spmv-csrk/cuda/csrk.cu:103-107): uploads m entries into the
+ * handle's device y as they are (kernel row order). */
+int hspmv_set_y(hspmv_matrix *A, const void *y_host);
 /* Library-owned device vectors of the handle (x in kernel order, n entries; y, m entries). */
 void *hspmv_x_device(hspmv_matrix *A);
 void *hspmv_y_device(hspmv_matrix *A);

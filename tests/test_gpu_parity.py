@@ -1,0 +1,298 @@
+"""Parity of the CUDA path against the oracle, through the C ABI (ctypes -> libhspmv.so).
+Run on the B200 box: python -m pytest tests -m gpu.
+
+Bar (BASELINE.json north_star): index work bit-exact; |y - y_ref|_i <= 1e-12 * sum_j |a_ij x_j|
+in fp64, 1e-5 in fp32 (conftest.assert_within_bound)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import assert_within_bound
+
+pytestmark = pytest.mark.gpu
+
+DT = [np.float64, np.float32]
+DT_IDS = ["f64", "f32"]
+
+
+def check_csr(hs, oracle, gen, rp, ci, v, algos, x=None, opts=None, what=""):
+    dtype = v.dtype
+    n = len(rp) - 1
+    x = gen.vector_x(n, dtype) if x is None else x.astype(dtype)
+    y_ref = oracle.csr_spmv(rp, ci, v, x)
+    scale = oracle.abs_rowsum(rp, ci, v, x)
+    A = hs.Matrix.from_csr(rp, ci, v)
+    for k_, val in (opts or {}).items():
+        A.set_option(k_, val)
+    A.set_x(x)
+    for algo in algos:
+        A.set_y(np.full(n, np.nan, dtype))   # poison: rows a kernel forgets to write are caught
+        A.spmv(algo)
+        y = A.get_y()
+        assert_within_bound(y, y_ref, scale, dtype, "%s %s [%s]" % (what, hs.ALGO_NAMES[algo], A.last_kernel()))
+    A.close()
+
+
+@pytest.mark.parametrize("dtype", DT, ids=DT_IDS)
+def test_csr_regular_matrices(dtype, hs, oracle, gen):
+    algos = [hs.ALGO_CSR_VECTOR, hs.ALGO_CSR_STREAM, hs.ALGO_CSR_MERGE, hs.ALGO_AUTO]
+    for name, (rp, ci, v) in [("lap64rcm", gen.laplace2d_5pt(64, dtype=dtype, rcm=True, mode="varied")),
+                              ("lap33", gen.laplace2d_5pt(33, dtype=dtype)),
+                              ("st27_16", gen.stencil27(16, dtype=dtype, mode="varied")),
+                              ("shell", gen.banded_shell(20000, dtype=dtype, band=400))]:
+        check_csr(hs, oracle, gen, rp, ci, v, algos, what=name)
+
+
+@pytest.mark.parametrize("dtype", DT, ids=DT_IDS)
+def test_csr_ragged_empty_and_long_rows(dtype, hs, oracle, gen):
+    algos = [hs.ALGO_CSR_VECTOR, hs.ALGO_CSR_STREAM, hs.ALGO_CSR_MERGE, hs.ALGO_AUTO]
+    check_csr(hs, oracle, gen, *gen.random_ragged(3000, max_len=70, dtype=dtype), algos, what="ragged")
+    check_csr(hs, oracle, gen, *gen.random_ragged(257, max_len=257, dtype=dtype, empty_frac=0.5), algos, what="ragged-half-empty")
+    check_csr(hs, oracle, gen, *gen.rmat(13, 8, dtype=dtype), algos, what="rmat13")
+    # leading / trailing empty rows, one row longer than the block-per-row threshold and than a merge tile
+    n = 9000
+    lens = np.zeros(n, np.int64)
+    lens[5] = 8999
+    lens[6:40] = 3
+    lens[100] = 4100
+    lens[8000:8990] = 1
+    rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    rng = np.random.default_rng(1)
+    ci = np.concatenate([np.sort(rng.choice(n, size=l, replace=False)) for l in lens]).astype(np.int32)
+    v = (rng.integers(1, 64, size=len(ci)) / 64.0).astype(dtype)
+    check_csr(hs, oracle, gen, rp, ci, v, algos, what="long-rows")
+    for vec in (1, 2, 4, 8, 16, 32):   # forced lane counts incl. mismatched ones
+        check_csr(hs, oracle, gen, rp, ci, v, [hs.ALGO_CSR_VECTOR, hs.ALGO_CSR_STREAM], opts={hs.OPT_VEC: vec}, what="long-rows vec=%d" % vec)
+    # tiny capacity: every tile takes the direct (non-staged) path; tiny merge tile: rows span many tiles
+    check_csr(hs, oracle, gen, rp, ci, v, [hs.ALGO_CSR_STREAM, hs.ALGO_CSR_MERGE],
+              opts={hs.OPT_STAGE_NNZ: 64, hs.OPT_MERGE_TILE: 64, hs.OPT_ROWS_PER_TILE: 7}, what="long-rows tiny tiles")
+
+
+@pytest.mark.parametrize("dtype", DT, ids=DT_IDS)
+def test_csr_degenerate_shapes(dtype, hs, oracle, gen):
+    algos = [hs.ALGO_CSR_VECTOR, hs.ALGO_CSR_STREAM, hs.ALGO_CSR_MERGE, hs.ALGO_AUTO]
+    # 1x1, single dense row, all-empty matrix, diagonal
+    check_csr(hs, oracle, gen, np.array([0, 1], np.int32), np.array([0], np.int32), np.array([2.5], dtype), algos, what="1x1")
+    n = 300
+    rp = np.zeros(n + 1, np.int32)
+    rp[1:] = n
+    check_csr(hs, oracle, gen, rp, np.arange(n, dtype=np.int32), np.full(n, 0.5, dtype), algos, what="one dense row")
+    check_csr(hs, oracle, gen, np.zeros(n + 1, np.int32), np.zeros(0, np.int32), np.zeros(0, dtype), algos, what="empty matrix")
+    check_csr(hs, oracle, gen, np.arange(n + 1, dtype=np.int32), np.arange(n, dtype=np.int32), np.full(n, -1.5, dtype), algos, what="diagonal")
+
+
+def test_x_with_inf_outside_the_row_pattern(hs, oracle, gen):
+    """Masked lanes must be selected away, not multiplied by zero."""
+    rp, ci, v = gen.random_ragged(600, max_len=9, dtype=np.float64, seed=11)
+    x = gen.vector_x(600)
+    unused = np.setdiff1d(np.arange(600), ci)
+    assert unused.size > 0
+    x[unused] = np.inf
+    check_csr(hs, oracle, gen, rp, ci, v, [hs.ALGO_CSR_VECTOR, hs.ALGO_CSR_STREAM, hs.ALGO_CSR_MERGE], x=x, what="inf")
+
+
+CSRK_CASES = [
+    ("laplace2d_5pt", {"g": 64, "rcm": True, "mode": "varied"}, 2, [16]),
+    ("laplace2d_5pt", {"g": 64, "rcm": True}, 3, [8, 8]),
+    ("stencil27", {"g": 16, "mode": "varied"}, 2, [32]),
+    ("stencil27", {"g": 16, "mode": "varied"}, 3, [20, 10]),
+    ("stencil27", {"g": 16}, 3, [3, 2]),            # tiny groups
+    ("stencil27", {"g": 12}, 2, [100000]),           # a single super-row, far over the stage capacity
+    ("banded_shell", {"n": 20000, "band": 400}, 3, [9, 12]),
+    ("banded_shell", {"n": 20000, "band": 400}, 2, [96]),
+    ("random_ragged", {"n": 2000, "diag": True, "max_len": 50}, 3, [6, 5]),
+]
+
+
+@pytest.mark.parametrize("dtype", DT, ids=DT_IDS)
+@pytest.mark.parametrize("case", CSRK_CASES, ids=["%s-k%d-%s" % (c[0], c[2], "x".join(map(str, c[3]))) for c in CSRK_CASES])
+def test_csrk_matches_oracle(case, dtype, hs, oracle, gen):
+    g, kw, k, sizes = case
+    rp, ci, v = getattr(gen, g)(dtype=dtype, **kw)
+    n = len(rp) - 1
+    x = gen.vector_x(n, dtype)
+    o = oracle.bandk_build(rp, ci, k, sizes)
+    r2, c2, v2 = oracle.bandk_reorder(o["perm"], rp, ci, v)
+    maps = [o["sr_ptr"]] + ([o["ssr_ptr"]] if k == 3 else [])
+    y_ref_perm = oracle.csrk_spmv(k, maps, r2, c2, v2, x[o["perm"]])
+    scale = oracle.abs_rowsum(rp, ci, v, x)
+
+    # reference-named interface, as spmv-csrk/spmv.cpp:139-187 uses it
+    A = hs.CSRk_Graph(n, n, len(ci), rp, ci, v, "SpMV", "", "HAND", False, k, sizes)
+    A.putInCSRkFormat()
+    got = A.A.csrk()
+    assert np.array_equal(A.getPermutation(), o["perm"])
+    assert np.array_equal(got["sr_ptr"], o["sr_ptr"])
+    if k == 3:
+        assert np.array_equal(got["ssr_ptr"], o["ssr_ptr"])
+    assert A.getNumCoarsestRows() == len(maps[-1]) - 1
+    d_rp, d_ci, d_v = A.A.download()      # the REORDERED matrix is what lives in HBM
+    assert np.array_equal(d_rp, r2.astype(np.int32)) and np.array_equal(d_ci, c2.astype(np.int32)) and np.array_equal(d_v, v2)
+    A.setX(x)
+    y = np.full(n, np.nan, dtype)
+    A.SpMV(y)
+    assert_within_bound(y, y_ref_perm, scale[o["perm"]], dtype, "CSRk_Graph.SpMV [%s]" % A.A.last_kernel())
+    # the reference driver's own check: y[i] vs y_csrser[perm[i]]
+    y_csr = oracle.csr_spmv(rp, ci, v, x)
+    assert_within_bound(y, y_csr[o["perm"]], scale[o["perm"]], dtype, "vs serial CSR")
+    assert_within_bound(A.A.get_y(original_order=True), y_csr, scale, dtype, "original order")
+    # every kernel knob; plain-CSR kernels must also work on the reordered matrix
+    for vec in (1, 2, 4, 8, 16, 32):
+        for warps, stages in ((4, 2), (8, 3), (16, 2)):
+            A.A.set_option(hs.OPT_VEC, vec)
+            A.A.set_option(hs.OPT_WARPS, warps)
+            A.A.set_option(hs.OPT_STAGES, stages)
+            A.SpMV(y)
+            assert_within_bound(y, y_ref_perm, scale[o["perm"]], dtype, "knobs [%s]" % A.A.last_kernel())
+    A.A.set_option(hs.OPT_VEC, 0)
+    for algo in (hs.ALGO_CSR_VECTOR, hs.ALGO_CSR_STREAM, hs.ALGO_CSR_MERGE):
+        A.A.spmv(algo)
+        assert_within_bound(A.A.get_y(False), y_ref_perm, scale[o["perm"]], dtype, hs.ALGO_NAMES[algo])
+
+
+def test_csrk_against_golden_reference_vectors(hs, oracle, gen):
+    """y from the reference's own OpenMP CSR-k / CSR runs, stored in tests/golden."""
+    import importlib.util
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    spec = importlib.util.spec_from_file_location("mg", os.path.join(gold, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    for path in sorted(glob.glob(os.path.join(gold, "*.npz"))):
+        g = np.load(path)
+        fn, kw, k, sizes = mg.CASES[os.path.basename(path)[:-4]]
+        for dtype, tag in ((np.float32, "f32"), (np.float64, "f64")):
+            rp, ci, v = getattr(gen, fn)(dtype=dtype, **kw)
+            x = gen.vector_x(len(rp) - 1, dtype)
+            scale = oracle.abs_rowsum(rp, ci, v, x)
+            A = hs.Matrix.from_csr(rp, ci, v)
+            A.set_x(x)
+            for algo in (hs.ALGO_CSR_VECTOR, hs.ALGO_CSR_STREAM, hs.ALGO_CSR_MERGE):
+                A.spmv(algo)
+                assert_within_bound(A.get_y(), g["y_csr_" + tag], scale, dtype, path + " csr")
+            A.build_csrk(k, sizes)
+            c = A.csrk()
+            assert np.array_equal(c["perm"], g["perm"]) and np.array_equal(c["sr_ptr"], g["sr_ptr"])
+            if k == 3:
+                assert np.array_equal(c["ssr_ptr"], g["ssr_ptr"])
+            A.set_x(x)
+            A.spmv(hs.ALGO_CSRK)
+            assert_within_bound(A.get_y(False), g["y_csrk_" + tag], scale[g["perm"]], dtype, path + " csrk")
+            A.close()
+
+
+def test_csr3_file_direct_load(tmp_path, hs, oracle, gen):
+    rp, ci, v = gen.stencil27(12, mode="varied")
+    o = oracle.bandk_build(rp, ci, 3, [20, 10])
+    r2, c2, v2 = oracle.bandk_reorder(o["perm"], rp, ci, v)
+    p = str(tmp_path / "m.csr3")
+    hs.write_csr3(p, o["ssr_ptr"], o["sr_ptr"], r2, c2, v2)
+    d = hs.read_csr3(p)
+    A = hs.Matrix.from_csrk(d["sr_ptr"], d["row_ptr"], d["col_idx"], d["val"], ssr_ptr=d["ssr_ptr"])
+    assert A.info()["k"] == 3
+    x = gen.vector_x(len(rp) - 1)
+    xp = x[o["perm"]]
+    A.set_x(xp)                     # a .csr3 carries no permutation: vectors are in file order
+    A.spmv(hs.ALGO_CSRK)
+    y_ref = oracle.csrk_spmv(3, [o["sr_ptr"], o["ssr_ptr"]], r2, c2, v2, xp)
+    assert_within_bound(A.get_y(), y_ref, oracle.abs_rowsum(rp, ci, v, x)[o["perm"]], np.float64, "csr3")
+    B = hs.Matrix.from_csrk(d["sr_ptr"], d["row_ptr"], d["col_idx"], d["val"])   # k = 2 view
+    B.set_x(xp)
+    B.spmv(hs.ALGO_CSRK)
+    assert_within_bound(B.get_y(), y_ref, oracle.abs_rowsum(rp, ci, v, x)[o["perm"]], np.float64, "csr2")
+
+
+@pytest.mark.parametrize("dtype", DT, ids=DT_IDS)
+def test_device_generators_match_numpy(dtype, hs, gen):
+    for kind, g, fn in ((27, 9, gen.stencil27), (27, 2, gen.stencil27), (27, 1, gen.stencil27),
+                        (5, 17, gen.laplace2d_5pt), (5, 2, gen.laplace2d_5pt)):
+        for mode, mname in ((0, "classic"), (1, "varied")):
+            rp, ci, v = fn(g, dtype=dtype, mode=mname)
+            A = hs.Matrix.stencil(kind, g, dtype, mode)
+            d = A.download()
+            assert np.array_equal(d[0], rp) and np.array_equal(d[1], ci) and np.array_equal(d[2], v), (kind, g, mname)
+            A.close()
+    # a row block with localised columns (multi-GPU shard)
+    full = gen.stencil27(10, dtype=dtype, mode="varied")
+    lo, hi = 333, 777
+    A = hs.Matrix.stencil(27, 10, dtype, 1, row_lo=lo, row_hi=hi)
+    cmin, cmax = A.col_range()
+    e0, e1 = full[0][lo], full[0][hi]
+    assert (cmin, cmax) == (full[1][e0:e1].min(), full[1][e0:e1].max())
+    A.close()
+    B = hs.Matrix.stencil(27, 10, dtype, 1, row_lo=lo, row_hi=hi, col_shift=cmin, n_cols=cmax - cmin + 1)
+    d = B.download()
+    assert np.array_equal(d[0], full[0][lo:hi + 1] - e0) and np.array_equal(d[1], full[1][e0:e1] - cmin)
+    B.fill_x_synthetic(cmin)
+    B.spmv()
+    import oracle as O
+    y_ref = O.csr_spmv(full[0], full[1], full[2], gen.vector_x(1000, dtype))[lo:hi]
+    sc = O.abs_rowsum(full[0], full[1], full[2], gen.vector_x(1000, dtype))[lo:hi]
+    assert_within_bound(B.get_y(), y_ref, sc, dtype, "row block")
+
+
+def test_merge_tile_table_device_equals_host(hs, gen):
+    rp, ci, v = gen.rmat(12, 8)
+    A = hs.Matrix.from_csr(rp, ci, v)
+    A.set_option(hs.OPT_MERGE_TILE, 256)
+    A.set_x(gen.vector_x(len(rp) - 1))
+    A.spmv(hs.ALGO_CSR_MERGE)
+    tile, table = A.merge_tile_rows()
+    assert tile == 256 and np.array_equal(table, hs.merge_tile_rows_host(rp, 256))
+
+
+def test_end_to_end_host_call_and_spmv_h_compat(hs, oracle, gen):
+    rp, ci, v = gen.stencil27(14, mode="varied")
+    n = len(rp) - 1
+    x = gen.vector_x(n)
+    y_ref = oracle.csr_spmv(rp, ci, v, x)
+    scale = oracle.abs_rowsum(rp, ci, v, x)
+    # spmv.h:11-12 signature; second call hits the upload cache
+    y = np.zeros(n)
+    before = hs.launch_count()
+    hs.omp_spmv(n, n, len(ci), rp, ci, v, x, y)
+    assert_within_bound(y, y_ref, scale, np.float64, "omp_spmv")
+    y2 = np.zeros(n)
+    hs.omp_spmv(n, n, len(ci), rp, ci, v, 2 * x, y2)
+    assert_within_bound(y2, 2 * y_ref, 2 * scale, np.float64, "omp_spmv cached")
+    assert hs.launch_count() >= before + 2
+    hs.lib().hspmv_omp_spmv_cache_clear()
+    # CSR-k handle: host x in original order -> host y in original order
+    A = hs.Matrix.from_csr(rp, ci, v)
+    A.build_csrk(3, [20, 10])
+    assert_within_bound(A.spmv_host(x), y_ref, scale, np.float64, "spmv_host csrk")
+    ms = A.spmv_timed(hs.ALGO_CSRK, warmup=2, iters=5, flush_l2=True)
+    assert ms.shape == (5,) and np.all(ms > 0)
+    A.set_option(hs.OPT_L2_PERSIST_X, 1)
+    assert_within_bound(A.spmv_host(x), y_ref, scale, np.float64, "with L2 window")
+
+
+def test_linearity_and_scaling_properties_at_config2_size(hs, gen):
+    """Size-independent properties at BASELINE config-2 size (27-pt 100^3, 26.5 M nnz), generated
+    in HBM: A(ax+by) = aAx + bAy, classic stencil rows sum to {<=0 interior = 0}, all kernels agree."""
+    g = 100
+    A = hs.Matrix.stencil(27, g, np.float64, 0)
+    n = g ** 3
+    assert A.info()["nnz"] == 298 ** 3
+    x1 = gen.vector_x(n)
+    x2 = np.cos(np.arange(n) * 0.001)
+    ys = {}
+    for algo in (hs.ALGO_CSR_VECTOR, hs.ALGO_CSR_STREAM, hs.ALGO_CSR_MERGE):
+        ys[algo] = A.spmv_host(x1, algo)
+    ref = ys[hs.ALGO_CSR_VECTOR]
+    for algo, y in ys.items():
+        assert np.max(np.abs(y - ref)) <= 1e-12 * 27 * 26 * 2, hs.ALGO_NAMES[algo]
+    y2 = A.spmv_host(x2, hs.ALGO_CSR_STREAM)
+    y12 = A.spmv_host(3.0 * x1 - 0.5 * x2, hs.ALGO_CSR_STREAM)
+    assert np.max(np.abs(y12 - (3.0 * ys[hs.ALGO_CSR_STREAM] - 0.5 * y2))) < 1e-9
+    ones = A.spmv_host(np.ones(n), hs.ALGO_CSR_STREAM)
+    i = np.arange(n)
+    xx, yy, zz = i % g, (i // g) % g, i // (g * g)
+    interior = (xx > 0) & (xx < g - 1) & (yy > 0) & (yy < g - 1) & (zz > 0) & (zz < g - 1)
+    assert np.all(ones[interior] == 0.0) and np.all(ones[~interior] > 0)
+    # spot rows against the numpy generator + oracle
+    import oracle as O
+    rp, ci, v = gen.stencil27(g, row_lo=500000, row_hi=500200)
+    y_rows = O.csr_spmv(rp, ci, v, x1)
+    assert np.max(np.abs(y_rows - ys[hs.ALGO_CSR_STREAM][500000:500200])) < 1e-10

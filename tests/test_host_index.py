@@ -1,0 +1,208 @@
+"""CPU tests of the product's host side (no device needed): Band-k builder, reorderA, text I/O,
+heuristics, partition / bins / merge tiles -- bit-exact against the oracle."""
+import glob
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import partition_oracle as PO
+
+
+def test_library_exports_every_declared_symbol(hs):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "hspmv.h")).read()
+    declared = set(re.findall(r"\b(hspmv_[a-z0-9_]+)\s*\(", hdr))
+    declared.discard("hspmv_matrix")
+    assert len(declared) >= 35
+    out = subprocess.check_output(["nm", "-D", "--defined-only", hs.LIB_PATH]).decode()
+    exported = set(re.findall(r" T (hspmv_[a-z0-9_]+)", out))
+    assert declared <= exported, "declared but not exported: %s" % sorted(declared - exported)
+    L = hs.lib()
+    for name in declared:
+        assert hasattr(L, name)
+    assert L.hspmv_version() >= 100
+
+
+def test_no_cpu_fallback_without_device(hs, gen):
+    """On a box without a usable sm_100 device the compute entry points fail loudly."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    rp, ci, v = gen.laplace2d_5pt(8)
+    with pytest.raises(hs.HspmvError):
+        hs.Matrix.from_csr(rp, ci, v)
+
+
+CASES = [
+    ("laplace2d_5pt", {"g": 30}, 3, [7, 8]),
+    ("laplace2d_5pt", {"g": 50, "rcm": True}, 2, [16]),
+    ("laplace2d_5pt", {"g": 50, "rcm": True}, 3, [8, 8]),
+    ("stencil27", {"g": 14}, 2, [32]),
+    ("stencil27", {"g": 14, "mode": "varied"}, 3, [20, 10]),
+    ("stencil27", {"g": 10}, 3, [1, 1]),
+    ("stencil27", {"g": 10}, 2, [100000]),     # one super-row
+    ("banded_shell", {"n": 6000, "band": 150}, 3, [9, 12]),
+    ("banded_shell", {"n": 6000, "band": 150}, 2, [96]),
+    ("random_ragged", {"n": 500, "diag": True}, 3, [5, 4]),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=["%s-k%d-%s" % (c[0], c[2], "x".join(map(str, c[3]))) for c in CASES])
+def test_bandk_host_bit_exact(case, hs, oracle, gen):
+    g, kw, k, sizes = case
+    rp, ci, v = getattr(gen, g)(**kw)
+    a = hs.bandk_host(rp, ci, k, sizes)
+    b = oracle.bandk_build(rp, ci, k, sizes)
+    for key in b:
+        assert np.array_equal(a[key], b[key]), key
+    assert sorted(a["perm"].tolist()) == list(range(len(rp) - 1))
+    assert a["sr_ptr"][0] == 0 and a["sr_ptr"][-1] == len(rp) - 1
+    for dt in (np.float32, np.float64):
+        r1 = hs.reorder_host(a["perm"], rp, ci, v.astype(dt))
+        r2 = oracle.bandk_reorder(b["perm"], rp, ci, v.astype(dt))
+        for p, q in zip(r1, r2):
+            assert np.array_equal(p, q)
+
+
+def test_bandk_golden_vectors(hs, gen):
+    import importlib.util
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    spec = importlib.util.spec_from_file_location("mg", os.path.join(gold, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    for path in sorted(glob.glob(os.path.join(gold, "*.npz"))):
+        g = np.load(path)
+        fn, kw, k, sizes = mg.CASES[os.path.basename(path)[:-4]]
+        rp, ci, v = getattr(gen, fn)(**kw)
+        a = hs.bandk_host(rp, ci, k, sizes)
+        assert np.array_equal(a["perm"], g["perm"]) and np.array_equal(a["sr_ptr"], g["sr_ptr"]), path
+        if k == 3:
+            assert np.array_equal(a["ssr_ptr"], g["ssr_ptr"]), path
+
+
+def test_bandk_rejects_directed_graph_without_upper_entries(hs):
+    # a "star" stored one-sided: every row references column 0 only, so every coarse vertex but
+    # the first has no upper/diagonal entry -- the reference would read out of bounds
+    n = 64
+    rp = np.arange(n + 1, dtype=np.int32)
+    ci = np.zeros(n, dtype=np.int32)
+    with pytest.raises(hs.HspmvError):
+        hs.bandk_host(rp, ci, 2, [4])
+    import oracle as O
+    with pytest.raises(RuntimeError):
+        O.bandk_build(rp, ci, 2, [4])
+
+
+def test_heuristics_reproduce_reference_formulas(hs):
+    # 30x30 Laplacian, Volta formula -> {7, 8} (reformat-auto prints "78")
+    sizes, vec, bdy = hs.auto_params(4380, 900, hs.ARCH_VOLTA)
+    assert sizes == [7, 8] and vec == 0 and bdy == 12
+    # helpers/params.txt style spot checks of the Ampere bands (spmv-auto-ampere.cu:130-158)
+    import math
+    for nnz, n in [(4996000, 1000000), (26463592, 1000000), (52500000, 1500000), (10, 1), (5000, 50)]:
+        d = nnz / n
+        ssrs = math.floor(0.5 + (9.175 - 1.32 * math.log(d)))
+        srs = math.floor(0.5 + (20.5 - 3.5 * math.log(d)))
+        vec = 0
+        if 8 < d <= 16:
+            vec, srs = 4, ssrs * 4
+        elif 16 < d <= 32:
+            vec = 8
+            ssrs = math.floor(ssrs * 2.5 + 0.5)
+            srs = ssrs * 3
+        elif 32 < d <= 64:
+            vec = 16
+            ssrs *= 2
+            srs = ssrs * 2
+        elif d > 64:
+            vec = 32
+            ssrs = math.floor(ssrs * 2.7 + 0.5)
+            srs = math.floor(ssrs / 4 + 0.5)
+        got, gvec, _ = hs.auto_params(nnz, n, hs.ARCH_AMPERE)
+        assert got == [max(ssrs, 1), max(srs, 1)] and gvec == vec
+    sizes, vec, _ = hs.auto_params(26463592, 1000000, hs.ARCH_B200)
+    assert sizes[0] % (32 // vec) == 0 and 600 <= sizes[0] * 26.46 <= 1000
+
+
+def test_text_io_round_trip(tmp_path, hs, gen, oracle):
+    rp, ci, v = gen.stencil27(7, mode="varied")
+    for base in (0, 1):
+        for dt in (np.float32, np.float64):
+            p = str(tmp_path / ("m%d.mtx.rcm.csr" % base))
+            hs.my_write_csr(p, rp, ci, v.astype(dt), index_base=base)
+            # our writer is readable by the reference-grammar reader restated in the oracle
+            m, n, o_rp, o_ci, o_v = oracle.read_csr_text(p, base)
+            assert np.array_equal(o_rp, rp) and np.array_equal(o_ci, ci) and np.array_equal(o_v, v)
+            m2, n2, nnz2, r, c, w = hs.my_read_csr(p, index_base=base, dtype=dt)
+            assert (m2, n2, nnz2) == (343, 343, len(ci)) and w.dtype == dt
+            assert np.array_equal(r, rp) and np.array_equal(c, ci) and np.array_equal(w, v.astype(dt))
+    # generator's python writer (helpers/converter.m layout) is read identically
+    p = str(tmp_path / "py.mtx.csr")
+    gen.write_csr_text(p, rp, ci, v, base=0)
+    _, _, _, r, c, w = hs.my_read_csr(p, 0, np.float64)
+    assert np.array_equal(r, rp) and np.array_equal(c, ci) and np.array_equal(w, v)
+    # exotic number spellings fall back to strtod
+    with open(str(tmp_path / "e.csr"), "w") as f:
+        f.write("2 2 3\n0 2 3 \n0 1 1 \n1e-3 -2.5E+2 0.1234567890123456789 \n")
+    _, _, _, r, c, w = hs.my_read_csr(str(tmp_path / "e.csr"), 0, np.float64)
+    assert w.tolist() == [1e-3, -250.0, 0.1234567890123456789]
+    with pytest.raises(hs.HspmvError):
+        hs.my_read_csr(str(tmp_path / "missing.csr"))
+    with open(str(tmp_path / "short.csr"), "w") as f:
+        f.write("2 2 3\n0 2 3 \n0 1 \n")
+    with pytest.raises(hs.HspmvError):
+        hs.my_read_csr(str(tmp_path / "short.csr"))
+
+
+def test_csr3_round_trip_and_layout(tmp_path, hs, gen):
+    rp, ci, v = gen.laplace2d_5pt(30, dtype=np.float32)
+    o = hs.bandk_host(rp, ci, 3, [7, 8])
+    r2, c2, v2 = hs.reorder_host(o["perm"], rp, ci, v)
+    p = str(tmp_path / "lap30.csr3")
+    hs.write_csr3(p, o["ssr_ptr"], o["sr_ptr"], r2, c2, v2)
+    text = open(p).read()
+    # header of SURVEY Appendix B: "16 124 900 900 4380"
+    assert text.split("\n")[0].split() == ["16", "124", "900", "900", "4380"]
+    body = text.split("\n", 1)[1].split()
+    assert body[:17] == [str(t) for t in o["ssr_ptr"]]
+    assert body[-1] == "%.6f" % v2[-1]
+    d = hs.read_csr3(p, np.float32)
+    assert np.array_equal(d["ssr_ptr"], o["ssr_ptr"]) and np.array_equal(d["sr_ptr"], o["sr_ptr"])
+    assert np.array_equal(d["row_ptr"], r2) and np.array_equal(d["col_idx"], c2) and np.array_equal(d["val"], v2)
+
+
+@pytest.mark.parametrize("parts", [1, 2, 3, 8])
+def test_partition_bit_exact(parts, hs, gen):
+    for rp, ci, v in (gen.stencil27(12), gen.random_ragged(3000, max_len=60), gen.laplace2d_5pt(40, rcm=True)):
+        a = hs.partition_rows(rp, parts)
+        b = PO.partition_rows(rp, parts)
+        assert np.array_equal(a, b)
+        assert a[0] == 0 and a[-1] == len(rp) - 1 and np.all(np.diff(a) >= 0)
+        nnz = rp[a[1:]] - rp[a[:-1]]
+        assert nnz.sum() == rp[-1]
+        if parts > 1 and rp[-1] > 0:
+            assert nnz.max() - nnz.min() <= 2 * int(np.diff(rp).max()) + 1
+        for p in range(parts):
+            assert hs.block_col_range(rp, ci, a[p], a[p + 1]) == PO.col_range(rp, ci, a[p], a[p + 1])
+    # snapping to super-row boundaries
+    rp, ci, v = gen.stencil27(12)
+    o = hs.bandk_host(rp, ci, 2, [32])
+    r2, _, _ = hs.reorder_host(o["perm"], rp, ci, v)
+    a = hs.partition_rows(r2.astype(np.int32), 4, align_ptr=o["sr_ptr"])
+    assert np.array_equal(a, PO.partition_rows(r2, 4, o["sr_ptr"]))
+    assert set(a.tolist()) <= set(o["sr_ptr"].tolist())
+
+
+def test_bins_and_tiles_bit_exact(hs, gen):
+    lens = np.array([0, 1, 4, 5, 8, 9, 16, 17, 32, 33, 64, 65, 4096, 4097, 0, 3], dtype=np.int64)
+    rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    rows, bp = hs.bin_rows_host(rp)
+    orows, obp = PO.bin_rows(rp)
+    assert np.array_equal(rows, orows) and np.array_equal(bp, obp)
+    assert PO.bin_of_len(lens).tolist() == [0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 0, 1]
+    for rp in (gen.random_ragged(5000, max_len=70)[0], gen.stencil27(9)[0], rp):
+        for tile in (4, 64, 4096):
+            assert np.array_equal(hs.merge_tile_rows_host(rp, tile), PO.tile_rows(rp, tile))
