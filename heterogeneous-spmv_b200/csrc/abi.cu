@@ -94,6 +94,8 @@ struct hspmv_matrix {
 
   int64_t opt[16] = {0};
   cudaStream_t stream = nullptr; // handle's own stream (timed runs, set_x/get_y)
+  cudaStream_t last_stream = nullptr; // stream of the most recent hspmv_spmv (may be the caller's)
+  bool last_stream_valid = false;
   void *d_flush = nullptr;
   size_t flush_bytes = 0;
   bool l2_window_set = false;
@@ -504,6 +506,8 @@ int dispatch(hspmv_matrix *A, int algo, const void *dx, void *dy, cudaStream_t s
 }
 
 int do_spmv(hspmv_matrix *A, int algo, const void *dx, void *dy, cudaStream_t st) {
+  A->last_stream = st;
+  A->last_stream_valid = true;
   return A->dtype == HSPMV_F64 ? dispatch<double>(A, algo, dx, dy, st) : dispatch<float>(A, algo, dx, dy, st);
 }
 
@@ -867,6 +871,8 @@ int hspmv_set_x(hspmv_matrix *A, const void *x_host) {
 int hspmv_get_y(hspmv_matrix *A, void *y_host, int original_order) {
   if (!A || !y_host) return fail(HSPMV_EINVAL, "null");
   const size_t vs = A->vsize();
+  // the last SpMV may have been enqueued on the caller's stream: order the read-back after it
+  if (A->last_stream_valid && A->last_stream != A->stream) CU(cudaStreamSynchronize(A->last_stream));
   if (original_order && A->d_perm) {
     const int grid = grid_for(A->m, 256, A->dev.sms * 16);
     if (A->dtype == HSPMV_F64)
