@@ -291,10 +291,10 @@ int run_csr_vector(hspmv_matrix *A, const T *x, T *y, cudaStream_t st) {
   return HSPMV_OK;
 }
 
-template <typename T, int VEC>
-int launch_csrk(hspmv_matrix *A, const hspmv::CsrkParams<T> &p, int grid, int warps, size_t smem,
-                cudaStream_t st) {
-  auto kern = hspmv::csrk_tma_kernel<T, VEC>;
+template <typename T, int VEC, int CH>
+int launch_csrk_ch(hspmv_matrix *A, const hspmv::CsrkParams<T> &p, int grid, int warps, size_t smem,
+                   cudaStream_t st) {
+  auto kern = hspmv::csrk_tma_kernel<T, VEC, CH>;
   static size_t configured[64] = {0}; // per device: opt-in shared memory already granted
   size_t &have = configured[A->dev.device & 63];
   if (smem > have) {
@@ -304,6 +304,14 @@ int launch_csrk(hspmv_matrix *A, const hspmv::CsrkParams<T> &p, int grid, int wa
   kern<<<grid, warps * 32, smem, st>>>(p);
   LAUNCHED();
   return HSPMV_OK;
+}
+
+template <typename T, int VEC>
+int launch_csrk(hspmv_matrix *A, const hspmv::CsrkParams<T> &p, int grid, int warps, size_t smem,
+                cudaStream_t st, int chunk) {
+  if (chunk >= 16) return launch_csrk_ch<T, VEC, 16>(A, p, grid, warps, smem, st);
+  if (chunk >= 8) return launch_csrk_ch<T, VEC, 8>(A, p, grid, warps, smem, st);
+  return launch_csrk_ch<T, VEC, 4>(A, p, grid, warps, smem, st);
 }
 
 // CSRK (k = 2,3 after hspmv_build_csrk / hspmv_create_csrk) and CSR_STREAM (k = 1, fixed-row tiles)
@@ -318,6 +326,12 @@ int run_csrk(hspmv_matrix *A, bool stream_mode, const T *x, T *y, cudaStream_t s
   if (warps > 16) warps = 16;
   int stages = (int)A->opt[HSPMV_OPT_STAGES];
   if (stages <= 0) stages = 2;
+  int chunk = (int)A->opt[HSPMV_OPT_CHUNK];
+  if (chunk <= 0) { // gathers in flight per lane: enough to cover one row's share in <= 2 rounds
+    const double per_lane = mean / vec;
+    chunk = per_lane > 12 ? 16 : per_lane > 5 ? 8 : 4;
+  }
+  chunk = chunk >= 16 ? 16 : chunk >= 8 ? 8 : 4;
 
   hspmv::CsrkParams<T> p;
   p.m = A->m;
@@ -388,17 +402,17 @@ int run_csrk(hspmv_matrix *A, bool stream_mode, const T *x, T *y, cudaStream_t s
 
   int rc;
   switch (vec) {
-  case 1: rc = launch_csrk<T, 1>(A, p, (int)grid, warps, smem, st); break;
-  case 2: rc = launch_csrk<T, 2>(A, p, (int)grid, warps, smem, st); break;
-  case 4: rc = launch_csrk<T, 4>(A, p, (int)grid, warps, smem, st); break;
-  case 8: rc = launch_csrk<T, 8>(A, p, (int)grid, warps, smem, st); break;
-  case 16: rc = launch_csrk<T, 16>(A, p, (int)grid, warps, smem, st); break;
-  default: rc = launch_csrk<T, 32>(A, p, (int)grid, warps, smem, st); vec = 32; break;
+  case 1: rc = launch_csrk<T, 1>(A, p, (int)grid, warps, smem, st, chunk); break;
+  case 2: rc = launch_csrk<T, 2>(A, p, (int)grid, warps, smem, st, chunk); break;
+  case 4: rc = launch_csrk<T, 4>(A, p, (int)grid, warps, smem, st, chunk); break;
+  case 8: rc = launch_csrk<T, 8>(A, p, (int)grid, warps, smem, st, chunk); break;
+  case 16: rc = launch_csrk<T, 16>(A, p, (int)grid, warps, smem, st, chunk); break;
+  default: rc = launch_csrk<T, 32>(A, p, (int)grid, warps, smem, st, chunk); vec = 32; break;
   }
   if (rc) return rc;
   char name[160];
-  std::snprintf(name, sizeof(name), "csrk_tma<%s,vec=%d> k=%d grid=%d warps=%d stages=%d cap_nnz=%d cap_rows=%d%s",
-                sizeof(T) == 8 ? "f64" : "f32", vec, p.k, (int)grid, warps, stages, cap_nnz, cap_rows,
+  std::snprintf(name, sizeof(name), "csrk_tma<%s,vec=%d,ch=%d> k=%d grid=%d warps=%d stages=%d cap_nnz=%d cap_rows=%d%s",
+                sizeof(T) == 8 ? "f64" : "f32", vec, chunk, p.k, (int)grid, warps, stages, cap_nnz, cap_rows,
                 stream_mode ? " (CSR stream tiles)" : "");
   A->last_kernel = name;
   return HSPMV_OK;

@@ -236,8 +236,16 @@ struct SrCursor {
   int64_t cur, end, step;     // k < 3: cur, cur+step, ... < end
   int64_t s, s_step, n_ssr;   // k == 3: CTA walks super-super-rows s, s+s_step, ...
   const uint32_t *ssr_ptr;
+  uint32_t pre_lo, pre_hi;    // k == 3: super-row range of the NEXT super-super-row, loaded one
+                              // switch ahead so that its latency is off the warp's critical path
   int w, W;
   bool three;
+  __device__ __forceinline__ void prefetch_range(int64_t ss) {
+    if (ss < n_ssr) {
+      pre_lo = __ldg(ssr_ptr + ss);
+      pre_hi = __ldg(ssr_ptr + ss + 1);
+    }
+  }
   __device__ __forceinline__ bool next(int64_t &sr) {
     if (!three) {
       if (cur >= end) return false;
@@ -253,8 +261,9 @@ struct SrCursor {
       }
       s += s_step;
       if (s >= n_ssr) return false;
-      cur = (int64_t)__ldg(ssr_ptr + s) + w;
-      end = (int64_t)__ldg(ssr_ptr + s + 1);
+      cur = (int64_t)pre_lo + w;
+      end = (int64_t)pre_hi;
+      prefetch_range(s + s_step);
     }
   }
 };
@@ -269,7 +278,11 @@ __host__ __device__ inline size_t csrk_stage_bytes(int cap_nnz, int cap_rows, si
   return 16 + (size_t)(cap_rows + 8) * 4 + (size_t)(cap_nnz + 8) * 4 + (size_t)(cap_nnz + 8) * vsize;
 }
 
-template <typename T, int VEC>
+// Rows [r0,r1) of one super-row: row -> group of VEC lanes.  The nonzeros of a row are taken in
+// chunks of CH per lane; within a chunk every shared-memory read and every x gather is issued
+// before the first FMA, so a lane has CH independent gathers in flight (the gathers, not the
+// streamed matrix data, are what this loop waits for -- profiles/r1_stream_before.txt).
+template <typename T, int VEC, int CH>
 __device__ __forceinline__ void csrk_rows(int r0, int r1, const int *__restrict__ rp_w, int rbase,
                                           const int *__restrict__ ci_w, const T *__restrict__ val_w,
                                           int64_t ebase, const T *__restrict__ x, T *__restrict__ y,
@@ -286,15 +299,31 @@ __device__ __forceinline__ void csrk_rows(int r0, int r1, const int *__restrict_
       re = rp_w[r + 1 - rbase];
     }
     T acc = 0;
-#pragma unroll 4
-    for (int64_t j = rs + sub; j < re; j += VEC)
-      acc += val_w[j - ebase] * __ldg(x + ci_w[j - ebase]);
+    for (int64_t j0 = rs + sub - ebase; j0 < re - ebase; j0 += VEC * CH) {
+      int c[CH];
+      T v[CH], xv[CH];
+      const int64_t lim = re - ebase;
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        const int64_t j = j0 + u * VEC;
+        const bool ok = j < lim;
+        c[u] = ok ? ci_w[j] : 0;
+        v[u] = ok ? val_w[j] : (T)0;
+      }
+#pragma unroll
+      for (int u = 0; u < CH; ++u) xv[u] = __ldg(x + c[u]);
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        const T t = v[u] * xv[u];
+        acc += (j0 + u * VEC < lim) ? t : (T)0; // select, not multiply-by-zero: x[0] may be Inf/NaN
+      }
+    }
     acc = group_sum<T, VEC>(acc);
     if (active && sub == 0) y[r] = acc;
   }
 }
 
-template <typename T, int VEC>
+template <typename T, int VEC, int CH>
 __global__ void __launch_bounds__(512, 1) csrk_tma_kernel(const CsrkParams<T> p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
@@ -325,6 +354,8 @@ __global__ void __launch_bounds__(512, 1) csrk_tma_kernel(const CsrkParams<T> p)
     cur.cur = 0;
     cur.end = 0;
     cur.step = 0;
+    cur.pre_lo = cur.pre_hi = 0;
+    cur.prefetch_range(blockIdx.x);
   } else {
     cur.cur = (int64_t)blockIdx.x * W + w;
     cur.step = (int64_t)gridDim.x * W;
@@ -410,9 +441,9 @@ __global__ void __launch_bounds__(512, 1) csrk_tma_kernel(const CsrkParams<T> p)
       const int *ci_w = rp_w + (p.cap_rows + 8);
       const T *va_w = reinterpret_cast<const T *>(reinterpret_cast<const unsigned char *>(ci_w) +
                                                    (size_t)(p.cap_nnz + 8) * 4);
-      csrk_rows<T, VEC>(r0, r1, rp_w, r0 & ~3, ci_w, va_w, (int64_t)(e0 & ~3), p.x, p.y, lane);
+      csrk_rows<T, VEC, CH>(r0, r1, rp_w, r0 & ~3, ci_w, va_w, (int64_t)(e0 & ~3), p.x, p.y, lane);
     } else {
-      csrk_rows<T, VEC>(r0, r1, p.rp, 0, p.ci, p.val, 0, p.x, p.y, lane);
+      csrk_rows<T, VEC, CH>(r0, r1, p.rp, 0, p.ci, p.val, 0, p.x, p.y, lane);
     }
     __syncwarp();
     --live;

@@ -19,7 +19,7 @@ def alg_bytes(m, n, nnz, vs, n_sr=0, n_ssr=0):
 
 def run(A, algo, opts, iters, flush, peak, label, out):
     for k in (hs.OPT_VEC, hs.OPT_WARPS, hs.OPT_STAGES, hs.OPT_STAGE_NNZ, hs.OPT_CTAS_PER_SM, hs.OPT_ROWS_PER_TILE,
-              hs.OPT_L2_PERSIST_X, hs.OPT_MERGE_TILE):
+              hs.OPT_L2_PERSIST_X, hs.OPT_MERGE_TILE, hs.OPT_CHUNK):
         A.set_option(k, 0)
     for k, v in opts.items():
         A.set_option(k, v)
@@ -71,16 +71,23 @@ def main():
     if not a.quick:
         for tile, c in ((2048, 4), (4096, 6), (8192, 3)):
             run(A, hs.ALGO_CSR_MERGE, {hs.OPT_MERGE_TILE: tile, hs.OPT_CTAS_PER_SM: c}, a.iters, F, a.peak, tag + "merge tile=%d ctas=%d" % (tile, c), out)
-    svecs = (1, 2, 4, 8) if a.kind == 27 else (1, 2)
+    svecs = (1, 2, 4) if a.kind == 27 else (1, 2)
     for vec in svecs:
         run(A, hs.ALGO_CSR_STREAM, {hs.OPT_VEC: vec}, a.iters, F, a.peak, tag + "stream vec=%d default" % vec, out)
     if not a.quick:
-        for vec in svecs[:3]:
-            for warps, stages, rpt in ((8, 2, 32), (8, 3, 16), (16, 2, 16), (16, 3, 8), (16, 2, 32), (4, 4, 32), (12, 2, 24), (16, 4, 8)):
-                run(A, hs.ALGO_CSR_STREAM, {hs.OPT_VEC: vec, hs.OPT_WARPS: warps, hs.OPT_STAGES: stages, hs.OPT_ROWS_PER_TILE: rpt},
-                    a.iters, F, a.peak, tag + "stream vec=%d w=%d s=%d rpt=%d" % (vec, warps, stages, rpt), out)
+        best = None
+        for vec in svecs:
+            for ch in (4, 8, 16):
+                for warps, stages, rpt in ((8, 2, 32), (10, 2, 32), (6, 3, 32), (16, 2, 16), (12, 3, 16), (16, 3, 8), (10, 4, 16), (8, 2, 64), (4, 2, 128)):
+                    if a.kind == 5:
+                        rpt *= 4
+                    r = run(A, hs.ALGO_CSR_STREAM, {hs.OPT_VEC: vec, hs.OPT_WARPS: warps, hs.OPT_STAGES: stages, hs.OPT_ROWS_PER_TILE: rpt, hs.OPT_CHUNK: ch},
+                            a.iters, F, a.peak, tag + "stream vec=%d ch=%d w=%d s=%d rpt=%d" % (vec, ch, warps, stages, rpt), out)
+                    if r and (best is None or r["gbs"] > best["gbs"]):
+                        best = r
+        print("BEST stream:", best["label"], "%.1f GB/s" % best["gbs"], best["kernel"])
     if a.csrk and i["nnz"] < 300e6:
-        for k, sizes in ((2, [32]), (3, [32, 8]), (3, [16, 16])):
+        for k, sizes in ((2, [32]), (3, [32, 8]), (3, [32, 10]), (3, [16, 16])):
             B = hs.Matrix.stencil(a.kind, a.g, dt, 0)
             t0 = time.time()
             B.build_csrk(k, sizes)
@@ -91,9 +98,10 @@ def main():
             for vec in svecs[:3]:
                 run(B, hs.ALGO_CSRK, {hs.OPT_VEC: vec}, a.iters, F, a.peak, tag + "csrk k=%d %s vec=%d" % (k, sizes, vec), out)
             if not a.quick:
-                for warps, stages in ((16, 2), (8, 3), (4, 4)):
-                    run(B, hs.ALGO_CSRK, {hs.OPT_VEC: 2, hs.OPT_WARPS: warps, hs.OPT_STAGES: stages}, a.iters, F, a.peak,
-                        tag + "csrk k=%d %s vec=2 w=%d s=%d" % (k, sizes, warps, stages), out)
+                for vec in svecs[:2]:
+                    for warps, stages, ch in ((8, 2, 16), (10, 2, 16), (8, 2, 8), (16, 2, 8), (6, 3, 16)):
+                        run(B, hs.ALGO_CSRK, {hs.OPT_VEC: vec, hs.OPT_WARPS: warps, hs.OPT_STAGES: stages, hs.OPT_CHUNK: ch}, a.iters, F, a.peak,
+                            tag + "csrk k=%d %s vec=%d w=%d s=%d ch=%d" % (k, sizes, vec, warps, stages, ch), out)
             B.close()
     A.close()
 
