@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline measurement on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): fp64 SpMV GFLOP/s (2*nnz/t) with the HBM roofline beside it.
+Workload: BASELINE.json configs[4] -- the 3-D 27-point stencil on a 400^3 grid (n = 64,000,000,
+nnz = 1,719,374,392, 21.9 GB of algorithmic traffic per SpMV), the configuration the
+"1/2/4/8 B200" part of the metric is quoted on; it fits one GPU, so N = 1 runs the same matrix
+and N > 1 is strong scaling of it (nnz-balanced row blocks + x halo exchange over NVLink).
+A step is one y = A*x over the whole matrix.  The matrix is far larger than L2 (126 MB), so no
+flush is needed between timed iterations.
+
+One JSON line on stdout (rank 0).  `value` = device-timed (CUDA events, max over ranks) with
+inputs resident in HBM; `e2e` = the same metric through the C-ABI call with HOST buffers
+(hspmv_spmv_host: H2D of x, kernel, D2H of y inside the timed region).
+`--impl reference` times the reference's own OpenMP spmv-csr (oracle/_ref, compiled from the
+unmodified sources; the oracle port if that is missing) on the host cores, on a bounded sample
+of the same matrix.
+"""
+import argparse
+import bisect
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+G_DEFAULT = 400
+CPU_SAMPLE_ROWS = 4_000_000   # bounded sample for the CPU arms: first 4 M rows (25 z-planes of 400^2)
+
+
+# ----------------------------------------------------------------------------- closed forms
+def line_len(t, g):
+    return 1 if g == 1 else 3 - (t == 0) - (t == g - 1)
+
+
+def line_prefix(t, g):
+    return t if g == 1 else (0 if t == 0 else 3 * t - 1)
+
+
+def stencil27_before(i, g):
+    """nonzeros in rows < i (same closed form as csrc/gen.cuh and generators.py)."""
+    S = 1 if g == 1 else 3 * g - 2
+    if i >= g ** 3:
+        return S ** 3
+    x, y, z = i % g, (i // g) % g, i // (g * g)
+    return line_prefix(z, g) * S * S + line_len(z, g) * (line_prefix(y, g) * S + line_len(y, g) * line_prefix(x, g))
+
+
+class _RowPtr:
+    def __init__(self, g):
+        self.g = g
+
+    def __len__(self):
+        return self.g ** 3 + 1
+
+    def __getitem__(self, i):
+        return stencil27_before(i, self.g)
+
+
+def partition_stencil(g, parts):
+    """hspmv_partition_rows' rule on the closed-form row pointer: row_lo[p] = first row r with
+    row_ptr[r] >= floor(p*nnz/P)."""
+    rp = _RowPtr(g)
+    nnz = stencil27_before(g ** 3, g)
+    out = [0]
+    for p in range(1, parts):
+        out.append(max(out[-1], bisect.bisect_left(rp, (nnz * p) // parts)))
+    out.append(g ** 3)
+    return out
+
+
+def alg_bytes(m, n, nnz, vs=8):
+    """nnz*(V+4) + (m+1)*4 + n*V (x once) + m*V (y)."""
+    return nnz * (vs + 4) + (m + 1) * 4 + n * vs + m * vs
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.lines = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t_lo, t_hi):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.lines:
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 9 or not (t_lo - 0.05 <= ts <= t_hi + 0.15):
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v == "Active":
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arms
+def cpu_setup_threads(force=False):
+    """OpenMP environment of the CPU arms (run_scripts/run_epyc.py:78-80 style): all host cores,
+    static schedule.  Must run before libgomp is loaded; torchrun exports OMP_NUM_THREADS=1, which
+    the CPU arm overrides (force)."""
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if force or "OMP_NUM_THREADS" not in os.environ:
+        os.environ["OMP_NUM_THREADS"] = str(cores)
+    os.environ.setdefault("OMP_SCHEDULE", "static")      # spmv-csr uses schedule(runtime); libgomp's default is dynamic,1
+    os.environ.setdefault("OMP_PROC_BIND", "true")
+    os.environ.setdefault("OMP_PLACES", "cores")
+    return int(os.environ["OMP_NUM_THREADS"])
+
+
+def cpu_sample_arrays(g, rows):
+    """CSR arrays of rows [0,rows) of the stencil, fetched from the device generator when a GPU is
+    present (fast), else built with numpy."""
+    import numpy as np
+    import torch
+    rows = min(rows, g ** 3)
+    n_cols = min(g ** 3, rows + g * g + g + 1)
+    if torch.cuda.is_available():
+        import heterogeneous_spmv_b200 as hs
+        A = hs.Matrix.stencil(27, g, np.float64, 0, row_lo=0, row_hi=rows, col_shift=0, n_cols=n_cols)
+        rp, ci, v = A.download()
+        A.close()
+    else:
+        from heterogeneous_spmv_b200 import generators as G
+        rp, ci, v = G.stencil27(g, row_lo=0, row_hi=rows)
+    from heterogeneous_spmv_b200 import generators as G
+    return rp, ci, v, G.vector_x(n_cols), n_cols
+
+
+def cpu_time_sample(g, rows, warmup, iters):
+    """(seconds per SpMV (min), nnz of the sample, kind).  Reference omp_spmv if oracle/_ref is
+    there, else the oracle's OpenMP port."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    rp, ci, v, x, n_cols = cpu_sample_arrays(g, rows)
+    if O.have_ref():
+        t, _ = _ref_timed(O, rp, ci, v, x, warmup, iters)
+        kind = "reference"
+    else:
+        t, _ = O.csr_spmv_timed(rp, ci, v, x, warmup, iters)   # (min; the port has no mean output)
+        kind = "port"
+    return t, int(len(ci)), kind
+
+
+def _ref_timed(O, rp, ci, v, x, warmup, iters):
+    # the reference's omp_spmv only ever indexes x by column id, so a rectangular sample
+    # (rows [0,R) with columns up to R + g^2+g+1) is a valid input for it
+    import ctypes as C
+    import numpy as np
+    L = O.ref("csr", np.float64)
+    y = np.zeros(len(rp) - 1)
+    fp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+    ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+    L.ref_csr_spmv_timed.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip, fp, fp, fp, C.c_int, C.c_int,
+                                     C.POINTER(C.c_double)]
+    L.ref_csr_spmv_timed.restype = C.c_double
+    avg = C.c_double()
+    L.ref_csr_spmv_timed(len(rp) - 1, len(x), len(ci), np.ascontiguousarray(rp, np.int32),
+                         np.ascontiguousarray(ci, np.int32), v, x, y, warmup, iters, C.byref(avg))
+    return float(avg.value), y      # mean over the timed calls, like the GPU arm's K-step mean
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU implementation on the host cores."""
+    if rank != 0:
+        return
+    cores = cpu_setup_threads(force=True)
+    t, nnz, kind = cpu_time_sample(args.g, args.cpu_rows, args.warmup, args.steps)
+    gf = 2.0 * nnz / t / 1e9
+    sample = "rows [0,%d) of stencil27 g=%d: %d nnz; mean of %d timed omp_spmv calls after %d warm-ups" % (
+        min(args.cpu_rows, args.g ** 3), args.g, nnz, args.steps, args.warmup)
+    print(json.dumps({
+        "impl": "reference", "metric": "fp64 SpMV GFLOP/s", "value": gf, "unit": "GFLOP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "stencil27_g%d_csr" % args.g, "n": args.g ** 3,
+                   "nnz": stencil27_before(args.g ** 3, args.g), "format": "csr"},
+        "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import heterogeneous_spmv_b200 as hs
+    from heterogeneous_spmv_b200 import dist as hd
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the SpMV path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    hs.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    g = args.g
+    n = g ** 3
+    nnz_total = stencil27_before(n, g)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    algo = {"stream": hs.ALGO_CSR_STREAM, "vector": hs.ALGO_CSR_VECTOR, "merge": hs.ALGO_CSR_MERGE,
+            "auto": hs.ALGO_AUTO}[args.algo]
+
+    # ---- this rank's block
+    row_lo = partition_stencil(g, world)
+    lo, hi = row_lo[rank], row_lo[rank + 1]
+    if world > 1:   # column window of this block = the part of x it needs (owned rows + halo)
+        probe = hs.Matrix.stencil(27, g, np.float64, 0, row_lo=lo, row_hi=hi)
+        cmin, cmax = probe.col_range()
+        probe.close()
+    else:
+        cmin, cmax = 0, n - 1
+    A = hs.Matrix.stencil(27, g, np.float64, 0, row_lo=lo, row_hi=hi, col_shift=cmin, n_cols=cmax - cmin + 1)
+    info = A.info()
+    m_loc, nnz_loc = info["m"], info["nnz"]
+    x_local = torch.empty(cmax - cmin + 1, dtype=torch.float64, device="cuda")
+    idx = torch.arange(cmin, cmax + 1, device="cuda", dtype=torch.int64)
+    x_local.copy_(1.0 + (idx % 97).to(torch.float64) / 128.0)     # generators.vector_x
+    del idx
+    y_local = torch.zeros(m_loc, dtype=torch.float64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def compute(a, b):
+        A.spmv_range(a, b, algo, d_x=x_local.data_ptr(), d_y=y_local.data_ptr(), stream=stream)
+
+    if world > 1:
+        ranges = hd.gather_col_ranges((cmin, cmax))
+        interior = A.interior_rows(lo - cmin, hi - cmin)
+        sh = hd.ShardedSpMV(row_lo, ranges, rank, x_local, compute, interior)
+        step = lambda: sh.step(overlap=not args.no_overlap)   # noqa: E731
+        halo_bytes = sh.halo_elems * 8
+    else:
+        step = lambda: compute(0, m_loc)                      # noqa: E731
+        halo_bytes = 0
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    for _ in range(max(args.warmup, 3)):
+        step()
+    # ---- timed: K steps, device events, max over ranks
+    barrier()
+    launches0 = hs.launch_count()
+    t_wall0 = time.time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = hs.launch_count() - launches0
+    barrier()
+    kernel_name = A.last_kernel()
+
+    # ---- e2e: host x -> device, (halo,) kernel, device y -> host, every step
+    x_host = torch.empty(hi - lo, dtype=torch.float64).pin_memory()
+    x_host.copy_(x_local[lo - cmin: hi - cmin].cpu())
+    y_host = torch.empty(m_loc, dtype=torch.float64).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+    if world == 1:
+        A.spmv_host_ptr(x_host.data_ptr(), y_host.data_ptr(), algo)          # warm-up (first-touch of pinned pages)
+        barrier()
+        e2e_ms = A.spmv_host_timed(x_host.data_ptr(), y_host.data_ptr(), e2e_steps, algo)
+        chk = float(y_host[:1000].abs().sum())
+    else:
+        def e2e_step():
+            x_local[lo - cmin: hi - cmin].copy_(x_host, non_blocking=True)
+            step()
+            y_host.copy_(y_local, non_blocking=True)
+        e2e_step()
+        barrier()
+        e0.record()
+        for _ in range(e2e_steps):
+            e2e_step()
+        e1.record()
+        torch.cuda.synchronize()
+        e2e_ms = e0.elapsed_time(e1)
+        chk = float(y_host[:1000].abs().sum())
+    t_wall1 = time.time()
+    barrier()
+
+    # ---- reduce over ranks
+    stats = torch.tensor([ms, e2e_ms, float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, e2e_ms, launches = float(mx[0]), float(mx[1]), int(sm[2])
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+
+    if rank == 0:
+        ms_step = ms / args.steps
+        value = 2.0 * nnz_total / (ms_step * 1e-3) / 1e9
+        e2e_value = 2.0 * nnz_total / (e2e_ms / e2e_steps * 1e-3) / 1e9
+        # roofline of the dominant kernel: at N = 1 the step IS one launch of it; at N > 1 it is the
+        # interior launch (plus two thin boundary launches), so per-rank bytes / step time is reported
+        b_launch = alg_bytes(m_loc, cmax - cmin + 1, nnz_loc)
+        achieved = b_launch / (ms_step * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("stencil27_g%d" % g)
+        except Exception:
+            pass
+        line = {
+            "metric": "fp64 SpMV GFLOP/s", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "stencil27_g%d_csr" % g, "n": n, "nnz": nnz_total, "format": "csr",
+                       "kernel": kernel_name, "partition": "nnz-balanced row blocks" if world > 1 else "single GPU",
+                       "halo_bytes_per_rank_per_step": halo_bytes, "overlap": world > 1 and not args.no_overlap,
+                       "l2": "input (21.9 GB) >> L2 (126 MB): no flush needed"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                         "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
+                         "frac_of_nominal_8TBs": achieved / 8000.0,
+                         "algorithmic_bytes_per_launch": b_launch},
+            "e2e": {"value": e2e_value, "unit": "GFLOP/s", "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 8,
+                    "steps": e2e_steps, "checksum": chk},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            cores = cpu_setup_threads()
+            t, nnz_s, kind = cpu_time_sample(g, args.cpu_rows, 5, 20)
+            line["cpu_baseline"] = {
+                "value": 2.0 * nnz_s / t / 1e9, "unit": "GFLOP/s", "cores": cores, "kind": kind,
+                "sample": "rows [0,%d) of the same matrix (%d nnz), omp_spmv, mean of 20 after 5 warm-ups, "
+                          "OMP_SCHEDULE=static" % (min(args.cpu_rows, n), nnz_s)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--g", type=int, default=G_DEFAULT, help="grid edge of the 27-point stencil (400 = BASELINE config 5)")
+    ap.add_argument("--algo", default="stream", choices=["stream", "vector", "merge", "auto"])
+    ap.add_argument("--cpu-rows", type=int, default=CPU_SAMPLE_ROWS)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-overlap", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-launch ourselves under it
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"), __file__] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    # before anything loads libgomp: the CPU legs use every host core
+    cpu_setup_threads(force=(args.impl == "reference" or world == 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -310,6 +310,11 @@ class Matrix:
         _check(lib().hspmv_col_range_device(self.h, C.byref(lo), C.byref(hi)))
         return lo.value, hi.value
 
+    def interior_rows(self, own_col_lo, own_col_hi):
+        a, b = C.c_int64(), C.c_int64()
+        _check(lib().hspmv_interior_rows(self.h, C.c_int64(own_col_lo), C.c_int64(own_col_hi), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     # -- Band-k
     def build_csrk(self, k, sup_row_sizes):
         sizes = (C.c_int * 2)(*(list(sup_row_sizes) + [0])[:2])
@@ -356,6 +361,17 @@ class Matrix:
 
     def spmv(self, algo=ALGO_AUTO, d_x=None, d_y=None, stream=None):
         _check(lib().hspmv_spmv(self.h, int(algo), C.c_void_p(d_x), C.c_void_p(d_y), C.c_void_p(stream)))
+
+    def spmv_range(self, row_lo, row_hi, algo=ALGO_AUTO, d_x=None, d_y=None, stream=None):
+        _check(lib().hspmv_spmv_range(self.h, int(algo), C.c_int64(row_lo), C.c_int64(row_hi), C.c_void_p(d_x),
+                                      C.c_void_p(d_y), C.c_void_p(stream)))
+
+    def spmv_host_timed(self, x_ptr, y_ptr, iters, algo=ALGO_AUTO):
+        """iters x (H2D x, kernel, D2H y) on raw host addresses; returns total device-event ms."""
+        ms = C.c_float()
+        _check(lib().hspmv_spmv_host_timed(self.h, int(algo), C.c_void_p(x_ptr), C.c_void_p(y_ptr), int(iters),
+                                           C.byref(ms)))
+        return float(ms.value)
 
     def spmv_timed(self, algo=ALGO_AUTO, warmup=3, iters=20, flush_l2=False):
         ms = np.zeros(iters, np.float32)

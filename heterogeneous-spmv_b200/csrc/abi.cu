@@ -248,7 +248,7 @@ int pow2_floor_clamped(int64_t v) {
 // CSR_VECTOR: one contiguous launch when every row fits the chosen lane count in a few steps,
 // otherwise one launch per non-empty bin.
 template <typename T>
-int run_csr_vector(hspmv_matrix *A, const T *x, T *y, cudaStream_t st) {
+int run_csr_vector(hspmv_matrix *A, const T *x, T *y, cudaStream_t st, int64_t row_lo = 0, int64_t row_hi = -1) {
   int rc = ensure_stats(A);
   if (rc) return rc;
   const int64_t max_len = A->stats[8];
@@ -258,10 +258,12 @@ int run_csr_vector(hspmv_matrix *A, const T *x, T *y, cudaStream_t st) {
     vec = 1;
     while (vec < 32 && vec * 4 < mean + 3) vec <<= 1;
   }
-  const bool regular = max_len <= (int64_t)vec * 4 * 8 || A->opt[HSPMV_OPT_VEC] > 0;
+  if (row_hi < 0) row_hi = A->m;
+  const bool ranged = row_lo != 0 || row_hi != A->m;
+  const bool regular = max_len <= (int64_t)vec * 4 * 8 || A->opt[HSPMV_OPT_VEC] > 0 || ranged;
   char name[96];
   if (regular) {
-    launch_vector_vec<T>(A, vec, false, nullptr, A->m, 0, x, y, st);
+    launch_vector_vec<T>(A, vec, false, nullptr, row_hi - row_lo, row_lo, x, y, st);
     std::snprintf(name, sizeof(name), "csr_vector<%s,vec=%d> contiguous", sizeof(T) == 8 ? "f64" : "f32", vec);
     A->last_kernel = name;
     return HSPMV_OK;
@@ -316,25 +318,28 @@ int launch_csrk(hspmv_matrix *A, const hspmv::CsrkParams<T> &p, int grid, int wa
 
 // CSRK (k = 2,3 after hspmv_build_csrk / hspmv_create_csrk) and CSR_STREAM (k = 1, fixed-row tiles)
 template <typename T>
-int run_csrk(hspmv_matrix *A, bool stream_mode, const T *x, T *y, cudaStream_t st) {
+int run_csrk(hspmv_matrix *A, bool stream_mode, const T *x, T *y, cudaStream_t st, int64_t row_lo = 0, int64_t row_hi = -1) {
   if (!stream_mode && A->k < 2) return fail(HSPMV_ESTATE, "HSPMV_ALGO_CSRK needs hspmv_build_csrk or hspmv_create_csrk first");
+  int rc0 = ensure_stats(A);
+  if (rc0) return rc0;
   const double mean = A->m ? (double)A->nnz / (double)A->m : 1.0;
+  const int64_t max_len = A->stats[8];
+  // lanes per row: one round of `chunk` gathers per lane should cover the mean row
   int vec = (int)A->opt[HSPMV_OPT_VEC];
-  if (vec <= 0) vec = mean <= 12 ? 1 : mean <= 48 ? 2 : mean <= 96 ? 4 : mean <= 192 ? 8 : mean <= 384 ? 16 : 32;
+  if (vec <= 0) vec = mean <= 8 ? 1 : mean <= 16 ? 2 : mean <= 40 ? 4 : mean <= 96 ? 8 : mean <= 256 ? 16 : 32;
+  int chunk = (int)A->opt[HSPMV_OPT_CHUNK];
+  if (chunk <= 0) chunk = 8;
+  chunk = chunk >= 16 ? 16 : chunk >= 8 ? 8 : 4;
   int warps = (int)A->opt[HSPMV_OPT_WARPS];
-  if (warps <= 0) warps = 8;
+  if (warps <= 0) warps = 16; // r1 sweep: occupancy matters more than stage size (profiles/)
   if (warps > 16) warps = 16;
   int stages = (int)A->opt[HSPMV_OPT_STAGES];
   if (stages <= 0) stages = 2;
-  int chunk = (int)A->opt[HSPMV_OPT_CHUNK];
-  if (chunk <= 0) { // gathers in flight per lane: enough to cover one row's share in <= 2 rounds
-    const double per_lane = mean / vec;
-    chunk = per_lane > 12 ? 16 : per_lane > 5 ? 8 : 4;
-  }
-  chunk = chunk >= 16 ? 16 : chunk >= 8 ? 8 : 4;
 
+  if (row_hi < 0) row_hi = A->m;
   hspmv::CsrkParams<T> p;
-  p.m = A->m;
+  p.m = stream_mode ? row_hi : A->m;
+  p.row_begin = stream_mode ? row_lo : 0;
   p.rp = A->d_rp;
   p.ci = A->d_ci;
   p.val = (const T *)A->d_val;
@@ -347,54 +352,63 @@ int run_csrk(hspmv_matrix *A, bool stream_mode, const T *x, T *y, cudaStream_t s
   p.stages = stages;
   p.rows_per_tile = 0;
 
-  int64_t work_items; // what the grid is spread over
-  int64_t typical_rows, typical_nnz;
+  int64_t typical_rows, typical_nnz, worst_nnz;
   if (stream_mode) {
     int rpt = (int)A->opt[HSPMV_OPT_ROWS_PER_TILE];
-    if (rpt <= 0) { // ~768 nonzeros per tile, whole passes of the warp
+    if (rpt <= 0) { // ~448 nonzeros per tile, whole passes of the warp
       const int per_pass = 32 / vec;
-      rpt = (int)(768.0 / (mean > 1 ? mean : 1.0) + 0.5);
+      rpt = (int)(448.0 / (mean > 1 ? mean : 1.0) + 0.5);
       rpt = ((rpt + per_pass - 1) / per_pass) * per_pass;
       if (rpt < per_pass) rpt = per_pass;
     }
     p.k = 1;
     p.rows_per_tile = rpt;
-    p.n_sr = (A->m + rpt - 1) / rpt;
-    work_items = (p.n_sr + warps - 1) / warps;
+    p.n_sr = (row_hi - row_lo + rpt - 1) / rpt;
     typical_rows = rpt;
-    typical_nnz = (int64_t)(rpt * mean);
+    typical_nnz = (int64_t)(rpt * mean + 0.999);
+    worst_nnz = (int64_t)rpt * max_len; // a tile can never hold more than this
   } else {
     p.k = A->k;
     p.n_sr = A->n_sr;
-    work_items = A->k == 3 ? A->n_ssr : (A->n_sr + warps - 1) / warps;
     typical_rows = A->n_sr ? (A->m + A->n_sr - 1) / A->n_sr : 1;
     typical_nnz = A->n_sr ? (A->nnz + A->n_sr - 1) / A->n_sr : 1;
+    worst_nnz = typical_nnz * 4;
   }
 
-  // stage capacity: explicit option, else 1.5x the typical super-row, within shared memory
+  // Stage capacity: explicit option, else 1.5x the typical super-row (never more than the worst
+  // case).  If warps*stages of that do not fit in shared memory, give up warps first, capacity
+  // last: an under-sized stage sends every super-row down the unstaged path.
   int cap_nnz = (int)A->opt[HSPMV_OPT_STAGE_NNZ];
-  if (cap_nnz <= 0) cap_nnz = (int)((typical_nnz * 3 / 2 + 64 + 3) & ~(int64_t)3);
-  int cap_rows = (int)((typical_rows * 2 + 32 + 3) & ~(int64_t)3);
+  if (cap_nnz <= 0) {
+    int64_t c = typical_nnz * 3 / 2 + 64;
+    if (c > worst_nnz) c = worst_nnz;
+    if (c < typical_nnz) c = typical_nnz;
+    cap_nnz = (int)((c + 3) & ~(int64_t)3);
+  }
   if (cap_nnz < 64) cap_nnz = 64;
+  cap_nnz = (cap_nnz + 3) & ~3;
+  int cap_rows = (int)((typical_rows * (stream_mode ? 1 : 2) + (stream_mode ? 0 : 32) + 3) & ~(int64_t)3);
+  if (cap_rows < 8) cap_rows = 8;
   const size_t budget = A->dev.max_smem_optin - 1024;
-  auto total = [&](int cn, int cr) {
-    return (((size_t)warps * stages * 8 + 127) & ~(size_t)127) +
-           (size_t)warps * stages * hspmv::csrk_stage_bytes(cn, cr, sizeof(T));
+  auto total = [&](int w, int cn, int cr) {
+    return (((size_t)w * stages * 8 + 127) & ~(size_t)127) +
+           (size_t)w * stages * hspmv::csrk_stage_bytes(cn, cr, sizeof(T));
   };
-  while (total(cap_nnz, cap_rows) > budget && cap_nnz > 64) cap_nnz = (cap_nnz * 3 / 4) & ~3;
-  while (total(cap_nnz, cap_rows) > budget && cap_rows > 8) cap_rows = (cap_rows / 2) & ~3;
-  if (total(cap_nnz, cap_rows) > budget) return fail(HSPMV_EINVAL, "warps*stages does not fit shared memory");
-  cap_nnz &= ~3;
-  cap_rows &= ~3;
+  while (warps > 4 && total(warps, cap_nnz, cap_rows) > budget) --warps;
+  while (total(warps, cap_nnz, cap_rows) > budget && cap_nnz > 64) cap_nnz = (cap_nnz * 3 / 4) & ~3;
+  while (total(warps, cap_nnz, cap_rows) > budget && cap_rows > 8) cap_rows = (cap_rows / 2) & ~3;
+  while (warps > 1 && total(warps, cap_nnz, cap_rows) > budget) --warps;
+  if (total(warps, cap_nnz, cap_rows) > budget) return fail(HSPMV_EINVAL, "stages do not fit shared memory");
   p.cap_nnz = cap_nnz;
   p.cap_rows = cap_rows;
-  const size_t smem = total(cap_nnz, cap_rows);
+  const size_t smem = total(warps, cap_nnz, cap_rows);
 
+  const int64_t work_items = (!stream_mode && A->k == 3) ? A->n_ssr : (p.n_sr + warps - 1) / warps;
   int ctas_per_sm = (int)A->opt[HSPMV_OPT_CTAS_PER_SM];
   if (ctas_per_sm <= 0) {
     ctas_per_sm = (int)((A->dev.max_smem_optin + 1024) / (smem + 1024));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
-    if (ctas_per_sm * warps > 32) ctas_per_sm = 32 / warps > 0 ? 32 / warps : 1;
+    if (ctas_per_sm * warps > 20) ctas_per_sm = 20 / warps > 0 ? 20 / warps : 1; // register file: <= 20 warps of <= 100 regs
   }
   int64_t grid = (int64_t)A->dev.sms * ctas_per_sm;
   if (grid > work_items) grid = work_items;
@@ -490,10 +504,20 @@ int apply_l2_window(hspmv_matrix *A, const void *x, cudaStream_t st) {
 }
 
 template <typename T>
-int dispatch(hspmv_matrix *A, int algo, const void *dx, void *dy, cudaStream_t st) {
+int dispatch(hspmv_matrix *A, int algo, const void *dx, void *dy, cudaStream_t st, int64_t row_lo = 0,
+             int64_t row_hi = -1) {
   const T *x = (const T *)(dx ? dx : A->d_x);
   T *y = (T *)(dy ? dy : A->d_y);
   if (A->m == 0) return HSPMV_OK;
+  if (row_hi < 0) row_hi = A->m;
+  const bool ranged = row_lo != 0 || row_hi != A->m;
+  if (ranged) {
+    if (row_lo < 0 || row_lo > row_hi || row_hi > A->m) return fail(HSPMV_EINVAL, "bad row range");
+    if (row_lo == row_hi) return HSPMV_OK;
+    if (algo == HSPMV_ALGO_AUTO) algo = HSPMV_ALGO_CSR_STREAM;
+    if (algo != HSPMV_ALGO_CSR_STREAM && algo != HSPMV_ALGO_CSR_VECTOR)
+      return fail(HSPMV_EUNSUPPORTED, "row ranges are supported by CSR_STREAM and CSR_VECTOR only");
+  }
   int rc = apply_l2_window(A, x, st);
   if (rc) return rc;
   if (algo == HSPMV_ALGO_AUTO) {
@@ -508,8 +532,8 @@ int dispatch(hspmv_matrix *A, int algo, const void *dx, void *dy, cudaStream_t s
     }
   }
   switch (algo) {
-  case HSPMV_ALGO_CSR_VECTOR: rc = run_csr_vector<T>(A, x, y, st); break;
-  case HSPMV_ALGO_CSR_STREAM: rc = run_csrk<T>(A, true, x, y, st); break;
+  case HSPMV_ALGO_CSR_VECTOR: rc = run_csr_vector<T>(A, x, y, st, row_lo, row_hi); break;
+  case HSPMV_ALGO_CSR_STREAM: rc = run_csrk<T>(A, true, x, y, st, row_lo, row_hi); break;
   case HSPMV_ALGO_CSR_MERGE: rc = run_csr_merge<T>(A, x, y, st); break;
   case HSPMV_ALGO_CSRK: rc = run_csrk<T>(A, false, x, y, st); break;
   default: return fail(HSPMV_EINVAL, "unknown algo");
@@ -519,10 +543,12 @@ int dispatch(hspmv_matrix *A, int algo, const void *dx, void *dy, cudaStream_t s
   return HSPMV_OK;
 }
 
-int do_spmv(hspmv_matrix *A, int algo, const void *dx, void *dy, cudaStream_t st) {
+int do_spmv(hspmv_matrix *A, int algo, const void *dx, void *dy, cudaStream_t st, int64_t row_lo = 0,
+            int64_t row_hi = -1) {
   A->last_stream = st;
   A->last_stream_valid = true;
-  return A->dtype == HSPMV_F64 ? dispatch<double>(A, algo, dx, dy, st) : dispatch<float>(A, algo, dx, dy, st);
+  return A->dtype == HSPMV_F64 ? dispatch<double>(A, algo, dx, dy, st, row_lo, row_hi)
+                               : dispatch<float>(A, algo, dx, dy, st, row_lo, row_hi);
 }
 
 int upload_csrk_maps(hspmv_matrix *A) {
@@ -938,6 +964,31 @@ int hspmv_spmv(hspmv_matrix *A, int algo, const void *d_x, void *d_y, void *stre
   return do_spmv(A, algo, d_x, d_y, (cudaStream_t)stream);
 }
 
+int hspmv_spmv_range(hspmv_matrix *A, int algo, int64_t row_lo, int64_t row_hi, const void *d_x, void *d_y,
+                     void *stream) {
+  if (!A) return fail(HSPMV_EINVAL, "null handle");
+  return do_spmv(A, algo, d_x, d_y, (cudaStream_t)stream, row_lo, row_hi);
+}
+
+int hspmv_spmv_host_timed(hspmv_matrix *A, int algo, const void *x_host, void *y_host, int iters,
+                          float *ms_total) {
+  if (!A || !x_host || !y_host || iters < 1 || !ms_total) return fail(HSPMV_EINVAL, "bad arguments");
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, A->stream));
+  for (int i = 0; i < iters; ++i) {
+    int rc = hspmv_spmv_host(A, algo, x_host, y_host);
+    if (rc) return rc;
+  }
+  CU(cudaEventRecord(e1, A->stream));
+  CU(cudaEventSynchronize(e1));
+  CU(cudaEventElapsedTime(ms_total, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return HSPMV_OK;
+}
+
 int hspmv_spmv_timed(hspmv_matrix *A, int algo, int warmup, int iters, int flush_l2, float *ms_out) {
   if (!A || iters < 1 || !ms_out) return fail(HSPMV_EINVAL, "bad arguments");
   if (flush_l2 && !A->d_flush) {
@@ -1038,6 +1089,27 @@ int hspmv_col_range_device(const hspmv_matrix *A, int64_t *col_min, int64_t *col
   cudaFree(d);
   *col_min = A->nnz ? res[0] : 0;
   *col_max = A->nnz ? res[1] : -1;
+  return HSPMV_OK;
+}
+
+int hspmv_interior_rows(const hspmv_matrix *A, int64_t own_col_lo, int64_t own_col_hi, int64_t *row_a,
+                        int64_t *row_b) {
+  if (!A || !row_a || !row_b) return fail(HSPMV_EINVAL, "null");
+  int *d = nullptr;
+  CU(cudaMalloc(&d, 8));
+  int init[2] = {0, (int)A->m};
+  CU(cudaMemcpy(d, init, 8, cudaMemcpyHostToDevice));
+  if (A->m) {
+    hspmv::interior_rows_kernel<<<grid_for(A->m * 32, 256, A->dev.sms * 16), 256, 0, A->stream>>>(
+        A->m, A->d_rp, A->d_ci, (int)own_col_lo, (int)own_col_hi, d, d + 1);
+    LAUNCHED();
+  }
+  CU(cudaStreamSynchronize(A->stream));
+  int res[2];
+  CU(cudaMemcpy(res, d, 8, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  *row_a = res[0];
+  *row_b = res[1] < res[0] ? res[0] : res[1];
   return HSPMV_OK;
 }
 

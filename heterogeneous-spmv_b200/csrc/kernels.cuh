@@ -214,7 +214,8 @@ __global__ void zero_rows_kernel(int64_t n_rows, const int *__restrict__ row_lis
 // ------------------------------------------------------------------------------------------
 template <typename T> struct CsrkParams {
   int k;              // 1: implicit tiles of rows_per_tile rows, 2: sr_ptr, 3: ssr_ptr + sr_ptr
-  int64_t m;          // rows
+  int64_t m;          // rows (k == 1: end of the row range being processed)
+  int64_t row_begin;  // k == 1: first row of tile 0 (hspmv_spmv_range); 0 for the whole matrix
   int64_t n_sr;       // super-rows (k == 1: number of tiles)
   int64_t n_ssr;      // super-super-rows (k == 3)
   const uint32_t *ssr_ptr; // [n_ssr+1]
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(512, 1) csrk_tma_kernel(const CsrkParams<T> p)
   auto load_meta = [&](int64_t sr) -> SrMeta {
     SrMeta mt;
     if (p.k == 1) {
-      const int64_t r0 = sr * p.rows_per_tile;
+      const int64_t r0 = p.row_begin + sr * p.rows_per_tile;
       const int64_t r1 = (r0 + p.rows_per_tile < p.m) ? r0 + p.rows_per_tile : p.m;
       mt.r0 = (int)r0;
       mt.r1 = (int)r1;
@@ -484,6 +485,27 @@ __global__ void sr_offsets_kernel(int64_t n_sr, const uint32_t *__restrict__ sr_
        i += (int64_t)gridDim.x * blockDim.x)
     sr_e[i] = (uint32_t)rp[sr_ptr[i]];
 }
+// Rows whose columns all lie in [own_lo, own_hi) are "interior" (need no halo).  Reports the last
+// non-interior row of the first half (+1) and the first non-interior row of the second half, so
+// that [row_a, row_b) is a contiguous all-interior range.  One warp per row.
+__global__ void interior_rows_kernel(int64_t m, const int *__restrict__ rp, const int *__restrict__ ci,
+                                     int own_lo, int own_hi, int *row_a, int *row_b) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n_warps = (int64_t)gridDim.x * blockDim.x / 32;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32; r < m; r += n_warps) {
+    bool outside = false;
+    for (int64_t j = rp[r] + lane; j < rp[r + 1]; j += 32) {
+      const int c = ci[j];
+      outside = outside || c < own_lo || c >= own_hi;
+    }
+    outside = __any_sync(0xffffffffu, outside);
+    if (outside && lane == 0) {
+      if (r < m / 2) atomicMax(row_a, (int)r + 1);
+      else atomicMin(row_b, (int)r);
+    }
+  }
+}
+
 __global__ void col_minmax_kernel(int64_t nnz, const int *__restrict__ ci, int *out_min,
                                   int *out_max) {
   int lo = INT32_MAX, hi = -1;

@@ -179,6 +179,10 @@ int hspmv_set_option(hspmv_matrix *A, int option, int64_t value);
  * 186-198, spmv-auto-ampere.cu:205-217 and the CPU loops omp_spmv (spmv-csr/spmv.c:92-114)
  * and CSRk_Graph::SpMV (spmv-csrk/csrk.cpp:149-330). */
 int hspmv_spmv(hspmv_matrix *A, int algo, const void *d_x, void *d_y, void *stream);
+/* Same, restricted to rows [row_lo,row_hi) (CSR_STREAM / CSR_VECTOR on a plain-CSR handle): lets
+ * the multi-GPU layer run the interior rows while the x halo is still in flight. */
+int hspmv_spmv_range(hspmv_matrix *A, int algo, int64_t row_lo, int64_t row_hi, const void *d_x,
+                     void *d_y, void *stream);
 /* N timed launches after `warmup` untimed ones; ms_out[i] = device time of launch i from
  * CUDA events on the launching stream.  flush_l2 != 0 overwrites an L2-sized scratch buffer
  * before every launch (outside the event pair).  Replaces the host-timer loops at
@@ -188,6 +192,10 @@ int hspmv_spmv_timed(hspmv_matrix *A, int algo, int warmup, int iters, int flush
 /* End-to-end plugin call with HOST buffers: set_x (permute + H2D) -> kernel -> get_y (D2H,
  * original row order), synchronous.  This is setX + SpMV + getY of the reference drivers. */
 int hspmv_spmv_host(hspmv_matrix *A, int algo, const void *x_host, void *y_host);
+/* `iters` back-to-back hspmv_spmv_host calls bracketed by CUDA events on the handle's stream:
+ * *ms_total covers every H2D copy of x, permutation, kernel and D2H copy of y. */
+int hspmv_spmv_host_timed(hspmv_matrix *A, int algo, const void *x_host, void *y_host, int iters,
+                          float *ms_total);
 /* Name of the kernel variant the last hspmv_spmv on this handle launched (for reports). */
 const char *hspmv_last_kernel(const hspmv_matrix *A);
 
@@ -213,6 +221,12 @@ int hspmv_block_col_range(const int32_t *row_ptr, const int32_t *col_idx, int64_
 /* Device variant for matrices that only exist in HBM (generated or already uploaded). */
 int hspmv_col_range_device(const hspmv_matrix *A, int64_t *col_min, int64_t *col_max);
 
+
+/* Contiguous range [row_a,row_b) of rows whose column indices all lie in [own_col_lo,own_col_hi)
+ * (local column ids): row_a = 1 + last row of the first half that references a column outside,
+ * row_b = first such row of the second half.  Rows outside the range wait for the x halo. */
+int hspmv_interior_rows(const hspmv_matrix *A, int64_t own_col_lo, int64_t own_col_hi,
+                        int64_t *row_a, int64_t *row_b);
 
 /* ---- kernel-side index tables, exposed for the bit-exactness tests ------------------ */
 /* CSR_MERGE tile table: tile_row[t] = last row r with row_ptr[r] <= t*tile, t = 0..n_tiles

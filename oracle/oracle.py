@@ -309,8 +309,8 @@ def ref_csr_spmv_timed(rp, ci, v, x, warmup=5, iters=20):
     y = np.zeros(m, dtype=v.dtype)
     fp = _fp(v.dtype)
     L.ref_csr_spmv_timed.argtypes = [C.c_int, C.c_int, C.c_int, i32p, i32p, fp, fp, fp, C.c_int,
-                                     C.c_int]
-    return float(L.ref_csr_spmv_timed(m, m, len(ci), rp, ci, v, x, y, warmup, iters)), y
+                                     C.c_int, C.POINTER(C.c_double)]
+    return float(L.ref_csr_spmv_timed(m, len(x), len(ci), rp, ci, v, x, y, warmup, iters, None)), y
 
 
 def ref_read_csr_f32(path):

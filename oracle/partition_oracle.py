@@ -63,3 +63,42 @@ def tile_rows(row_ptr, tile):
     t = np.arange(n_tiles, dtype=np.int64) * tile
     out = np.searchsorted(rp, t, side="right") - 1
     return np.concatenate([out, [m]]).astype(np.int32)
+
+
+def interior_rows(row_ptr, col_idx, own_lo, own_hi):
+    """[row_a,row_b): row_a = 1 + last row of the first half with a column outside [own_lo,own_hi),
+    row_b = first such row of the second half (include/hspmv.h: hspmv_interior_rows)."""
+    rp = np.asarray(row_ptr, dtype=np.int64)
+    ci = np.asarray(col_idx, dtype=np.int64)
+    m = len(rp) - 1
+    bad = np.zeros(m, dtype=bool)
+    rows = np.repeat(np.arange(m), np.diff(rp))
+    out = (ci < own_lo) | (ci >= own_hi)
+    bad[np.unique(rows[out])] = True
+    half = m // 2
+    first = np.nonzero(bad[:half])[0]
+    second = np.nonzero(bad[half:])[0]
+    a = int(first[-1]) + 1 if first.size else 0
+    b = int(second[0]) + half if second.size else m
+    return a, max(a, b)
+
+
+def halo_plan(row_lo, col_ranges, rank):
+    """recv/send segments (peer, global_start, global_end) for `rank`: the parts of its column
+    window [cmin,cmax] owned by others, and the parts of its own rows that others' windows cover."""
+    P = len(row_lo) - 1
+    recv, send = [], []
+    lo, hi = int(row_lo[rank]), int(row_lo[rank + 1])
+    cmin, cmax = col_ranges[rank]
+    for q in range(P):
+        if q == rank:
+            continue
+        qlo, qhi = int(row_lo[q]), int(row_lo[q + 1])
+        a, b = max(cmin, qlo), min(cmax + 1, qhi)
+        if a < b:
+            recv.append((q, a, b))
+        qmin, qmax = col_ranges[q]
+        a, b = max(qmin, lo), min(qmax + 1, hi)
+        if a < b:
+            send.append((q, a, b))
+    return recv, send

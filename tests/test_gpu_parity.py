@@ -296,3 +296,35 @@ def test_linearity_and_scaling_properties_at_config2_size(hs, gen):
     rp, ci, v = gen.stencil27(g, row_lo=500000, row_hi=500200)
     y_rows = O.csr_spmv(rp, ci, v, x1)
     assert np.max(np.abs(y_rows - ys[hs.ALGO_CSR_STREAM][500000:500200])) < 1e-10
+
+
+def test_row_ranges_and_interior_rows(hs, oracle, gen):
+    """hspmv_spmv_range / hspmv_interior_rows: what the multi-GPU layer launches per shard."""
+    import partition_oracle as PO
+    g = 14
+    rp, ci, v = gen.stencil27(g, mode="varied")
+    n = len(rp) - 1
+    row_lo = hs.partition_rows(rp, 3)
+    x = gen.vector_x(n)
+    y_full = oracle.csr_spmv(rp, ci, v, x)
+    scale = oracle.abs_rowsum(rp, ci, v, x)
+    for r in range(3):
+        lo, hi = int(row_lo[r]), int(row_lo[r + 1])
+        probe = hs.Matrix.stencil(27, g, np.float64, 1, row_lo=lo, row_hi=hi)
+        cmin, cmax = probe.col_range()
+        assert (cmin, cmax) == hs.block_col_range(rp, ci, lo, hi)
+        B = hs.Matrix.stencil(27, g, np.float64, 1, row_lo=lo, row_hi=hi, col_shift=cmin, n_cols=cmax - cmin + 1)
+        b_rp, b_ci, _ = B.download()
+        a, b = B.interior_rows(lo - cmin, hi - cmin)
+        assert (a, b) == PO.interior_rows(b_rp, b_ci, lo - cmin, hi - cmin)
+        B.set_x(x[cmin:cmax + 1])
+        for algo in (hs.ALGO_CSR_STREAM, hs.ALGO_CSR_VECTOR, hs.ALGO_AUTO):
+            B.set_y(np.full(hi - lo, np.nan))
+            B.spmv_range(a, b, algo)                       # interior first, as ShardedSpMV does
+            y = B.get_y()
+            assert np.all(np.isnan(y[:a])) and np.all(np.isnan(y[b:])) and not np.any(np.isnan(y[a:b]))
+            B.spmv_range(0, a, algo)
+            B.spmv_range(b, hi - lo, algo)
+            assert_within_bound(B.get_y(), y_full[lo:hi], scale[lo:hi], np.float64, "shard %d %s" % (r, hs.ALGO_NAMES[algo]))
+        with pytest.raises(hs.HspmvError):
+            B.spmv_range(0, 5, hs.ALGO_CSR_MERGE)
