@@ -266,7 +266,10 @@ def run_ours(args, rank, world, local_rank):
         ranges = hd.gather_col_ranges((cmin, cmax))
         interior = A.interior_rows(lo - cmin, hi - cmin)
         sh = hd.ShardedSpMV(row_lo, ranges, rank, x_local, compute, interior)
-        step = lambda: sh.step(overlap=not args.no_overlap)   # noqa: E731
+        if args.no_exchange:   # diagnosis only: local kernels without the halo traffic (x is static)
+            step = lambda: compute(0, m_loc)                  # noqa: E731
+        else:
+            step = lambda: sh.step(overlap=not args.no_overlap)   # noqa: E731
         halo_bytes = sh.halo_elems * 8
     else:
         step = lambda: compute(0, m_loc)                      # noqa: E731
@@ -279,7 +282,8 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    for _ in range(max(args.warmup, 3)):
+    n_warm = max(args.warmup, 3) if world == 1 else max(args.warmup, 10)   # NCCL P2P channels settle late
+    for _ in range(n_warm):
         step()
     # ---- timed: K steps, device events, max over ranks
     barrier()
@@ -348,11 +352,11 @@ def run_ours(args, rank, world, local_rank):
             pass
         line = {
             "metric": "fp64 SpMV GFLOP/s", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "warmup": n_warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "stencil27_g%d_csr" % g, "n": n, "nnz": nnz_total, "format": "csr",
                        "kernel": kernel_name, "partition": "nnz-balanced row blocks" if world > 1 else "single GPU",
-                       "halo_bytes_per_rank_per_step": halo_bytes, "overlap": world > 1 and not args.no_overlap,
+                       "halo_bytes_per_rank_per_step": halo_bytes, "overlap": world > 1 and not args.no_overlap, "exchange": not args.no_exchange,
                        "l2": "input (21.9 GB) >> L2 (126 MB): no flush needed"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                          "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
@@ -386,6 +390,7 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=CPU_SAMPLE_ROWS)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--no-exchange", action="store_true", help="diagnosis: skip the halo exchange (invalid as a result)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -293,10 +293,10 @@ int run_csr_vector(hspmv_matrix *A, const T *x, T *y, cudaStream_t st, int64_t r
   return HSPMV_OK;
 }
 
-template <typename T, int VEC, int CH>
-int launch_csrk_ch(hspmv_matrix *A, const hspmv::CsrkParams<T> &p, int grid, int warps, size_t smem,
-                   cudaStream_t st) {
-  auto kern = hspmv::csrk_tma_kernel<T, VEC, CH>;
+template <typename T, int VEC, int MAIN, int TAIL>
+int launch_csrk_one(hspmv_matrix *A, const hspmv::CsrkParams<T> &p, int grid, int warps, size_t smem,
+                    cudaStream_t st) {
+  auto kern = hspmv::csrk_tma_kernel<T, VEC, MAIN, TAIL>;
   static size_t configured[64] = {0}; // per device: opt-in shared memory already granted
   size_t &have = configured[A->dev.device & 63];
   if (smem > have) {
@@ -308,12 +308,45 @@ int launch_csrk_ch(hspmv_matrix *A, const hspmv::CsrkParams<T> &p, int grid, int
   return HSPMV_OK;
 }
 
-template <typename T, int VEC>
+// The (lanes per row, unmasked chunk, masked chunk) variants that are compiled.  MAIN = 0 is the
+// fully masked loop; the others run MAIN-slot unmasked chunks and finish a row with TAIL-slot
+// masked ones.  pick_variant() snaps a request to the nearest compiled shape.
+#define HSPMV_CSRK_VARIANTS(X) \
+  X(1, 0, 4) X(1, 4, 4) X(1, 8, 4) X(1, 9, 4) X(1, 13, 4) \
+  X(2, 0, 8) X(2, 4, 2) X(2, 6, 2) X(2, 8, 2) X(2, 13, 1) \
+  X(4, 0, 8) X(4, 3, 1) X(4, 4, 2) X(4, 6, 1) X(4, 8, 2) \
+  X(8, 0, 4) X(8, 3, 1) X(8, 4, 2) X(8, 8, 2) \
+  X(16, 0, 4) X(16, 4, 2) X(16, 8, 2) \
+  X(32, 0, 4) X(32, 4, 2) X(32, 8, 2)
+
+struct CsrkVariant { int vec, main, tail; };
+static const CsrkVariant kCsrkVariants[] = {
+#define X(v, m, t) {v, m, t},
+    HSPMV_CSRK_VARIANTS(X)
+#undef X
+};
+
+// largest compiled MAIN <= want for this vec (want < 0: masked-only)
+CsrkVariant pick_variant(int vec, int want_main) {
+  CsrkVariant best = {vec, 0, 4};
+  bool have = false;
+  for (const CsrkVariant &c : kCsrkVariants) {
+    if (c.vec != vec) continue;
+    if (!have) { best = c; have = true; }
+    if (c.main <= want_main && c.main >= best.main) best = c;
+    if (want_main <= 0 && c.main == 0) { best = c; break; }
+  }
+  return best;
+}
+
+template <typename T>
 int launch_csrk(hspmv_matrix *A, const hspmv::CsrkParams<T> &p, int grid, int warps, size_t smem,
-                cudaStream_t st, int chunk) {
-  if (chunk >= 16) return launch_csrk_ch<T, VEC, 16>(A, p, grid, warps, smem, st);
-  if (chunk >= 8) return launch_csrk_ch<T, VEC, 8>(A, p, grid, warps, smem, st);
-  return launch_csrk_ch<T, VEC, 4>(A, p, grid, warps, smem, st);
+                cudaStream_t st, const CsrkVariant &v) {
+#define X(vv, mm, tt) \
+  if (v.vec == vv && v.main == mm && v.tail == tt) return launch_csrk_one<T, vv, mm, tt>(A, p, grid, warps, smem, st);
+  HSPMV_CSRK_VARIANTS(X)
+#undef X
+  return fail(HSPMV_EINVAL, "no compiled csrk_tma variant for this (vec, chunk)");
 }
 
 // CSRK (k = 2,3 after hspmv_build_csrk / hspmv_create_csrk) and CSR_STREAM (k = 1, fixed-row tiles)
@@ -327,9 +360,15 @@ int run_csrk(hspmv_matrix *A, bool stream_mode, const T *x, T *y, cudaStream_t s
   // lanes per row: one round of `chunk` gathers per lane should cover the mean row
   int vec = (int)A->opt[HSPMV_OPT_VEC];
   if (vec <= 0) vec = mean <= 8 ? 1 : mean <= 16 ? 2 : mean <= 40 ? 4 : mean <= 96 ? 8 : mean <= 256 ? 16 : 32;
+  // gathers a lane keeps in flight per unmasked chunk: the whole share of a typical row if it is
+  // short enough (then a row costs one round of latency), else a divisor-ish of it.
+  // HSPMV_OPT_CHUNK: > 0 requests that chunk, < 0 forces the fully masked loop.
   int chunk = (int)A->opt[HSPMV_OPT_CHUNK];
-  if (chunk <= 0) chunk = 8;
-  chunk = chunk >= 16 ? 16 : chunk >= 8 ? 8 : 4;
+  if (chunk == 0) {
+    const int per_lane = (int)(mean / vec);           // floor: every lane of the group has that many
+    chunk = per_lane <= 13 ? per_lane : (per_lane % 9 == 0 ? 9 : 8);
+  }
+  const CsrkVariant variant = pick_variant(vec, chunk);
   int warps = (int)A->opt[HSPMV_OPT_WARPS];
   if (warps <= 0) warps = 16; // r1 sweep: occupancy matters more than stage size (profiles/)
   if (warps > 16) warps = 16;
@@ -414,19 +453,11 @@ int run_csrk(hspmv_matrix *A, bool stream_mode, const T *x, T *y, cudaStream_t s
   if (grid > work_items) grid = work_items;
   if (grid < 1) grid = 1;
 
-  int rc;
-  switch (vec) {
-  case 1: rc = launch_csrk<T, 1>(A, p, (int)grid, warps, smem, st, chunk); break;
-  case 2: rc = launch_csrk<T, 2>(A, p, (int)grid, warps, smem, st, chunk); break;
-  case 4: rc = launch_csrk<T, 4>(A, p, (int)grid, warps, smem, st, chunk); break;
-  case 8: rc = launch_csrk<T, 8>(A, p, (int)grid, warps, smem, st, chunk); break;
-  case 16: rc = launch_csrk<T, 16>(A, p, (int)grid, warps, smem, st, chunk); break;
-  default: rc = launch_csrk<T, 32>(A, p, (int)grid, warps, smem, st, chunk); vec = 32; break;
-  }
+  int rc = launch_csrk<T>(A, p, (int)grid, warps, smem, st, variant);
   if (rc) return rc;
   char name[160];
-  std::snprintf(name, sizeof(name), "csrk_tma<%s,vec=%d,ch=%d> k=%d grid=%d warps=%d stages=%d cap_nnz=%d cap_rows=%d%s",
-                sizeof(T) == 8 ? "f64" : "f32", vec, chunk, p.k, (int)grid, warps, stages, cap_nnz, cap_rows,
+  std::snprintf(name, sizeof(name), "csrk_tma<%s,vec=%d,main=%d,tail=%d> k=%d grid=%d warps=%d stages=%d cap_nnz=%d cap_rows=%d%s",
+                sizeof(T) == 8 ? "f64" : "f32", vec, variant.main, variant.tail, p.k, (int)grid, warps, stages, cap_nnz, cap_rows,
                 stream_mode ? " (CSR stream tiles)" : "");
   A->last_kernel = name;
   return HSPMV_OK;

@@ -279,14 +279,21 @@ __host__ __device__ inline size_t csrk_stage_bytes(int cap_nnz, int cap_rows, si
   return 16 + (size_t)(cap_rows + 8) * 4 + (size_t)(cap_nnz + 8) * 4 + (size_t)(cap_nnz + 8) * vsize;
 }
 
-// Rows [r0,r1) of one super-row: row -> group of VEC lanes.  The nonzeros of a row are taken in
-// chunks of CH per lane; within a chunk every shared-memory read and every x gather is issued
-// before the first FMA, so a lane has CH independent gathers in flight (the gathers, not the
-// streamed matrix data, are what this loop waits for -- profiles/r1_stream_before.txt).
-template <typename T, int VEC, int CH>
+// Rows [r0,r1) of one super-row: row -> group of VEC lanes (VEC = 1: the CSR-k "row -> lane").
+// A lane's share of a row (every VEC-th nonzero) is consumed in two loops:
+//   MAIN  unmasked chunks of MAIN slots: all MAIN column reads, value reads and x gathers are
+//         issued before the first FMA, so a lane keeps MAIN independent gathers in flight (the
+//         gathers, not the streamed matrix data, are what this loop waits for -- see
+//         profiles/r1_*): 5 instructions per nonzero;
+//   TAIL  what is left (< MAIN slots) in masked chunks of TAIL slots: a slot past the row's end
+//         re-reads the row's LAST entry with value 0, so the gather stays unconditional and inside
+//         the row's own column set (0 * x[c] only meets an x entry this row references anyway).
+// MAIN = 0 disables the unmasked loop.  Index type I: int for the staged path (offsets into the
+// shared-memory window), int64_t for the unstaged path (global nonzero indices).
+template <typename T, int VEC, int MAIN, int TAIL, typename I>
 __device__ __forceinline__ void csrk_rows(int r0, int r1, const int *__restrict__ rp_w, int rbase,
                                           const int *__restrict__ ci_w, const T *__restrict__ val_w,
-                                          int64_t ebase, const T *__restrict__ x, T *__restrict__ y,
+                                          I ebase, const T *__restrict__ x, T *__restrict__ y,
                                           int lane) {
   const int sub = lane & (VEC - 1);
   const int gid = lane / VEC;
@@ -294,37 +301,51 @@ __device__ __forceinline__ void csrk_rows(int r0, int r1, const int *__restrict_
   for (int rb = r0; rb < r1; rb += 32 / VEC) {
     const int r = rb + gid;
     const bool active = r < r1;
-    int64_t rs = 0, re = 0;
+    I rs = 0, re = 0;
     if (active) {
-      rs = rp_w[r - rbase];
-      re = rp_w[r + 1 - rbase];
+      rs = (I)rp_w[r - rbase] - ebase;
+      re = (I)rp_w[r + 1 - rbase] - ebase;
     }
     T acc = 0;
-    for (int64_t j0 = rs + sub - ebase; j0 < re - ebase; j0 += VEC * CH) {
-      int c[CH];
-      T v[CH], xv[CH];
-      const int64_t lim = re - ebase;
+    I j = rs + sub;
+    if (MAIN > 0) {
+      for (; j + (I)((MAIN - 1) * VEC) < re; j += VEC * MAIN) {
+        int c[MAIN > 0 ? MAIN : 1];
+        T v[MAIN > 0 ? MAIN : 1], xv[MAIN > 0 ? MAIN : 1];
 #pragma unroll
-      for (int u = 0; u < CH; ++u) {
-        const int64_t j = j0 + u * VEC;
-        const bool ok = j < lim;
-        c[u] = ok ? ci_w[j] : 0;
-        v[u] = ok ? val_w[j] : (T)0;
+        for (int u = 0; u < MAIN; ++u) {
+          c[u] = ci_w[j + u * VEC];
+          v[u] = val_w[j + u * VEC];
+        }
+#pragma unroll
+        for (int u = 0; u < MAIN; ++u) xv[u] = __ldg(x + c[u]);
+#pragma unroll
+        for (int u = 0; u < MAIN; ++u) acc += v[u] * xv[u];
+      }
+    }
+    const I last = re - 1;
+    for (; j < re; j += VEC * TAIL) {
+      int c[TAIL];
+      T v[TAIL], xv[TAIL];
+#pragma unroll
+      for (int u = 0; u < TAIL; ++u) {
+        const I jj = j + u * VEC;
+        const I jc = jj < last ? jj : last;
+        c[u] = ci_w[jc];
+        v[u] = val_w[jc];
+        if (jj > last) v[u] = (T)0;
       }
 #pragma unroll
-      for (int u = 0; u < CH; ++u) xv[u] = __ldg(x + c[u]);
+      for (int u = 0; u < TAIL; ++u) xv[u] = __ldg(x + c[u]);
 #pragma unroll
-      for (int u = 0; u < CH; ++u) {
-        const T t = v[u] * xv[u];
-        acc += (j0 + u * VEC < lim) ? t : (T)0; // select, not multiply-by-zero: x[0] may be Inf/NaN
-      }
+      for (int u = 0; u < TAIL; ++u) acc += v[u] * xv[u];
     }
     acc = group_sum<T, VEC>(acc);
     if (active && sub == 0) y[r] = acc;
   }
 }
 
-template <typename T, int VEC, int CH>
+template <typename T, int VEC, int MAIN, int TAIL>
 __global__ void __launch_bounds__(512, 1) csrk_tma_kernel(const CsrkParams<T> p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
@@ -442,9 +463,9 @@ __global__ void __launch_bounds__(512, 1) csrk_tma_kernel(const CsrkParams<T> p)
       const int *ci_w = rp_w + (p.cap_rows + 8);
       const T *va_w = reinterpret_cast<const T *>(reinterpret_cast<const unsigned char *>(ci_w) +
                                                    (size_t)(p.cap_nnz + 8) * 4);
-      csrk_rows<T, VEC, CH>(r0, r1, rp_w, r0 & ~3, ci_w, va_w, (int64_t)(e0 & ~3), p.x, p.y, lane);
+      csrk_rows<T, VEC, MAIN, TAIL, int>(r0, r1, rp_w, r0 & ~3, ci_w, va_w, e0 & ~3, p.x, p.y, lane);
     } else {
-      csrk_rows<T, VEC, CH>(r0, r1, p.rp, 0, p.ci, p.val, 0, p.x, p.y, lane);
+      csrk_rows<T, VEC, MAIN, TAIL, int64_t>(r0, r1, p.rp, 0, p.ci, p.val, (int64_t)0, p.x, p.y, lane);
     }
     __syncwarp();
     --live;

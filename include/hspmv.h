@@ -58,7 +58,7 @@ enum {
   HSPMV_OPT_L2_PERSIST_X = 7, /* 1: put x under a persisting L2 access-policy window */
   HSPMV_OPT_MERGE_TILE = 8,   /* CSR_MERGE: nonzeros per CTA tile */
   HSPMV_OPT_THREADS = 9,      /* CSR_VECTOR / CSR_MERGE block size */
-  HSPMV_OPT_CHUNK = 10        /* TMA kernels: x gathers a lane keeps in flight (4, 8 or 16); 0 = auto */
+  HSPMV_OPT_CHUNK = 10        /* TMA kernels: unmasked x gathers a lane keeps in flight per chunk; 0 = auto, < 0 = masked loop only */
 };
 
 /* ---- runtime ---------------------------------------------------------------------- */

@@ -76,19 +76,20 @@ def main():
         run(A, hs.ALGO_CSR_STREAM, {hs.OPT_VEC: vec}, a.iters, F, a.peak, tag + "stream vec=%d default" % vec, out)
     if not a.quick:
         best = None
-        for vec in ((2, 4, 8) if a.kind == 27 else (1, 2)):
-            for ch in (4, 8):
-                for warps, stages in ((16, 2), (12, 3), (10, 3), (8, 4), (14, 2)):
-                    for rpt in ((8, 16, 24, 32) if a.kind == 27 else (64, 96, 128)):
-                        if rpt % (32 // vec):
-                            continue
-                        r = run(A, hs.ALGO_CSR_STREAM, {hs.OPT_VEC: vec, hs.OPT_WARPS: warps, hs.OPT_STAGES: stages, hs.OPT_ROWS_PER_TILE: rpt, hs.OPT_CHUNK: ch},
-                                a.iters, F, a.peak, tag + "stream vec=%d ch=%d w=%d s=%d rpt=%d" % (vec, ch, warps, stages, rpt), out)
-                        if r and (best is None or r["gbs"] > best["gbs"]):
-                            best = r
+        if a.kind == 27:
+            grid = [(1, 9, 32), (1, 13, 32), (1, 8, 32), (1, -1, 32), (1, 9, 64), (2, 13, 16), (2, 13, 32), (2, 6, 16), (2, 8, 32), (2, -1, 16),
+                    (4, 6, 16), (4, 6, 24), (4, 6, 32), (4, 3, 24), (4, -1, 24), (4, -1, 16), (8, 3, 16), (8, 3, 24), (8, -1, 16)]
+        else:
+            grid = [(1, 4, 96), (1, 4, 128), (1, 4, 64), (1, -1, 96), (2, -1, 64), (1, 4, 160)]
+        for vec, ch, rpt in grid:
+            for warps, stages in ((16, 2), (12, 3), (8, 4)):
+                r = run(A, hs.ALGO_CSR_STREAM, {hs.OPT_VEC: vec, hs.OPT_WARPS: warps, hs.OPT_STAGES: stages, hs.OPT_ROWS_PER_TILE: rpt, hs.OPT_CHUNK: ch},
+                        a.iters, F, a.peak, tag + "stream vec=%d ch=%d w=%d s=%d rpt=%d" % (vec, ch, warps, stages, rpt), out)
+                if r and (best is None or r["gbs"] > best["gbs"]):
+                    best = r
         print("BEST stream:", best["label"], "%.1f GB/s" % best["gbs"], best["kernel"])
     if a.csrk and i["nnz"] < 300e6:
-        for k, sizes in ((2, [16]), (3, [16, 16])):
+        for k, sizes in ((2, [16]), (2, [32]), (3, [16, 16]), (3, [32, 8])):
             B = hs.Matrix.stencil(a.kind, a.g, dt, 0)
             t0 = time.time()
             B.build_csrk(k, sizes)
@@ -99,8 +100,8 @@ def main():
             for vec in svecs[:3]:
                 run(B, hs.ALGO_CSRK, {hs.OPT_VEC: vec}, a.iters, F, a.peak, tag + "csrk k=%d %s vec=%d" % (k, sizes, vec), out)
             if not a.quick:
-                for vec in (2, 4):
-                    for warps, stages, ch in ((16, 2, 8), (16, 2, 4), (12, 3, 8), (10, 3, 8)):
+                for vec, ch in ((1, 9), (2, 13), (4, 6), (4, -1)):
+                    for warps, stages in ((16, 2), (12, 3)):
                         run(B, hs.ALGO_CSRK, {hs.OPT_VEC: vec, hs.OPT_WARPS: warps, hs.OPT_STAGES: stages, hs.OPT_CHUNK: ch}, a.iters, F, a.peak,
                             tag + "csrk k=%d %s vec=%d w=%d s=%d ch=%d" % (k, sizes, vec, warps, stages, ch), out)
             B.close()
