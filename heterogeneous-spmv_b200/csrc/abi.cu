@@ -5,6 +5,7 @@
 #include "host_index.h"
 #include "kernels.cuh"
 #include "merge.cuh"
+#include "csrk_variants.h"
 
 #include <atomic>
 #include <cstdio>
@@ -80,6 +81,8 @@ struct hspmv_matrix {
   int64_t bin_ptr[hspmv::NUM_BINS + 1] = {0};
   int64_t stats[10] = {0};
   bool stats_ready = false;
+
+  int64_t sr_max_rows = 0, sr_max_nnz = 0; // largest super-row (exact stage capacity)
 
   // CSR_MERGE
   int64_t merge_tile = 0, merge_tiles = 0;
@@ -293,60 +296,29 @@ int run_csr_vector(hspmv_matrix *A, const T *x, T *y, cudaStream_t st, int64_t r
   return HSPMV_OK;
 }
 
-template <typename T, int VEC, int MAIN, int TAIL>
-int launch_csrk_one(hspmv_matrix *A, const hspmv::CsrkParams<T> &p, int grid, int warps, size_t smem,
-                    cudaStream_t st) {
-  auto kern = hspmv::csrk_tma_kernel<T, VEC, MAIN, TAIL>;
-  static size_t configured[64] = {0}; // per device: opt-in shared memory already granted
-  size_t &have = configured[A->dev.device & 63];
-  if (smem > have) {
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    have = smem;
-  }
-  kern<<<grid, warps * 32, smem, st>>>(p);
-  LAUNCHED();
-  return HSPMV_OK;
-}
-
-// The (lanes per row, unmasked chunk, masked chunk) variants that are compiled.  MAIN = 0 is the
-// fully masked loop; the others run MAIN-slot unmasked chunks and finish a row with TAIL-slot
-// masked ones.  pick_variant() snaps a request to the nearest compiled shape.
-#define HSPMV_CSRK_VARIANTS(X) \
-  X(1, 0, 4) X(1, 4, 4) X(1, 8, 4) X(1, 9, 4) X(1, 13, 4) \
-  X(2, 0, 8) X(2, 4, 2) X(2, 6, 2) X(2, 8, 2) X(2, 13, 1) \
-  X(4, 0, 8) X(4, 3, 1) X(4, 4, 2) X(4, 6, 1) X(4, 8, 2) \
-  X(8, 0, 4) X(8, 3, 1) X(8, 4, 2) X(8, 8, 2) \
-  X(16, 0, 4) X(16, 4, 2) X(16, 8, 2) \
-  X(32, 0, 4) X(32, 4, 2) X(32, 8, 2)
-
-struct CsrkVariant { int vec, main, tail; };
-static const CsrkVariant kCsrkVariants[] = {
-#define X(v, m, t) {v, m, t},
-    HSPMV_CSRK_VARIANTS(X)
-#undef X
-};
-
-// largest compiled MAIN <= want for this vec (want < 0: masked-only)
-CsrkVariant pick_variant(int vec, int want_main) {
-  CsrkVariant best = {vec, 0, 4};
+// largest compiled MAIN <= want_main for this vec (want_main <= 0: the fully masked loop)
+hspmv::CsrkVariant pick_variant(int vec, int want_main) {
+  hspmv::CsrkVariant best = {vec, 0, 4};
   bool have = false;
-  for (const CsrkVariant &c : kCsrkVariants) {
+  for (int i = 0; i < hspmv::kNumCsrkVariants; ++i) {
+    const hspmv::CsrkVariant &c = hspmv::kCsrkVariants[i];
     if (c.vec != vec) continue;
-    if (!have) { best = c; have = true; }
-    if (c.main <= want_main && c.main >= best.main) best = c;
-    if (want_main <= 0 && c.main == 0) { best = c; break; }
+    if (!have || (c.main <= want_main && c.main > best.main) || (best.main > want_main && c.main < best.main)) {
+      if (!have || c.main <= want_main || best.main > want_main) best = c;
+      have = true;
+    }
   }
   return best;
 }
 
 template <typename T>
 int launch_csrk(hspmv_matrix *A, const hspmv::CsrkParams<T> &p, int grid, int warps, size_t smem,
-                cudaStream_t st, const CsrkVariant &v) {
-#define X(vv, mm, tt) \
-  if (v.vec == vv && v.main == mm && v.tail == tt) return launch_csrk_one<T, vv, mm, tt>(A, p, grid, warps, smem, st);
-  HSPMV_CSRK_VARIANTS(X)
-#undef X
-  return fail(HSPMV_EINVAL, "no compiled csrk_tma variant for this (vec, chunk)");
+                cudaStream_t st, const hspmv::CsrkVariant &v) {
+  const int rc = hspmv::launch_csrk_variant(p, grid, warps, smem, st, A->dev.device, v);
+  if (rc == -1) return fail(HSPMV_EINVAL, "no compiled csrk_tma variant for this (vec, chunk)");
+  if (rc) return fail(HSPMV_ECUDA, std::string("csrk_tma launch: ") + cudaGetErrorString((cudaError_t)rc));
+  LAUNCHED();
+  return HSPMV_OK;
 }
 
 // CSRK (k = 2,3 after hspmv_build_csrk / hspmv_create_csrk) and CSR_STREAM (k = 1, fixed-row tiles)
@@ -359,7 +331,10 @@ int run_csrk(hspmv_matrix *A, bool stream_mode, const T *x, T *y, cudaStream_t s
   const int64_t max_len = A->stats[8];
   // lanes per row: one round of `chunk` gathers per lane should cover the mean row
   int vec = (int)A->opt[HSPMV_OPT_VEC];
-  if (vec <= 0) vec = mean <= 8 ? 1 : mean <= 16 ? 2 : mean <= 40 ? 4 : mean <= 96 ? 8 : mean <= 256 ? 16 : 32;
+  if (vec <= 0) { // smallest group whose lanes each get <= 14 nonzeros of a typical row (one unmasked chunk)
+    vec = 1;
+    while (vec < 32 && mean / vec > 14.0) vec <<= 1;
+  }
   // gathers a lane keeps in flight per unmasked chunk: the whole share of a typical row if it is
   // short enough (then a row costs one round of latency), else a divisor-ish of it.
   // HSPMV_OPT_CHUNK: > 0 requests that chunk, < 0 forces the fully masked loop.
@@ -367,8 +342,9 @@ int run_csrk(hspmv_matrix *A, bool stream_mode, const T *x, T *y, cudaStream_t s
   if (chunk == 0) {
     const int per_lane = (int)(mean / vec);           // floor: every lane of the group has that many
     chunk = per_lane <= 13 ? per_lane : (per_lane % 9 == 0 ? 9 : 8);
+    if (chunk < 3) chunk = -1;
   }
-  const CsrkVariant variant = pick_variant(vec, chunk);
+  const hspmv::CsrkVariant variant = pick_variant(vec, chunk);
   int warps = (int)A->opt[HSPMV_OPT_WARPS];
   if (warps <= 0) warps = 16; // r1 sweep: occupancy matters more than stage size (profiles/)
   if (warps > 16) warps = 16;
@@ -394,11 +370,11 @@ int run_csrk(hspmv_matrix *A, bool stream_mode, const T *x, T *y, cudaStream_t s
   int64_t typical_rows, typical_nnz, worst_nnz;
   if (stream_mode) {
     int rpt = (int)A->opt[HSPMV_OPT_ROWS_PER_TILE];
-    if (rpt <= 0) { // ~448 nonzeros per tile, whole passes of the warp
+    if (rpt <= 0) { // whole passes of the warp, ~432 nonzeros per tile (r1 sweep: 16 warps x 2 stages of that)
       const int per_pass = 32 / vec;
-      rpt = (int)(448.0 / (mean > 1 ? mean : 1.0) + 0.5);
-      rpt = ((rpt + per_pass - 1) / per_pass) * per_pass;
-      if (rpt < per_pass) rpt = per_pass;
+      int passes = (int)(432.0 / ((mean > 1 ? mean : 1.0) * per_pass) + 0.5);
+      if (passes < 1) passes = 1;
+      rpt = passes * per_pass;
     }
     p.k = 1;
     p.rows_per_tile = rpt;
@@ -411,7 +387,7 @@ int run_csrk(hspmv_matrix *A, bool stream_mode, const T *x, T *y, cudaStream_t s
     p.n_sr = A->n_sr;
     typical_rows = A->n_sr ? (A->m + A->n_sr - 1) / A->n_sr : 1;
     typical_nnz = A->n_sr ? (A->nnz + A->n_sr - 1) / A->n_sr : 1;
-    worst_nnz = typical_nnz * 4;
+    worst_nnz = A->sr_max_nnz > 0 ? A->sr_max_nnz : typical_nnz * 4;
   }
 
   // Stage capacity: explicit option, else 1.5x the typical super-row (never more than the worst
@@ -426,7 +402,9 @@ int run_csrk(hspmv_matrix *A, bool stream_mode, const T *x, T *y, cudaStream_t s
   }
   if (cap_nnz < 64) cap_nnz = 64;
   cap_nnz = (cap_nnz + 3) & ~3;
-  int cap_rows = (int)((typical_rows * (stream_mode ? 1 : 2) + (stream_mode ? 0 : 32) + 3) & ~(int64_t)3);
+  int64_t want_rows = stream_mode ? typical_rows : typical_rows * 2 + 32;
+  if (!stream_mode && A->sr_max_rows > 0 && A->sr_max_rows < want_rows) want_rows = A->sr_max_rows;
+  int cap_rows = (int)((want_rows + 3) & ~(int64_t)3);
   if (cap_rows < 8) cap_rows = 8;
   const size_t budget = A->dev.max_smem_optin - 1024;
   auto total = [&](int w, int cn, int cr) {
@@ -583,6 +561,13 @@ int do_spmv(hspmv_matrix *A, int algo, const void *dx, void *dy, cudaStream_t st
 }
 
 int upload_csrk_maps(hspmv_matrix *A) {
+  A->sr_max_rows = A->sr_max_nnz = 0;
+  if (!A->h_rp.empty())
+    for (int64_t s = 0; s < A->n_sr; ++s) {
+      const int64_t r0 = A->h_sr[(size_t)s], r1 = A->h_sr[(size_t)s + 1];
+      A->sr_max_rows = std::max(A->sr_max_rows, r1 - r0);
+      A->sr_max_nnz = std::max(A->sr_max_nnz, (int64_t)A->h_rp[(size_t)r1] - A->h_rp[(size_t)r0]);
+    }
   for (u32 **p : {&A->d_sr, &A->d_ssr, &A->d_sr_e, &A->d_perm})
     if (*p) {
       cudaFree(*p);

@@ -4,9 +4,9 @@
 //             helpers/csr3params.m:8-37)
 //   1 Ampere  cuda-spmv-csrk/cuda/spmv-auto-ampere.cu:130-158
 //   2 MI100   cuda-spmv-csrk/hip/spmv-auto-mi100.cu:130-159 (own base formula, Ampere-style rescale)
-//   3 B200    this library: the TMA kernel wants a super-row to fill one shared-memory stage
-//             (about 768 nonzeros) and to hold a multiple of (32 / lanes-per-row) rows; the
-//             super-super-row is one CTA's worth of super-rows (8 warps).
+//   3 B200    this library: a super-row fills one shared-memory stage of the TMA kernel (about
+//             432 nonzeros, a multiple of 32 / lanes-per-row rows); a super-super-row is one
+//             CTA's worth of super-rows (16 warps).  Retuned from the r1 sweeps in profiles/.
 #include "host_index.h"
 
 #include <cmath>
@@ -63,16 +63,18 @@ int auto_params(int64_t nnz, int64_t n_rows, int arch, int sizes[2], int *veclev
       srs = (int)std::floor((double)ssrs / 4 + 0.5);
     }
   } else if (arch == 3) {
-    // lanes per row from the mean row length, then rows per super-row so that one super-row is
-    // ~768 nonzeros but at least one full pass of the warp
-    vec = d <= 12 ? 1 : d <= 48 ? 2 : d <= 96 ? 4 : d <= 192 ? 8 : d <= 384 ? 16 : 32;
+    // Same rule as the kernel's own defaults (abi.cu:run_csrk): lanes per row = smallest power of
+    // two that leaves each lane <= 14 nonzeros of a typical row (one unmasked chunk of gathers);
+    // a super-row = whole passes of the warp holding ~432 nonzeros (16 warps x 2 shared-memory
+    // stages of that fill an SM); a super-super-row = one CTA's 16 warps.
+    vec = 1;
+    while (vec < 32 && d / vec > 14.0) vec <<= 1;
     const int rows_per_pass = 32 / vec;
-    int rows = (int)std::floor(768.0 / (d > 1 ? d : 1.0) + 0.5);
-    rows = ((rows + rows_per_pass - 1) / rows_per_pass) * rows_per_pass;
-    if (rows < rows_per_pass) rows = rows_per_pass;
-    ssrs = rows; // sizes[0]: rows per super-row (nnz-weighted) -- the reference calls it "ssrs" (Q9)
-    srs = 8;     // sizes[1]: super-rows per super-super-row = warps per CTA
-    bdy = 8;
+    int passes = (int)std::floor(432.0 / ((d > 1 ? d : 1.0) * rows_per_pass) + 0.5);
+    if (passes < 1) passes = 1;
+    ssrs = passes * rows_per_pass; // sizes[0]: rows per super-row (nnz-weighted) -- the reference calls it "ssrs" (Q9)
+    srs = 16;                      // sizes[1]: super-rows per super-super-row = warps per CTA
+    bdy = 16;
   } else {
     return HSPMV_EINVAL;
   }

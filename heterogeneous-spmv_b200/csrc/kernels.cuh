@@ -500,7 +500,7 @@ __global__ void scatter_kernel(int64_t n, const uint32_t *__restrict__ perm,
     dst[perm[i]] = src[i];
 }
 // sr_e[s] = rp[sr_ptr[s]]
-__global__ void sr_offsets_kernel(int64_t n_sr, const uint32_t *__restrict__ sr_ptr,
+static __global__ void sr_offsets_kernel(int64_t n_sr, const uint32_t *__restrict__ sr_ptr,
                                   const int *__restrict__ rp, uint32_t *__restrict__ sr_e) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n_sr;
        i += (int64_t)gridDim.x * blockDim.x)
@@ -509,7 +509,7 @@ __global__ void sr_offsets_kernel(int64_t n_sr, const uint32_t *__restrict__ sr_
 // Rows whose columns all lie in [own_lo, own_hi) are "interior" (need no halo).  Reports the last
 // non-interior row of the first half (+1) and the first non-interior row of the second half, so
 // that [row_a, row_b) is a contiguous all-interior range.  One warp per row.
-__global__ void interior_rows_kernel(int64_t m, const int *__restrict__ rp, const int *__restrict__ ci,
+static __global__ void interior_rows_kernel(int64_t m, const int *__restrict__ rp, const int *__restrict__ ci,
                                      int own_lo, int own_hi, int *row_a, int *row_b) {
   const int lane = threadIdx.x & 31;
   const int64_t n_warps = (int64_t)gridDim.x * blockDim.x / 32;
@@ -527,7 +527,7 @@ __global__ void interior_rows_kernel(int64_t m, const int *__restrict__ rp, cons
   }
 }
 
-__global__ void col_minmax_kernel(int64_t nnz, const int *__restrict__ ci, int *out_min,
+static __global__ void col_minmax_kernel(int64_t nnz, const int *__restrict__ ci, int *out_min,
                                   int *out_max) {
   int lo = INT32_MAX, hi = -1;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz;
