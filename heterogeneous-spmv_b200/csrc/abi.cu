@@ -951,6 +951,13 @@ int hspmv_set_y(hspmv_matrix *A, const void *y_host) {
   return HSPMV_OK;
 }
 
+int hspmv_sync(hspmv_matrix *A) {
+  if (!A) return fail(HSPMV_EINVAL, "null handle");
+  if (A->last_stream_valid) CU(cudaStreamSynchronize(A->last_stream));
+  CU(cudaStreamSynchronize(A->stream));
+  return HSPMV_OK;
+}
+
 void *hspmv_x_device(hspmv_matrix *A) { return A ? A->d_x : nullptr; }
 void *hspmv_y_device(hspmv_matrix *A) { return A ? A->d_y : nullptr; }
 

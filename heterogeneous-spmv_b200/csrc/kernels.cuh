@@ -239,6 +239,9 @@ struct SrCursor {
   const uint32_t *ssr_ptr;
   uint32_t pre_lo, pre_hi;    // k == 3: super-row range of the NEXT super-super-row, loaded one
                               // switch ahead so that its latency is off the warp's critical path
+  int carry;                  // k == 3: super-rows this CTA has dealt so far, mod W.  The CTA's
+                              // super-rows are dealt round-robin ACROSS super-super-rows, so a
+                              // 17-super-row SSR does not always give its extra one to warp 0
   int w, W;
   bool three;
   __device__ __forceinline__ void prefetch_range(int64_t ss) {
@@ -262,8 +265,11 @@ struct SrCursor {
       }
       s += s_step;
       if (s >= n_ssr) return false;
-      cur = (int64_t)pre_lo + w;
+      int first = w - carry;
+      if (first < 0) first += W;
+      cur = (int64_t)pre_lo + first;
       end = (int64_t)pre_hi;
+      carry = (int)((carry + (pre_hi - pre_lo)) % (uint32_t)W);
       prefetch_range(s + s_step);
     }
   }
@@ -377,12 +383,14 @@ __global__ void __launch_bounds__(512, 1) csrk_tma_kernel(const CsrkParams<T> p)
     cur.end = 0;
     cur.step = 0;
     cur.pre_lo = cur.pre_hi = 0;
+    cur.carry = 0;
     cur.prefetch_range(blockIdx.x);
   } else {
     cur.cur = (int64_t)blockIdx.x * W + w;
     cur.step = (int64_t)gridDim.x * W;
     cur.end = p.n_sr;
     cur.s = cur.s_step = 0;
+    cur.carry = 0;
   }
 
   const uint64_t policy = l2_policy_evict_first();

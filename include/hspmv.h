@@ -183,6 +183,10 @@ int hspmv_spmv(hspmv_matrix *A, int algo, const void *d_x, void *d_y, void *stre
  * the multi-GPU layer run the interior rows while the x halo is still in flight. */
 int hspmv_spmv_range(hspmv_matrix *A, int algo, int64_t row_lo, int64_t row_hi, const void *d_x,
                      void *d_y, void *stream);
+/* Blocks until everything this handle has enqueued (on its own stream and on the stream of the
+ * last hspmv_spmv) has finished: the cudaDeviceSynchronize() after each launch in the reference
+ * drivers (cuda-spmv-csr/spmv.cu:248, cuda-spmv-csrk/cuda/spmv.cu:200). */
+int hspmv_sync(hspmv_matrix *A);
 /* N timed launches after `warmup` untimed ones; ms_out[i] = device time of launch i from
  * CUDA events on the launching stream.  flush_l2 != 0 overwrites an L2-sized scratch buffer
  * before every launch (outside the event pair).  Replaces the host-timer loops at
