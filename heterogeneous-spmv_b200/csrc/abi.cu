@@ -95,6 +95,17 @@ struct hspmv_matrix {
   std::vector<unsigned char> h_val;
   std::vector<u32> h_perm, h_sr, h_ssr;
 
+  // pipelined host call (hspmv_spmv_host on large regular matrices): x pieces go up, row chunks
+  // are computed as soon as the pieces they reference have landed, y chunks go down meanwhile
+  struct Pipe {
+    bool tried = false, ok = false;
+    int chunks = 0;
+    std::vector<int64_t> row_lo, x_lo; // chunk row bounds, x piece bounds (chunks+1 each)
+    std::vector<int> need;             // last x piece chunk c reads
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    std::vector<cudaEvent_t> ev_x, ev_k;
+  } pipe;
+
   int64_t opt[16] = {0};
   cudaStream_t stream = nullptr; // handle's own stream (timed runs, set_x/get_y)
   cudaStream_t last_stream = nullptr; // stream of the most recent hspmv_spmv (may be the caller's)
@@ -109,7 +120,16 @@ struct hspmv_matrix {
 
 namespace {
 
+void free_pipe(hspmv_matrix *A) {
+  for (cudaEvent_t e : A->pipe.ev_x) cudaEventDestroy(e);
+  for (cudaEvent_t e : A->pipe.ev_k) cudaEventDestroy(e);
+  if (A->pipe.s_h2d) cudaStreamDestroy(A->pipe.s_h2d);
+  if (A->pipe.s_d2h) cudaStreamDestroy(A->pipe.s_d2h);
+  A->pipe = hspmv_matrix::Pipe();
+}
+
 void free_device(hspmv_matrix *A) {
+  free_pipe(A);
   void *ptrs[] = {A->d_rp, A->d_ci, A->d_val, A->d_x, A->d_y, A->d_tmp, A->d_sr, A->d_ssr,
                   A->d_sr_e, A->d_perm, A->d_bin_rows, A->d_tile_row, A->d_carry_row,
                   A->d_carry_val, A->d_flush};
@@ -884,6 +904,7 @@ int hspmv_build_csrk(hspmv_matrix *A, int k, const int *sup_row_sizes) {
   A->n_ssr = k == 3 ? (int64_t)A->h_ssr.size() - 1 : 0;
   A->bins_ready = false;
   A->merge_tile = 0;
+  free_pipe(A);
   hspmv::row_stats(A->m, A->h_rp.data(), A->stats);
   return upload_csrk_maps(A);
 }
@@ -1037,7 +1058,119 @@ int hspmv_spmv_timed(hspmv_matrix *A, int algo, int warmup, int iters, int flush
   return HSPMV_OK;
 }
 
+namespace {
+
+// Resolve AUTO the way dispatch() does; the pipelined host path needs a kernel that takes row ranges.
+int resolve_algo(hspmv_matrix *A, int algo) {
+  if (algo != HSPMV_ALGO_AUTO) return algo;
+  if (A->k >= 2) return HSPMV_ALGO_CSRK;
+  if (ensure_stats(A)) return HSPMV_ALGO_CSR_MERGE;
+  const double mean = A->m ? (double)A->nnz / (double)A->m : 0.0;
+  return (A->stats[8] <= 8 * (mean + 1) + 64) ? HSPMV_ALGO_CSR_STREAM : HSPMV_ALGO_CSR_MERGE;
+}
+
+int build_pipe(hspmv_matrix *A) {
+  hspmv_matrix::Pipe &P = A->pipe;
+  P.tried = true;
+  const size_t vs = A->vsize();
+  if (A->d_perm || A->k != 1 || (size_t)A->m * vs < ((size_t)32 << 20)) return HSPMV_OK; // small or permuted: plain path
+  int C = (int)(A->m / (2 << 20));
+  if (C < 4) C = 4;
+  if (C > 32) C = 32;
+  P.chunks = C;
+  P.row_lo.resize((size_t)C + 1);
+  P.x_lo.resize((size_t)C + 1);
+  for (int c = 0; c <= C; ++c) {
+    P.row_lo[(size_t)c] = ((A->m * c / C) + 3) & ~(int64_t)3; // 32 B-aligned y pieces
+    P.x_lo[(size_t)c] = ((A->n * c / C) + 3) & ~(int64_t)3;
+  }
+  P.row_lo[(size_t)C] = A->m;
+  P.x_lo[(size_t)C] = A->n;
+  // highest column each row chunk references -> the last x piece it has to wait for
+  std::vector<int> e((size_t)C + 1);
+  for (int c = 0; c <= C; ++c)
+    CU(cudaMemcpy(&e[(size_t)c], A->d_rp + P.row_lo[(size_t)c], 4, cudaMemcpyDeviceToHost));
+  int *d = nullptr;
+  CU(cudaMalloc(&d, (size_t)C * 8));
+  std::vector<int> init((size_t)C * 2);
+  for (int c = 0; c < C; ++c) {
+    init[(size_t)2 * c] = INT32_MAX;
+    init[(size_t)2 * c + 1] = -1;
+  }
+  CU(cudaMemcpy(d, init.data(), (size_t)C * 8, cudaMemcpyHostToDevice));
+  for (int c = 0; c < C; ++c) {
+    const int64_t cnt = (int64_t)e[(size_t)c + 1] - e[(size_t)c];
+    if (cnt <= 0) continue;
+    hspmv::col_minmax_kernel<<<grid_for(cnt, 256, A->dev.sms * 8), 256, 0, A->stream>>>(cnt, A->d_ci + e[(size_t)c], d + 2 * c, d + 2 * c + 1);
+    LAUNCHED();
+  }
+  CU(cudaStreamSynchronize(A->stream));
+  CU(cudaMemcpy(init.data(), d, (size_t)C * 8, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  P.need.assign((size_t)C, 0);
+  for (int c = 0; c < C; ++c) {
+    const int64_t cmax = init[(size_t)2 * c + 1];
+    int piece = 0;
+    while (piece + 1 < C && P.x_lo[(size_t)piece + 1] <= cmax) ++piece;
+    P.need[(size_t)c] = piece;
+  }
+  CU(cudaStreamCreateWithFlags(&P.s_h2d, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&P.s_d2h, cudaStreamNonBlocking));
+  P.ev_x.resize((size_t)C);
+  P.ev_k.resize((size_t)C);
+  for (int c = 0; c < C; ++c) {
+    CU(cudaEventCreateWithFlags(&P.ev_x[(size_t)c], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&P.ev_k[(size_t)c], cudaEventDisableTiming));
+  }
+  P.ok = true;
+  return HSPMV_OK;
+}
+
+int spmv_host_pipelined(hspmv_matrix *A, int algo, const void *x_host, void *y_host) {
+  hspmv_matrix::Pipe &P = A->pipe;
+  const size_t vs = A->vsize();
+  const int C = P.chunks;
+  for (int p = 0; p < C; ++p) {
+    const int64_t a = P.x_lo[(size_t)p], b = P.x_lo[(size_t)p + 1];
+    if (b > a)
+      CU(cudaMemcpyAsync((char *)A->d_x + (size_t)a * vs, (const char *)x_host + (size_t)a * vs, (size_t)(b - a) * vs,
+                         cudaMemcpyHostToDevice, P.s_h2d));
+    CU(cudaEventRecord(P.ev_x[(size_t)p], P.s_h2d));
+  }
+  int waited = -1;
+  for (int c = 0; c < C; ++c) {
+    const int64_t a = P.row_lo[(size_t)c], b = P.row_lo[(size_t)c + 1];
+    if (P.need[(size_t)c] > waited) { // pieces arrive in order: waiting for the last one needed is enough
+      waited = P.need[(size_t)c];
+      CU(cudaStreamWaitEvent(A->stream, P.ev_x[(size_t)waited], 0));
+    }
+    if (b > a) {
+      int rc = do_spmv(A, algo, nullptr, nullptr, A->stream, a, b);
+      if (rc) return rc;
+    }
+    CU(cudaEventRecord(P.ev_k[(size_t)c], A->stream));
+    CU(cudaStreamWaitEvent(P.s_d2h, P.ev_k[(size_t)c], 0));
+    if (b > a)
+      CU(cudaMemcpyAsync((char *)y_host + (size_t)a * vs, (const char *)A->d_y + (size_t)a * vs, (size_t)(b - a) * vs,
+                         cudaMemcpyDeviceToHost, P.s_d2h));
+  }
+  CU(cudaStreamSynchronize(P.s_d2h));
+  CU(cudaStreamSynchronize(A->stream));
+  return HSPMV_OK;
+}
+
+} // namespace
+
 int hspmv_spmv_host(hspmv_matrix *A, int algo, const void *x_host, void *y_host) {
+  if (!A || !x_host || !y_host) return fail(HSPMV_EINVAL, "null");
+  const int resolved = resolve_algo(A, algo);
+  if ((resolved == HSPMV_ALGO_CSR_STREAM || resolved == HSPMV_ALGO_CSR_VECTOR) && !A->opt[HSPMV_OPT_NO_PIPELINE]) {
+    if (!A->pipe.tried) {
+      int rc0 = build_pipe(A);
+      if (rc0) return rc0;
+    }
+    if (A->pipe.ok) return spmv_host_pipelined(A, resolved, x_host, y_host);
+  }
   int rc = hspmv_set_x(A, x_host);
   if (rc) return rc;
   rc = do_spmv(A, algo, nullptr, nullptr, A->stream);

@@ -58,6 +58,7 @@ enum {
   HSPMV_OPT_L2_PERSIST_X = 7, /* 1: put x under a persisting L2 access-policy window */
   HSPMV_OPT_MERGE_TILE = 8,   /* CSR_MERGE: nonzeros per CTA tile */
   HSPMV_OPT_THREADS = 9,      /* CSR_VECTOR / CSR_MERGE block size */
+  HSPMV_OPT_NO_PIPELINE = 11, /* 1: hspmv_spmv_host copies, computes, copies back strictly in sequence */
   HSPMV_OPT_CHUNK = 10        /* TMA kernels: unmasked x gathers a lane keeps in flight per chunk; 0 = auto, < 0 = masked loop only */
 };
 
@@ -194,7 +195,11 @@ int hspmv_sync(hspmv_matrix *A);
 int hspmv_spmv_timed(hspmv_matrix *A, int algo, int warmup, int iters, int flush_l2,
                      float *ms_out);
 /* End-to-end plugin call with HOST buffers: set_x (permute + H2D) -> kernel -> get_y (D2H,
- * original row order), synchronous.  This is setX + SpMV + getY of the reference drivers. */
+ * original row order), synchronous.  This is setX + SpMV + getY of the reference drivers.
+ * On large plain-CSR handles the three stages are pipelined over row chunks on three streams:
+ * x pieces go up in order, a row chunk is launched (hspmv_spmv_range) as soon as the last x piece
+ * it references has landed, its y piece goes down while later chunks compute.  Needs pinned host
+ * buffers to overlap; pageable buffers still work, without the overlap. */
 int hspmv_spmv_host(hspmv_matrix *A, int algo, const void *x_host, void *y_host);
 /* `iters` back-to-back hspmv_spmv_host calls bracketed by CUDA events on the handle's stream:
  * *ms_total covers every H2D copy of x, permutation, kernel and D2H copy of y. */
