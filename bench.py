@@ -252,10 +252,9 @@ def run_ours(args, rank, world, local_rank):
     A = hs.Matrix.stencil(27, g, np.float64, 0, row_lo=lo, row_hi=hi, col_shift=cmin, n_cols=cmax - cmin + 1)
     info = A.info()
     m_loc, nnz_loc = info["m"], info["nnz"]
-    x_local = torch.empty(cmax - cmin + 1, dtype=torch.float64, device="cuda")
-    idx = torch.arange(cmin, cmax + 1, device="cuda", dtype=torch.int64)
-    x_local.copy_(1.0 + (idx % 97).to(torch.float64) / 128.0)     # generators.vector_x
-    del idx
+    # x lives in the handle's own cudaMalloc'ed vector so that neighbours can map it (CUDA IPC)
+    x_local = hd.wrap_device_ptr(A.x_ptr(), cmax - cmin + 1, torch.float64)
+    A.fill_x_synthetic(cmin)                                       # generators.vector_x, global index
     y_local = torch.zeros(m_loc, dtype=torch.float64, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
 
@@ -265,7 +264,10 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         ranges = hd.gather_col_ranges((cmin, cmax))
         interior = A.interior_rows(lo - cmin, hi - cmin)
-        sh = hd.ShardedSpMV(row_lo, ranges, rank, x_local, compute, interior)
+        peer = None
+        if args.exchange == "peer":
+            peer = hd.PeerHalo(hs, A.x_ptr(), 8, row_lo, ranges, rank)
+        sh = hd.ShardedSpMV(row_lo, ranges, rank, x_local, compute, interior, peer=peer)
         if args.no_exchange:   # diagnosis only: local kernels without the halo traffic (x is static)
             step = lambda: compute(0, m_loc)                  # noqa: E731
         else:
@@ -356,7 +358,8 @@ def run_ours(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "stencil27_g%d_csr" % g, "n": n, "nnz": nnz_total, "format": "csr",
                        "kernel": kernel_name, "partition": "nnz-balanced row blocks" if world > 1 else "single GPU",
-                       "halo_bytes_per_rank_per_step": halo_bytes, "overlap": world > 1 and not args.no_overlap, "exchange": not args.no_exchange,
+                       "halo_bytes_per_rank_per_step": halo_bytes, "overlap": world > 1 and not args.no_overlap,
+                       "exchange": ("none" if args.no_exchange else args.exchange) if world > 1 else "n/a",
                        "l2": "input (21.9 GB) >> L2 (126 MB): no flush needed"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                          "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
@@ -376,6 +379,10 @@ def run_ours(args, rank, world, local_rank):
                           "OMP_SCHEDULE=static" % (min(args.cpu_rows, n), nnz_s)}
         print(json.dumps(line), flush=True)
     if world > 1:
+        if sh.peer is not None:
+            if sh.peer.timed_out():
+                raise SystemExit("bench.py: a halo flag wait timed out (a peer never arrived)")
+            sh.peer.close()
         dist.destroy_process_group()
 
 
@@ -390,6 +397,8 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=CPU_SAMPLE_ROWS)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="halo exchange: peer = NVLink stores into IPC-mapped neighbour buffers (default), nccl = send/recv")
     ap.add_argument("--no-exchange", action="store_true", help="diagnosis: skip the halo exchange (invalid as a result)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -556,8 +556,11 @@ int dispatch(hspmv_matrix *A, int algo, const void *dx, void *dy, cudaStream_t s
       rc = ensure_stats(A);
       if (rc) return rc;
       const double mean = A->m ? (double)A->nnz / (double)A->m : 0.0;
-      // regular short rows: the TMA tile engine; skewed row lengths: nnz-balanced merge
-      algo = (A->stats[8] <= 8 * (mean + 1) + 64) ? HSPMV_ALGO_CSR_STREAM : HSPMV_ALGO_CSR_MERGE;
+      // regular rows: the TMA tile engine.  Skewed row lengths (power law): the row-length-binned
+      // vector kernels -- on R-MAT scale 24 they run at 2.06 TB/s against 0.67 TB/s for the merge
+      // kernel (profiles/r1_configs_1to4_fullsize.jsonl); the random x gather (32 B sector per 8 B
+      // used) caps that matrix near 0.4 of the roofline whatever the row split.
+      algo = (A->stats[8] <= 8 * (mean + 1) + 64) ? HSPMV_ALGO_CSR_STREAM : HSPMV_ALGO_CSR_VECTOR;
     }
   }
   switch (algo) {
@@ -1064,9 +1067,9 @@ namespace {
 int resolve_algo(hspmv_matrix *A, int algo) {
   if (algo != HSPMV_ALGO_AUTO) return algo;
   if (A->k >= 2) return HSPMV_ALGO_CSRK;
-  if (ensure_stats(A)) return HSPMV_ALGO_CSR_MERGE;
+  if (ensure_stats(A)) return HSPMV_ALGO_CSR_VECTOR;
   const double mean = A->m ? (double)A->nnz / (double)A->m : 0.0;
-  return (A->stats[8] <= 8 * (mean + 1) + 64) ? HSPMV_ALGO_CSR_STREAM : HSPMV_ALGO_CSR_MERGE;
+  return (A->stats[8] <= 8 * (mean + 1) + 64) ? HSPMV_ALGO_CSR_STREAM : HSPMV_ALGO_CSR_VECTOR;
 }
 
 int build_pipe(hspmv_matrix *A) {
@@ -1266,6 +1269,68 @@ int hspmv_interior_rows(const hspmv_matrix *A, int64_t own_col_lo, int64_t own_c
   cudaFree(d);
   *row_a = res[0];
   *row_b = res[1] < res[0] ? res[0] : res[1];
+  return HSPMV_OK;
+}
+
+// ---- NVLink peer exchange (CUDA IPC) -------------------------------------------------------
+int hspmv_peer_export(void *dptr, void *handle64) {
+  if (!dptr || !handle64) return fail(HSPMV_EINVAL, "null");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle64, dptr));
+  return HSPMV_OK;
+}
+int hspmv_peer_open(const void *handle64, void **dptr) {
+  if (!handle64 || !dptr) return fail(HSPMV_EINVAL, "null");
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle64, sizeof(h));
+  CU(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return HSPMV_OK;
+}
+int hspmv_peer_close(void *dptr) {
+  if (dptr) CU(cudaIpcCloseMemHandle(dptr));
+  return HSPMV_OK;
+}
+int hspmv_peer_alloc(int64_t bytes, void **dptr) {
+  if (!dptr || bytes <= 0) return fail(HSPMV_EINVAL, "bad arguments");
+  CU(cudaMalloc(dptr, (size_t)bytes));
+  CU(cudaMemset(*dptr, 0, (size_t)bytes));
+  return HSPMV_OK;
+}
+int hspmv_peer_free(void *dptr) {
+  if (dptr) CU(cudaFree(dptr));
+  return HSPMV_OK;
+}
+int hspmv_peer_push(int n_segs, void *const *dst, const void *const *src, const int64_t *bytes, int *const *flags,
+                    int step, void *scratch, void *stream) {
+  if (n_segs < 0 || n_segs > 8 || !scratch) return fail(HSPMV_EINVAL, "at most 8 segments per push");
+  hspmv::PushArgs a;
+  std::memset(&a, 0, sizeof(a));
+  int64_t total = 0;
+  for (int i = 0; i < n_segs; ++i) {
+    if (bytes[i] & 3) return fail(HSPMV_EINVAL, "segment size must be a multiple of 4 bytes");
+    a.dst[i] = dst[i];
+    a.src[i] = src[i];
+    a.bytes[i] = bytes[i];
+    a.flag[i] = flags ? flags[i] : nullptr;
+    total += bytes[i];
+  }
+  a.n_segs = n_segs;
+  a.step = step;
+  a.counter = (unsigned int *)scratch;
+  int grid = (int)((total / 8 + 255) / 256);
+  if (grid < 1) grid = 1;
+  if (grid > 32) grid = 32; // a few CTAs saturate one NVLink direction for MB-sized halos
+  hspmv::halo_push_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  LAUNCHED();
+  CU(cudaGetLastError());
+  return HSPMV_OK;
+}
+int hspmv_peer_wait(const int *flags, int n_flags, int step, int *timed_out, void *stream) {
+  if (!flags || n_flags < 0 || n_flags > 32 || !timed_out) return fail(HSPMV_EINVAL, "bad arguments");
+  if (n_flags == 0) return HSPMV_OK;
+  hspmv::flag_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags, n_flags, step, (long long)4e9, timed_out);
+  LAUNCHED();
+  CU(cudaGetLastError());
   return HSPMV_OK;
 }
 

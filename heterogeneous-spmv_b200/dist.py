@@ -46,6 +46,105 @@ def gather_col_ranges(col_range, group=None):
     return [tuple(int(v) for v in t.tolist()) for t in out]
 
 
+def wrap_device_ptr(ptr, count, dtype=torch.float64):
+    """Zero-copy torch view of device memory owned by the library (CUDA array interface)."""
+    typestr = {torch.float64: "<f8", torch.float32: "<f4", torch.int32: "<i4"}[dtype]
+
+    class _Holder:
+        __cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+    return torch.as_tensor(_Holder(), device="cuda")
+
+
+class PeerHalo:
+    """Halo exchange by direct NVLink stores into the neighbours' x buffers (CUDA IPC), no NCCL.
+
+    Per step t, everything stream-ordered:
+      comm stream : wait for last step's acks -> ONE push kernel writes my boundary slices of x into
+                    every neighbour's halo region and then sets their data flag to t
+      main stream : interior rows | spin on my data flags until t | boundary rows | ack t to senders
+    The ack keeps a neighbour from overwriting a halo this rank is still reading when x changes
+    between steps (solver use); spins are bounded and report a timeout instead of hanging.
+    x_ptr must come from cudaMalloc (the matrix handle's own x vector)."""
+
+    def __init__(self, hs, x_ptr, itemsize, row_lo, col_ranges, rank, group=None):
+        self.hs = hs
+        self.rank = rank
+        self.P = P = len(row_lo) - 1
+        self.itemsize = itemsize
+        self.x_ptr = x_ptr
+        self.cmin = int(col_ranges[rank][0])
+        self.recv, self.send = halo_plan(row_lo, col_ranges, rank)
+        # int32 words: [0,P) data flags (slot = sender), [P,2P) ack flags (slot = receiver), 2P scratch, 2P+1 timeout
+        self.flags = hs.peer_alloc(4 * (2 * P + 8))
+        mine = torch.frombuffer(bytearray(hs.peer_export(x_ptr) + hs.peer_export(self.flags)), dtype=torch.uint8).cuda()
+        allh = [torch.zeros(128, dtype=torch.uint8, device="cuda") for _ in range(P)]
+        dist.all_gather(allh, mine, group=group)
+        cmins = [int(c[0]) for c in col_ranges]
+        self.peer_x, self.peer_flags = {}, {}
+        for q in sorted({q for q, _, _ in self.recv} | {q for q, _, _ in self.send}):
+            raw = bytes(allh[q].cpu().numpy().tobytes())
+            self.peer_x[q] = hs.peer_open(raw[:64])
+            self.peer_flags[q] = hs.peer_open(raw[64:])
+        self.peer_cmin = cmins
+        self.step = 0
+        self.comm = torch.cuda.Stream()
+        self.ready = torch.cuda.Event()
+        self.halo_elems = sum(b - a for _, a, b in self.recv)
+        # flags I wait on, compacted: data flags of my senders, ack flags of my receivers
+        self.senders = sorted({q for q, _, _ in self.recv})
+        self.receivers = sorted({q for q, _, _ in self.send})
+        dist.barrier(group=group)
+
+    def _flag(self, base_ptr, word):
+        return base_ptr + 4 * word
+
+    def post(self):
+        """Start step t: push my slices to the neighbours (comm stream), after x is ready."""
+        hs, P, r = self.hs, self.P, self.rank
+        self.step += 1
+        t = self.step
+        main = torch.cuda.current_stream()
+        self.ready.record(main)
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(self.ready)
+            cs = self.comm.cuda_stream
+            if t > 1:
+                for q in self.receivers:   # q has consumed what I sent at t-1
+                    hs.peer_wait(self._flag(self.flags, P + q), 1, t - 1, self._flag(self.flags, 2 * P + 1), cs)
+            segs = []
+            for q, a, b in self.send:      # global columns [a,b) of mine -> q's window
+                dst = self.peer_x[q] + (a - self.peer_cmin[q]) * self.itemsize
+                src = self.x_ptr + (a - self.cmin) * self.itemsize
+                segs.append((dst, src, (b - a) * self.itemsize, self._flag(self.peer_flags[q], r)))
+            for i in range(0, len(segs), 8):
+                hs.peer_push(segs[i:i + 8], t, self._flag(self.flags, 2 * P), cs)
+
+    def wait_data(self):
+        P = self.P
+        ms = torch.cuda.current_stream().cuda_stream
+        for q in self.senders:
+            self.hs.peer_wait(self._flag(self.flags, q), 1, self.step, self._flag(self.flags, 2 * P + 1), ms)
+
+    def ack(self):
+        P, r = self.P, self.rank
+        ms = torch.cuda.current_stream().cuda_stream
+        segs = [(0, 0, 0, self._flag(self.peer_flags[q], P + r)) for q in self.senders]
+        for i in range(0, len(segs), 8):
+            self.hs.peer_push(segs[i:i + 8], self.step, self._flag(self.flags, 2 * P + 2), ms)
+
+    def timed_out(self):
+        flag = wrap_device_ptr(self._flag(self.flags, 2 * self.P + 1), 1, torch.int32)
+        return bool(int(flag.item()))
+
+    def close(self):
+        torch.cuda.synchronize()
+        for p in list(self.peer_x.values()) + list(self.peer_flags.values()):
+            self.hs.peer_close(p)
+        self.hs.peer_free(self.flags)
+        self.peer_x, self.peer_flags = {}, {}
+
+
 class ShardedSpMV:
     """y_block = A_block * x for one rank's row block.
 
@@ -55,7 +154,8 @@ class ShardedSpMV:
               stream (GPU) or runs it (CPU tests).
     """
 
-    def __init__(self, row_lo, col_ranges, rank, x_local, compute, interior, group=None):
+    def __init__(self, row_lo, col_ranges, rank, x_local, compute, interior, group=None, peer=None):
+        self.peer = peer                             # PeerHalo: NVLink stores instead of NCCL send/recv
         self.rank = rank
         self.group = group
         self.lo, self.hi = int(row_lo[rank]), int(row_lo[rank + 1])
@@ -81,6 +181,20 @@ class ShardedSpMV:
 
     def step(self, overlap=True):
         """halo exchange + local SpMV.  With overlap, interior rows run while the halo is in flight."""
+        if self.peer is not None:
+            self.peer.post()
+            if self.row_b > self.row_a:
+                self.compute(self.row_a, self.row_b)
+            self.peer.wait_data()
+            if self.row_b > self.row_a:
+                if self.row_a > 0:
+                    self.compute(0, self.row_a)
+                if self.row_b < self.m:
+                    self.compute(self.row_b, self.m)
+            else:
+                self.compute(0, self.m)
+            self.peer.ack()
+            return
         works = self.post_exchange()
         if overlap and self.row_b > self.row_a:
             self.compute(self.row_a, self.row_b)

@@ -7,7 +7,9 @@ BASELINE.json `configs` names, in host CSR arrays (int32 indices, 0-based, sorte
 
     cfg 1  laplace2d_5pt(1000, rcm=True)      n=1M,   nnz=4,996,000
     cfg 2  stencil27(100)                     n=1M,   nnz=26,463,592 (=298^3)
-    cfg 3  banded_shell(1_500_000)            n=1.5M, ~35 nnz/row, RCM-banded
+    cfg 3  shell_blocks(1_500_000)            n=1.5M, 35 nnz/row in 5x5 node blocks, RCM-banded
+           (banded_shell(1_500_000): the SURVEY's "3-wide runs" recipe -- every row an independent
+            random column set, no row-to-row similarity; kept as the hostile variant)
     cfg 4  rmat(24, 16)                       n=16M,  nnz~256M, power law, not symmetric
     cfg 5  stencil27(400)                     n=64M,  nnz=1,719,374,392 (=1198^3)
 
@@ -121,6 +123,47 @@ def laplace2d_5pt(g, dtype=np.float64, mode="classic", rcm=False):
         val = np.where(rows == cols, 4.0, -1.0)
     else:
         val = value_of(rows, cols, mode)
+    return rp.astype(np.int32), cols.astype(np.int32), val.astype(dtype)
+
+
+def shell_blocks(n, dtype=np.float64, dofs=5, node_nbrs=6, node_band=600, seed=12345, rcm=True):
+    """cfg 3 (af_shell / Queen analog): a finite-element shell look.  n/dofs nodes, every node
+    coupled to itself and ~node_nbrs neighbour nodes inside a band of the node graph (symmetric),
+    every node-node coupling a dense dofs x dofs block -> (node_nbrs+1)*dofs = 35 entries per row
+    for the defaults, and the rows of one node share one column set, as in af_shell*.
+    RCM is applied to the NODE graph (what a mesh-based reordering does), then expanded."""
+    nodes = n // dofs
+    assert nodes * dofs == n, "n must be a multiple of dofs"
+    rng = np.random.default_rng(seed)
+    half = max(1, node_nbrs // 2)
+    base = np.repeat(np.arange(nodes, dtype=np.int64), half)
+    nb = base + rng.integers(1, node_band, size=base.size, dtype=np.int64)
+    ok = nb < nodes
+    base, nb = base[ok], nb[ok]
+    r = np.concatenate([base, nb, np.arange(nodes, dtype=np.int64)])
+    c = np.concatenate([nb, base, np.arange(nodes, dtype=np.int64)])
+    Gn = sp.csr_matrix((np.ones(len(r), dtype=np.int8), (r, c)), shape=(nodes, nodes))
+    Gn.sum_duplicates()
+    Gn.data[:] = 1
+    if rcm:
+        p = reverse_cuthill_mckee(Gn, symmetric_mode=True)
+        Gn = Gn[p][:, p].tocsr()
+    Gn.sort_indices()
+    nrp = Gn.indptr.astype(np.int64)
+    ncol = Gn.indices.astype(np.int64)
+    ndeg = np.diff(nrp)
+    # expand: row (node i, dof a) -> columns (node j, dof b) for every neighbour j, b = 0..dofs-1
+    row_len = np.repeat(ndeg * dofs, dofs)
+    rp = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(row_len, out=rp[1:])
+    node_of_row = np.repeat(np.arange(nodes, dtype=np.int64), dofs)
+    # for each row, its node's neighbour list repeated per dof block
+    starts = nrp[node_of_row]
+    idx_in_row = np.arange(rp[-1], dtype=np.int64) - np.repeat(rp[:-1], row_len)
+    nbr = ncol[np.repeat(starts, row_len) + idx_in_row // dofs]
+    cols = nbr * dofs + idx_in_row % dofs
+    rows = np.repeat(np.arange(n, dtype=np.int64), row_len)
+    val = value_of(rows, cols, "varied")
     return rp.astype(np.int32), cols.astype(np.int32), val.astype(dtype)
 
 

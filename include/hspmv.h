@@ -237,6 +237,24 @@ int hspmv_col_range_device(const hspmv_matrix *A, int64_t *col_min, int64_t *col
 int hspmv_interior_rows(const hspmv_matrix *A, int64_t own_col_lo, int64_t own_col_hi,
                         int64_t *row_a, int64_t *row_b);
 
+/* ---- NVLink halo exchange over peer memory (one process per GPU) --------------------------
+ * The reference has no multi-GPU code; this replaces what would otherwise be NCCL send/recv.
+ * A buffer that came from cudaMalloc (hspmv_x_device(), hspmv_peer_alloc()) is exported as a
+ * 64-byte CUDA-IPC handle, opened by the neighbour, and written directly:
+ *   hspmv_peer_push  one kernel copies up to 8 segments into peers' memory (NVLink stores),
+ *                    fences at system scope and then publishes `step` in each peer's flag word;
+ *   hspmv_peer_wait  enqueues a (bounded) spin on local flag words until they reach `step`;
+ *                    *timed_out (device int) is set if a peer never arrives.
+ * Everything is stream-ordered; there is no host synchronisation inside a step. */
+int hspmv_peer_export(void *dptr, void *handle64);
+int hspmv_peer_open(const void *handle64, void **dptr);
+int hspmv_peer_close(void *dptr);
+int hspmv_peer_alloc(int64_t bytes, void **dptr);
+int hspmv_peer_free(void *dptr);
+int hspmv_peer_push(int n_segs, void *const *dst, const void *const *src, const int64_t *bytes,
+                    int *const *flags, int step, void *scratch, void *stream);
+int hspmv_peer_wait(const int *flags, int n_flags, int step, int *timed_out, void *stream);
+
 /* ---- kernel-side index tables, exposed for the bit-exactness tests ------------------ */
 /* CSR_MERGE tile table: tile_row[t] = last row r with row_ptr[r] <= t*tile, t = 0..n_tiles
  * (n_tiles = ceil(nnz/tile)); tile_row[n_tiles] = m.  Host rule and the device copy. */

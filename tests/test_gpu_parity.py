@@ -360,3 +360,36 @@ def test_pipelined_host_call_equals_sequential(hs, gen):
             sc = O.abs_rowsum(rp, ci, v, x.numpy())
             assert_within_bound(y1.numpy()[lo:lo + 100], ref, sc, np.float64, "pipelined rows")
         A.close()
+
+
+@pytest.mark.parametrize("dtype", DT, ids=DT_IDS)
+def test_tolerance_is_exercised_by_rough_values(dtype, hs, oracle, gen):
+    """The generator values are dyadic, so sums are exact and every kernel matches the oracle bit
+    for bit.  With arbitrary values and x the kernels' FMA / lane-tree summation order differs from
+    the oracle's serial one: the difference must be non-zero somewhere and inside the bound."""
+    rng = np.random.default_rng(42)
+    rp, ci, _ = gen.shell_blocks(50000, dofs=5)
+    n = len(rp) - 1
+    v = rng.standard_normal(len(ci)).astype(dtype)
+    x = rng.standard_normal(n).astype(dtype)
+    y_ref = oracle.csr_spmv(rp, ci, v, x)
+    scale = oracle.abs_rowsum(rp, ci, v, x)
+    A = hs.Matrix.from_csr(rp, ci, v)
+    A.set_x(x)
+    differs = 0
+    for algo in (hs.ALGO_CSR_STREAM, hs.ALGO_CSR_VECTOR, hs.ALGO_CSR_MERGE):
+        A.spmv(algo)
+        y = A.get_y()
+        assert_within_bound(y, y_ref, scale, dtype, hs.ALGO_NAMES[algo])
+        differs += int(np.count_nonzero(y != y_ref))
+    A.build_csrk(3, hs.auto_params(len(ci), n, hs.ARCH_B200)[0])
+    A.set_x(x)
+    A.spmv(hs.ALGO_CSRK)
+    y = A.get_y(True)
+    assert_within_bound(y, y_ref, scale, dtype, "csrk")
+    differs += int(np.count_nonzero(y != y_ref))
+    assert differs > 0, "suspicious: rough inputs reproduced the serial sum bit for bit everywhere"
+    # and an fp32 accumulation of fp64 data would NOT pass: the bound is tight enough to tell
+    if dtype == np.float64:
+        y32 = oracle.csr_spmv(rp, ci, v.astype(np.float32), x.astype(np.float32)).astype(np.float64)
+        assert np.count_nonzero(np.abs(y32 - y_ref) > 1e-12 * scale) > n // 2
