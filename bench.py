@@ -264,10 +264,14 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         ranges = hd.gather_col_ranges((cmin, cmax))
         interior = A.interior_rows(lo - cmin, hi - cmin)
-        peer = None
-        if args.exchange == "peer":
+        peer = fused = None
+        if args.exchange in ("peer", "peer-unfused"):
             peer = hd.PeerHalo(hs, A.x_ptr(), 8, row_lo, ranges, rank)
-        sh = hd.ShardedSpMV(row_lo, ranges, rank, x_local, compute, interior, peer=peer)
+            if args.exchange == "peer":
+                def fused(a, b, flags, n, step, timeout):
+                    A.spmv_halo(a, b, d_x=x_local.data_ptr(), d_y=y_local.data_ptr(), wait_flags=flags, n_wait=n,
+                                wait_step=step, timed_out=timeout, stream=stream)
+        sh = hd.ShardedSpMV(row_lo, ranges, rank, x_local, compute, interior, peer=peer, fused=fused)
         if args.no_exchange:   # diagnosis only: local kernels without the halo traffic (x is static)
             step = lambda: compute(0, m_loc)                  # noqa: E731
         else:
@@ -397,8 +401,10 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=CPU_SAMPLE_ROWS)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-overlap", action="store_true")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
-                    help="halo exchange: peer = NVLink stores into IPC-mapped neighbour buffers (default), nccl = send/recv")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "peer-unfused", "nccl"],
+                    help="halo exchange: peer = copy-engine NVLink copies into IPC-mapped neighbour buffers + one fused "
+                         "kernel per step that waits on the halo flags itself (default); peer-unfused = same transport, "
+                         "separate interior/boundary launches; nccl = batch_isend_irecv")
     ap.add_argument("--no-exchange", action="store_true", help="diagnosis: skip the halo exchange (invalid as a result)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

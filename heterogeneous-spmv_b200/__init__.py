@@ -280,6 +280,18 @@ def peer_wait(flags_ptr, n_flags, step, timed_out_ptr, stream):
     _check(lib().hspmv_peer_wait(C.c_void_p(flags_ptr), int(n_flags), int(step), C.c_void_p(timed_out_ptr), C.c_void_p(stream)))
 
 
+def memcpy_async(dst, src, nbytes, stream):
+    _check(lib().hspmv_memcpy_async(C.c_void_p(dst), C.c_void_p(src), C.c_int64(nbytes), C.c_void_p(stream)))
+
+
+def stream_write(stream, addr, value):
+    _check(lib().hspmv_stream_write(C.c_void_p(stream), C.c_void_p(addr), int(value)))
+
+
+def stream_wait_ge(stream, addr, value):
+    _check(lib().hspmv_stream_wait_ge(C.c_void_p(stream), C.c_void_p(addr), int(value)))
+
+
 # ------------------------------------------------------------------------------ device matrices
 class Matrix:
     """A device-resident matrix handle (hspmv_matrix*)."""
@@ -408,6 +420,12 @@ class Matrix:
     def spmv_range(self, row_lo, row_hi, algo=ALGO_AUTO, d_x=None, d_y=None, stream=None):
         _check(lib().hspmv_spmv_range(self.h, int(algo), C.c_int64(row_lo), C.c_int64(row_hi), C.c_void_p(d_x),
                                       C.c_void_p(d_y), C.c_void_p(stream)))
+
+    def spmv_halo(self, interior_lo, interior_hi, d_x=None, d_y=None, wait_flags=None, n_wait=0, wait_step=0,
+                  timed_out=None, stream=None):
+        _check(lib().hspmv_spmv_halo(self.h, C.c_int64(interior_lo), C.c_int64(interior_hi), C.c_void_p(d_x),
+                                     C.c_void_p(d_y), C.c_void_p(wait_flags), int(n_wait), int(wait_step),
+                                     C.c_void_p(timed_out), C.c_void_p(stream)))
 
     def spmv_host_timed(self, x_ptr, y_ptr, iters, algo=ALGO_AUTO):
         """iters x (H2D x, kernel, D2H y) on raw host addresses; returns total device-event ms."""

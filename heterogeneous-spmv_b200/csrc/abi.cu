@@ -342,8 +342,17 @@ int launch_csrk(hspmv_matrix *A, const hspmv::CsrkParams<T> &p, int grid, int wa
 }
 
 // CSRK (k = 2,3 after hspmv_build_csrk / hspmv_create_csrk) and CSR_STREAM (k = 1, fixed-row tiles)
+struct HaloWait { // hspmv_spmv_halo: three row ranges + flags the boundary tiles wait for
+  int n_ranges = 0;
+  int64_t lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+  const int *flags = nullptr;
+  int n_wait = 0, step = 0;
+  int *timed_out = nullptr;
+};
+
 template <typename T>
-int run_csrk(hspmv_matrix *A, bool stream_mode, const T *x, T *y, cudaStream_t st, int64_t row_lo = 0, int64_t row_hi = -1) {
+int run_csrk(hspmv_matrix *A, bool stream_mode, const T *x, T *y, cudaStream_t st, int64_t row_lo = 0, int64_t row_hi = -1,
+             const HaloWait *halo = nullptr) {
   if (!stream_mode && A->k < 2) return fail(HSPMV_ESTATE, "HSPMV_ALGO_CSRK needs hspmv_build_csrk or hspmv_create_csrk first");
   int rc0 = ensure_stats(A);
   if (rc0) return rc0;
@@ -373,8 +382,30 @@ int run_csrk(hspmv_matrix *A, bool stream_mode, const T *x, T *y, cudaStream_t s
 
   if (row_hi < 0) row_hi = A->m;
   hspmv::CsrkParams<T> p;
-  p.m = stream_mode ? row_hi : A->m;
-  p.row_begin = stream_mode ? row_lo : 0;
+  p.m = A->m;
+  p.n_ranges = 1;
+  p.range_lo[0] = stream_mode ? row_lo : 0;
+  p.range_hi[0] = stream_mode ? row_hi : A->m;
+  p.range_lo[1] = p.range_hi[1] = p.range_lo[2] = p.range_hi[2] = 0;
+  p.own_row_lo = 0;
+  p.own_row_hi = A->m;
+  p.wait_flags = nullptr;
+  p.n_wait = 0;
+  p.wait_step = 0;
+  p.timed_out = nullptr;
+  if (stream_mode && halo) {
+    p.n_ranges = halo->n_ranges;
+    for (int i = 0; i < halo->n_ranges; ++i) {
+      p.range_lo[i] = halo->lo[i];
+      p.range_hi[i] = halo->hi[i];
+    }
+    p.own_row_lo = halo->lo[0]; // range 0 is the interior
+    p.own_row_hi = halo->hi[0];
+    p.wait_flags = halo->flags;
+    p.n_wait = halo->n_wait;
+    p.wait_step = halo->step;
+    p.timed_out = halo->timed_out;
+  }
   p.rp = A->d_rp;
   p.ci = A->d_ci;
   p.val = (const T *)A->d_val;
@@ -398,7 +429,12 @@ int run_csrk(hspmv_matrix *A, bool stream_mode, const T *x, T *y, cudaStream_t s
     }
     p.k = 1;
     p.rows_per_tile = rpt;
-    p.n_sr = (row_hi - row_lo + rpt - 1) / rpt;
+    p.tiles_before[0] = 0;
+    for (int i = 0; i < 3; ++i) {
+      const int64_t len = i < p.n_ranges ? p.range_hi[i] - p.range_lo[i] : 0;
+      p.tiles_before[i + 1] = p.tiles_before[i] + (len + rpt - 1) / rpt;
+    }
+    p.n_sr = p.tiles_before[3];
     typical_rows = rpt;
     typical_nnz = (int64_t)(rpt * mean + 0.999);
     worst_nnz = (int64_t)rpt * max_len; // a tile can never hold more than this
@@ -1015,6 +1051,73 @@ int hspmv_spmv_range(hspmv_matrix *A, int algo, int64_t row_lo, int64_t row_hi, 
                      void *stream) {
   if (!A) return fail(HSPMV_EINVAL, "null handle");
   return do_spmv(A, algo, d_x, d_y, (cudaStream_t)stream, row_lo, row_hi);
+}
+
+int hspmv_spmv_halo(hspmv_matrix *A, int64_t interior_lo, int64_t interior_hi, const void *d_x, void *d_y,
+                    const int *wait_flags, int n_wait, int wait_step, int *timed_out, void *stream) {
+  if (!A) return fail(HSPMV_EINVAL, "null handle");
+  if (A->k != 1) return fail(HSPMV_EUNSUPPORTED, "hspmv_spmv_halo works on plain-CSR shards");
+  if (interior_lo < 0 || interior_lo > interior_hi || interior_hi > A->m || n_wait < 0 || n_wait > 32 ||
+      (n_wait && (!wait_flags || !timed_out)))
+    return fail(HSPMV_EINVAL, "bad arguments");
+  HaloWait h;
+  // interior first, then the rows that need the halo; empty ranges are skipped by the tiling
+  h.n_ranges = 3;
+  h.lo[0] = interior_lo; h.hi[0] = interior_hi;
+  h.lo[1] = 0;           h.hi[1] = interior_lo;
+  h.lo[2] = interior_hi; h.hi[2] = A->m;
+  h.flags = wait_flags;
+  h.n_wait = n_wait;
+  h.step = wait_step;
+  h.timed_out = timed_out;
+  A->last_stream = (cudaStream_t)stream;
+  A->last_stream_valid = true;
+  int rc = ensure_stats(A);
+  if (rc) return rc;
+  if (A->dtype == HSPMV_F64)
+    rc = run_csrk<double>(A, true, (const double *)(d_x ? d_x : A->d_x), (double *)(d_y ? d_y : A->d_y), (cudaStream_t)stream, 0, A->m, &h);
+  else
+    rc = run_csrk<float>(A, true, (const float *)(d_x ? d_x : A->d_x), (float *)(d_y ? d_y : A->d_y), (cudaStream_t)stream, 0, A->m, &h);
+  if (rc) return rc;
+  CU(cudaGetLastError());
+  return HSPMV_OK;
+}
+
+// ---- stream-ordered flag operations executed by the front end (no SM): the halo protocol ----
+namespace {
+typedef int (*StreamValueFn)(void *stream, unsigned long long addr, unsigned int value, unsigned int flags);
+StreamValueFn g_wait_value = nullptr, g_write_value = nullptr;
+int load_stream_memops() {
+  if (g_wait_value && g_write_value) return HSPMV_OK;
+  void *w = nullptr, *r = nullptr;
+  cudaDriverEntryPointQueryResult q1, q2;
+  CU(cudaGetDriverEntryPoint("cuStreamWaitValue32", &w, cudaEnableDefault, &q1));
+  CU(cudaGetDriverEntryPoint("cuStreamWriteValue32", &r, cudaEnableDefault, &q2));
+  if (!w || !r || q1 != cudaDriverEntryPointSuccess || q2 != cudaDriverEntryPointSuccess)
+    return fail(HSPMV_EUNSUPPORTED, "driver has no stream memory operations");
+  g_wait_value = (StreamValueFn)w;
+  g_write_value = (StreamValueFn)r;
+  return HSPMV_OK;
+}
+} // namespace
+
+int hspmv_stream_wait_ge(void *stream, const int *addr, int value) {
+  int rc = load_stream_memops();
+  if (rc) return rc;
+  const int e = g_wait_value(stream, (unsigned long long)(uintptr_t)addr, (unsigned int)value, 0x1 /* CU_STREAM_WAIT_VALUE_GEQ */);
+  if (e) return fail(HSPMV_ECUDA, "cuStreamWaitValue32 failed with CUresult " + std::to_string(e));
+  return HSPMV_OK;
+}
+int hspmv_stream_write(void *stream, int *addr, int value) {
+  int rc = load_stream_memops();
+  if (rc) return rc;
+  const int e = g_write_value(stream, (unsigned long long)(uintptr_t)addr, (unsigned int)value, 0);
+  if (e) return fail(HSPMV_ECUDA, "cuStreamWriteValue32 failed with CUresult " + std::to_string(e));
+  return HSPMV_OK;
+}
+int hspmv_memcpy_async(void *dst, const void *src, int64_t bytes, void *stream) {
+  CU(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+  return HSPMV_OK;
 }
 
 int hspmv_spmv_host_timed(hspmv_matrix *A, int algo, const void *x_host, void *y_host, int iters,

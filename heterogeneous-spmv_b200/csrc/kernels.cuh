@@ -214,8 +214,19 @@ __global__ void zero_rows_kernel(int64_t n_rows, const int *__restrict__ row_lis
 // ------------------------------------------------------------------------------------------
 template <typename T> struct CsrkParams {
   int k;              // 1: implicit tiles of rows_per_tile rows, 2: sr_ptr, 3: ssr_ptr + sr_ptr
-  int64_t m;          // rows (k == 1: end of the row range being processed)
-  int64_t row_begin;  // k == 1: first row of tile 0 (hspmv_spmv_range); 0 for the whole matrix
+  int64_t m;          // rows
+  // k == 1: up to three row ranges, tiled one after the other (hspmv_spmv_range passes one,
+  // hspmv_spmv_halo passes interior | low boundary | high boundary); tiles_before[i] = number
+  // of tiles in ranges < i, tiles_before[n_ranges] = n_sr
+  int n_ranges;
+  int64_t range_lo[3], range_hi[3], tiles_before[4];
+  // fused halo wait (hspmv_spmv_halo): rows outside [own_row_lo, own_row_hi) read x entries that a
+  // neighbour GPU writes over NVLink; before a warp consumes its first such tile it spins
+  // (bounded) until every wait_flags[i] >= wait_step.  n_wait == 0: no waiting.
+  int64_t own_row_lo, own_row_hi;
+  const int *wait_flags;
+  int n_wait, wait_step;
+  int *timed_out;
   int64_t n_sr;       // super-rows (k == 1: number of tiles)
   int64_t n_ssr;      // super-super-rows (k == 3)
   const uint32_t *ssr_ptr; // [n_ssr+1]
@@ -398,8 +409,10 @@ __global__ void __launch_bounds__(512, 1) csrk_tma_kernel(const CsrkParams<T> p)
   auto load_meta = [&](int64_t sr) -> SrMeta {
     SrMeta mt;
     if (p.k == 1) {
-      const int64_t r0 = p.row_begin + sr * p.rows_per_tile;
-      const int64_t r1 = (r0 + p.rows_per_tile < p.m) ? r0 + p.rows_per_tile : p.m;
+      int g = 0;
+      if (p.n_ranges > 1 && sr >= p.tiles_before[1]) g = (p.n_ranges > 2 && sr >= p.tiles_before[2]) ? 2 : 1;
+      const int64_t r0 = p.range_lo[g] + (sr - p.tiles_before[g]) * p.rows_per_tile;
+      const int64_t r1 = (r0 + p.rows_per_tile < p.range_hi[g]) ? r0 + p.rows_per_tile : p.range_hi[g];
       mt.r0 = (int)r0;
       mt.r1 = (int)r1;
       mt.e0 = __ldg(p.rp + r0);
@@ -460,12 +473,32 @@ __global__ void __launch_bounds__(512, 1) csrk_tma_kernel(const CsrkParams<T> p)
   // ---- main loop
   int st = 0;
   uint32_t parity = 0;
+  bool halo_ready = (p.n_wait == 0);
   for (int live = filled; live > 0;) {
     const uint32_t bar = smem_u32(bars + st);
     mbar_wait(bar, parity);
     unsigned char *base = ring + (size_t)st * stage_bytes;
     const int *meta = reinterpret_cast<const int *>(base);
     const int r0 = meta[0], r1 = meta[1], e0 = meta[2], e1m = meta[3];
+    if (!halo_ready && (r0 < p.own_row_lo || r0 >= p.own_row_hi)) {
+      // first boundary tile of this warp: the halo part of x must have arrived.  The matrix
+      // data of this tile is already staged (it is local); only the gathers below need the halo.
+      if (lane < p.n_wait) {
+        const long long t0 = clock64();
+        for (;;) {
+          int v;
+          asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p.wait_flags + lane) : "memory");
+          if (v >= p.wait_step) break;
+          if (clock64() - t0 > 4000000000LL) {
+            atomicExch(p.timed_out, 1);
+            break;
+          }
+          __nanosleep(100);
+        }
+      }
+      __syncwarp();
+      halo_ready = true;
+    }
     if (e1m >= 0) {
       const int *rp_w = reinterpret_cast<const int *>(base + 16);
       const int *ci_w = rp_w + (p.cap_rows + 8);

@@ -57,15 +57,22 @@ def wrap_device_ptr(ptr, count, dtype=torch.float64):
 
 
 class PeerHalo:
-    """Halo exchange by direct NVLink stores into the neighbours' x buffers (CUDA IPC), no NCCL.
+    """Halo exchange straight into the neighbours' x buffers over NVLink (CUDA IPC), no NCCL and
+    no SM: the local SpMV kernel is persistent and owns every SM, so everything that must run
+    NEXT to it is a copy-engine or command-processor operation.
 
-    Per step t, everything stream-ordered:
-      comm stream : wait for last step's acks -> ONE push kernel writes my boundary slices of x into
-                    every neighbour's halo region and then sets their data flag to t
-      main stream : interior rows | spin on my data flags until t | boundary rows | ack t to senders
+    Per step t, all stream-ordered, no host synchronisation:
+      comm stream : wait (cuStreamWaitValue32) until every receiver has acked step t-1
+                    -> peer copies of my boundary slices of x into the neighbours' halo regions
+                    -> write t into each neighbour's data flag (cuStreamWriteValue32)
+      main stream : ONE kernel (hspmv_spmv_halo): interior tiles, then each warp spins (bounded) on
+                    my data flags until they reach t, then the boundary tiles
+                    -> write t into each sender's ack flag
     The ack keeps a neighbour from overwriting a halo this rank is still reading when x changes
-    between steps (solver use); spins are bounded and report a timeout instead of hanging.
-    x_ptr must come from cudaMalloc (the matrix handle's own x vector)."""
+    between steps.  x_ptr must come from cudaMalloc (the matrix handle's own x vector).
+    Flag words (int32) per rank: [0,P) data flags by sender, [P,2P) ack flags by receiver,
+    [2P] spare, [2P+1] timeout indicator; the data flags this rank waits on are also mirrored
+    compactly at [2P+8, 2P+8+n_senders) so that the kernel can poll one word per lane."""
 
     def __init__(self, hs, x_ptr, itemsize, row_lo, col_ranges, rank, group=None):
         self.hs = hs
@@ -75,66 +82,73 @@ class PeerHalo:
         self.x_ptr = x_ptr
         self.cmin = int(col_ranges[rank][0])
         self.recv, self.send = halo_plan(row_lo, col_ranges, rank)
-        # int32 words: [0,P) data flags (slot = sender), [P,2P) ack flags (slot = receiver), 2P scratch, 2P+1 timeout
-        self.flags = hs.peer_alloc(4 * (2 * P + 8))
+        self.senders = sorted({q for q, _, _ in self.recv})
+        self.receivers = sorted({q for q, _, _ in self.send})
+        self.flags = hs.peer_alloc(4 * (3 * P + 16))
         mine = torch.frombuffer(bytearray(hs.peer_export(x_ptr) + hs.peer_export(self.flags)), dtype=torch.uint8).cuda()
         allh = [torch.zeros(128, dtype=torch.uint8, device="cuda") for _ in range(P)]
         dist.all_gather(allh, mine, group=group)
-        cmins = [int(c[0]) for c in col_ranges]
-        self.peer_x, self.peer_flags = {}, {}
-        for q in sorted({q for q, _, _ in self.recv} | {q for q, _, _ in self.send}):
+        # which compact slot do I occupy in each receiver's wait list?  (its sorted sender list)
+        senders_t = torch.zeros(P, dtype=torch.int64, device="cuda")
+        for q in self.senders:
+            senders_t[q] = 1
+        all_senders = [torch.zeros(P, dtype=torch.int64, device="cuda") for _ in range(P)]
+        dist.all_gather(all_senders, senders_t, group=group)
+        self.peer_x, self.peer_flags, self.my_slot_at = {}, {}, {}
+        for q in sorted(set(self.senders) | set(self.receivers)):
             raw = bytes(allh[q].cpu().numpy().tobytes())
             self.peer_x[q] = hs.peer_open(raw[:64])
             self.peer_flags[q] = hs.peer_open(raw[64:])
-        self.peer_cmin = cmins
+        for q in self.receivers:
+            their_senders = [i for i in range(P) if int(all_senders[q][i])]
+            self.my_slot_at[q] = their_senders.index(rank)
+        self.peer_cmin = [int(c[0]) for c in col_ranges]
         self.step = 0
         self.comm = torch.cuda.Stream()
         self.ready = torch.cuda.Event()
         self.halo_elems = sum(b - a for _, a, b in self.recv)
-        # flags I wait on, compacted: data flags of my senders, ack flags of my receivers
-        self.senders = sorted({q for q, _, _ in self.recv})
-        self.receivers = sorted({q for q, _, _ in self.send})
         dist.barrier(group=group)
 
-    def _flag(self, base_ptr, word):
+    def _w(self, base_ptr, word):
         return base_ptr + 4 * word
 
+    def wait_words(self):
+        """(device pointer, count) of the compact data-flag words the fused kernel polls."""
+        return self._w(self.flags, 2 * self.P + 8), len(self.senders)
+
+    def timeout_word(self):
+        return self._w(self.flags, 2 * self.P + 1)
+
     def post(self):
-        """Start step t: push my slices to the neighbours (comm stream), after x is ready."""
+        """Start step t on the comm stream: my slices go to the neighbours, then their flags."""
         hs, P, r = self.hs, self.P, self.rank
         self.step += 1
         t = self.step
-        main = torch.cuda.current_stream()
-        self.ready.record(main)
-        with torch.cuda.stream(self.comm):
-            self.comm.wait_event(self.ready)
-            cs = self.comm.cuda_stream
-            if t > 1:
-                for q in self.receivers:   # q has consumed what I sent at t-1
-                    hs.peer_wait(self._flag(self.flags, P + q), 1, t - 1, self._flag(self.flags, 2 * P + 1), cs)
-            segs = []
-            for q, a, b in self.send:      # global columns [a,b) of mine -> q's window
-                dst = self.peer_x[q] + (a - self.peer_cmin[q]) * self.itemsize
-                src = self.x_ptr + (a - self.cmin) * self.itemsize
-                segs.append((dst, src, (b - a) * self.itemsize, self._flag(self.peer_flags[q], r)))
-            for i in range(0, len(segs), 8):
-                hs.peer_push(segs[i:i + 8], t, self._flag(self.flags, 2 * P), cs)
+        self.ready.record(torch.cuda.current_stream())
+        self.comm.wait_event(self.ready)
+        cs = self.comm.cuda_stream
+        if t > 1:
+            for q in self.receivers:   # q has consumed what I sent at t-1
+                hs.stream_wait_ge(cs, self._w(self.flags, P + q), t - 1)
+        for q, a, b in self.send:      # global columns [a,b) of mine -> q's window
+            hs.memcpy_async(self.peer_x[q] + (a - self.peer_cmin[q]) * self.itemsize,
+                            self.x_ptr + (a - self.cmin) * self.itemsize, (b - a) * self.itemsize, cs)
+        for q in self.receivers:
+            hs.stream_write(cs, self._w(self.peer_flags[q], 2 * P + 8 + self.my_slot_at[q]), t)
 
     def wait_data(self):
-        P = self.P
+        """Unfused variant: make the main stream wait for this step's halo (front-end wait)."""
         ms = torch.cuda.current_stream().cuda_stream
-        for q in self.senders:
-            self.hs.peer_wait(self._flag(self.flags, q), 1, self.step, self._flag(self.flags, 2 * P + 1), ms)
+        for i in range(len(self.senders)):
+            self.hs.stream_wait_ge(ms, self._w(self.flags, 2 * self.P + 8 + i), self.step)
 
     def ack(self):
-        P, r = self.P, self.rank
         ms = torch.cuda.current_stream().cuda_stream
-        segs = [(0, 0, 0, self._flag(self.peer_flags[q], P + r)) for q in self.senders]
-        for i in range(0, len(segs), 8):
-            self.hs.peer_push(segs[i:i + 8], self.step, self._flag(self.flags, 2 * P + 2), ms)
+        for q in self.senders:
+            self.hs.stream_write(ms, self._w(self.peer_flags[q], self.P + self.rank), self.step)
 
     def timed_out(self):
-        flag = wrap_device_ptr(self._flag(self.flags, 2 * self.P + 1), 1, torch.int32)
+        flag = wrap_device_ptr(self.timeout_word(), 1, torch.int32)
         return bool(int(flag.item()))
 
     def close(self):
@@ -154,8 +168,9 @@ class ShardedSpMV:
               stream (GPU) or runs it (CPU tests).
     """
 
-    def __init__(self, row_lo, col_ranges, rank, x_local, compute, interior, group=None, peer=None):
-        self.peer = peer                             # PeerHalo: NVLink stores instead of NCCL send/recv
+    def __init__(self, row_lo, col_ranges, rank, x_local, compute, interior, group=None, peer=None, fused=None):
+        self.peer = peer     # PeerHalo: NVLink peer copies + flags instead of NCCL send/recv
+        self.fused = fused   # fused(interior_lo, interior_hi, flags_ptr, n_flags, step, timeout_ptr): one launch per step
         self.rank = rank
         self.group = group
         self.lo, self.hi = int(row_lo[rank]), int(row_lo[rank + 1])
@@ -181,6 +196,12 @@ class ShardedSpMV:
 
     def step(self, overlap=True):
         """halo exchange + local SpMV.  With overlap, interior rows run while the halo is in flight."""
+        if self.peer is not None and self.fused is not None:
+            self.peer.post()
+            flags, n = self.peer.wait_words()
+            self.fused(self.row_a, self.row_b, flags, n, self.peer.step, self.peer.timeout_word())
+            self.peer.ack()
+            return
         if self.peer is not None:
             self.peer.post()
             if self.row_b > self.row_a:

@@ -251,6 +251,18 @@ int hspmv_peer_open(const void *handle64, void **dptr);
 int hspmv_peer_close(void *dptr);
 int hspmv_peer_alloc(int64_t bytes, void **dptr);
 int hspmv_peer_free(void *dptr);
+/* Front-end (copy-engine / command-processor) versions that use no SM, so they run next to a
+ * persistent kernel that occupies every SM: a peer copy, a 32-bit flag write and a >= wait, all
+ * stream-ordered (cuStreamWriteValue32 / cuStreamWaitValue32 resolved at run time). */
+int hspmv_memcpy_async(void *dst, const void *src, int64_t bytes, void *stream);
+int hspmv_stream_write(void *stream, int *addr, int value);
+int hspmv_stream_wait_ge(void *stream, const int *addr, int value);
+/* One launch for a whole shard: tiles of the interior rows [interior_lo, interior_hi) first, then
+ * the rows below and above, which reference the x halo; a warp reaching its first halo tile spins
+ * (bounded; *timed_out is set on failure) until every wait_flags[i] >= wait_step.  With
+ * n_wait == 0 it is hspmv_spmv over the three ranges in that order. */
+int hspmv_spmv_halo(hspmv_matrix *A, int64_t interior_lo, int64_t interior_hi, const void *d_x, void *d_y,
+                    const int *wait_flags, int n_wait, int wait_step, int *timed_out, void *stream);
 int hspmv_peer_push(int n_segs, void *const *dst, const void *const *src, const int64_t *bytes,
                     int *const *flags, int step, void *scratch, void *stream);
 int hspmv_peer_wait(const int *flags, int n_flags, int step, int *timed_out, void *stream);

@@ -393,3 +393,33 @@ def test_tolerance_is_exercised_by_rough_values(dtype, hs, oracle, gen):
     if dtype == np.float64:
         y32 = oracle.csr_spmv(rp, ci, v.astype(np.float32), x.astype(np.float32)).astype(np.float64)
         assert np.count_nonzero(np.abs(y32 - y_ref) > 1e-12 * scale) > n // 2
+
+
+def test_fused_halo_launch_single_gpu(hs, oracle, gen):
+    """hspmv_spmv_halo: interior | low | high ranges in one launch, with the in-kernel flag wait
+    satisfied by a front-end flag write on the same stream (what a neighbour GPU would do)."""
+    import torch
+    g = 18
+    rp, ci, v = gen.stencil27(g, mode="varied")
+    n = len(rp) - 1
+    x = gen.vector_x(n)
+    y_ref = oracle.csr_spmv(rp, ci, v, x)
+    scale = oracle.abs_rowsum(rp, ci, v, x)
+    A = hs.Matrix.from_csr(rp, ci, v)
+    A.set_x(x)
+    flags = hs.peer_alloc(64)
+    st = torch.cuda.current_stream().cuda_stream
+    for a, b in ((g * g + g + 1, n - g * g - g - 1), (0, n), (0, 0), (n, n), (100, 101)):
+        for n_wait, step in ((0, 0), (2, 7)):
+            A.set_y(np.full(n, np.nan))
+            if n_wait:
+                hs.stream_write(st, flags, step)            # two "neighbours" arrive
+                hs.stream_write(st, flags + 4, step + 1)
+            A.spmv_halo(a, b, wait_flags=flags if n_wait else None, n_wait=n_wait, wait_step=step,
+                        timed_out=(flags + 32) if n_wait else None, stream=st)
+            assert_within_bound(A.get_y(), y_ref, scale, np.float64, "halo launch [%d,%d) wait=%d" % (a, b, n_wait))
+    from heterogeneous_spmv_b200 import dist as hd
+    assert int(hd.wrap_device_ptr(flags + 32, 1, torch.int32).item()) == 0      # no timeout recorded
+    hs.stream_wait_ge(st, flags, 7)                                               # already satisfied: returns
+    torch.cuda.synchronize()
+    hs.peer_free(flags)
