@@ -19,7 +19,8 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libhspmv.so")
+# HSPMV_LIB: load another build of the SAME library (A/B timing of two kernel versions)
+LIB_PATH = os.environ.get("HSPMV_LIB") or os.path.join(HERE, "lib", "libhspmv.so")
 
 F32, F64 = 0, 1
 ALGO_AUTO, ALGO_CSR_VECTOR, ALGO_CSR_STREAM, ALGO_CSR_MERGE, ALGO_CSRK = 0, 1, 2, 3, 4

@@ -387,8 +387,6 @@ int run_csrk(hspmv_matrix *A, bool stream_mode, const T *x, T *y, cudaStream_t s
   p.range_lo[0] = stream_mode ? row_lo : 0;
   p.range_hi[0] = stream_mode ? row_hi : A->m;
   p.range_lo[1] = p.range_hi[1] = p.range_lo[2] = p.range_hi[2] = 0;
-  p.own_row_lo = 0;
-  p.own_row_hi = A->m;
   p.wait_flags = nullptr;
   p.n_wait = 0;
   p.wait_step = 0;
@@ -399,8 +397,6 @@ int run_csrk(hspmv_matrix *A, bool stream_mode, const T *x, T *y, cudaStream_t s
       p.range_lo[i] = halo->lo[i];
       p.range_hi[i] = halo->hi[i];
     }
-    p.own_row_lo = halo->lo[0]; // range 0 is the interior
-    p.own_row_hi = halo->hi[0];
     p.wait_flags = halo->flags;
     p.n_wait = halo->n_wait;
     p.wait_step = halo->step;

@@ -72,6 +72,22 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
       : "memory");
 }
 
+// Metadata loads of the TMA kernels.  `volatile` + "memory" pins them in program order between the
+// other asm statements (the TMA issue before, the mbarrier wait after), so that they are in flight
+// while the warp consumes stages.  The metadata queue is two tiles deep: with a single tile of
+// slack the load -> TMA-issue dependency sat on the critical path, and a handful of extra
+// instructions in front of the load cost 10-17 % of the kernel (profiles/r1_ab_control_path.txt).
+__device__ __forceinline__ int ld_meta(const int *p) {
+  int v;
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_meta(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // streaming 128-bit loads of the matrix arrays: read once, keep them out of L1
 __device__ __forceinline__ int4 ld_stream(const int4 *p) {
   int4 r;
@@ -220,10 +236,9 @@ template <typename T> struct CsrkParams {
   // of tiles in ranges < i, tiles_before[n_ranges] = n_sr
   int n_ranges;
   int64_t range_lo[3], range_hi[3], tiles_before[4];
-  // fused halo wait (hspmv_spmv_halo): rows outside [own_row_lo, own_row_hi) read x entries that a
+  // fused halo wait (hspmv_spmv_halo): the tiles of ranges 1 and 2 read x entries that a
   // neighbour GPU writes over NVLink; before a warp consumes its first such tile it spins
   // (bounded) until every wait_flags[i] >= wait_step.  n_wait == 0: no waiting.
-  int64_t own_row_lo, own_row_hi;
   const int *wait_flags;
   int n_wait, wait_step;
   int *timed_out;
@@ -257,8 +272,8 @@ struct SrCursor {
   bool three;
   __device__ __forceinline__ void prefetch_range(int64_t ss) {
     if (ss < n_ssr) {
-      pre_lo = __ldg(ssr_ptr + ss);
-      pre_hi = __ldg(ssr_ptr + ss + 1);
+      pre_lo = ld_meta(ssr_ptr + ss);
+      pre_hi = ld_meta(ssr_ptr + ss + 1);
     }
   }
   __device__ __forceinline__ bool next(int64_t &sr) {
@@ -362,6 +377,26 @@ __device__ __forceinline__ void csrk_rows(int r0, int r1, const int *__restrict_
   }
 }
 
+// First boundary tile of a warp in hspmv_spmv_halo: the halo part of x must have arrived.  The
+// tile's matrix data is already staged (it is local); only the gathers after this need the halo.
+// Kept out of line: it runs once per warp per launch and must not perturb the main loop's code.
+static __device__ __noinline__ void halo_spin_wait(const int *flags, int n_wait, int step, int *timed_out, int lane) {
+  if (lane < n_wait) {
+    const long long t0 = clock64();
+    for (;;) {
+      int v;
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + lane) : "memory");
+      if (v >= step) break;
+      if (clock64() - t0 > 4000000000LL) {
+        atomicExch(timed_out, 1);
+        break;
+      }
+      __nanosleep(100);
+    }
+  }
+  __syncwarp();
+}
+
 template <typename T, int VEC, int MAIN, int TAIL>
 __global__ void __launch_bounds__(512, 1) csrk_tma_kernel(const CsrkParams<T> p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -409,19 +444,27 @@ __global__ void __launch_bounds__(512, 1) csrk_tma_kernel(const CsrkParams<T> p)
   auto load_meta = [&](int64_t sr) -> SrMeta {
     SrMeta mt;
     if (p.k == 1) {
-      int g = 0;
-      if (p.n_ranges > 1 && sr >= p.tiles_before[1]) g = (p.n_ranges > 2 && sr >= p.tiles_before[2]) ? 2 : 1;
-      const int64_t r0 = p.range_lo[g] + (sr - p.tiles_before[g]) * p.rows_per_tile;
-      const int64_t r1 = (r0 + p.rows_per_tile < p.range_hi[g]) ? r0 + p.rows_per_tile : p.range_hi[g];
+      int64_t r0, hi;
+      if (sr < p.tiles_before[1]) {          // (warp-uniform branches; a single range always takes the first)
+        r0 = p.range_lo[0] + sr * p.rows_per_tile;
+        hi = p.range_hi[0];
+      } else if (sr < p.tiles_before[2]) {
+        r0 = p.range_lo[1] + (sr - p.tiles_before[1]) * p.rows_per_tile;
+        hi = p.range_hi[1];
+      } else {
+        r0 = p.range_lo[2] + (sr - p.tiles_before[2]) * p.rows_per_tile;
+        hi = p.range_hi[2];
+      }
+      const int64_t r1 = (r0 + p.rows_per_tile < hi) ? r0 + p.rows_per_tile : hi;
       mt.r0 = (int)r0;
       mt.r1 = (int)r1;
-      mt.e0 = __ldg(p.rp + r0);
-      mt.e1 = __ldg(p.rp + r1);
+      mt.e0 = ld_meta(p.rp + r0);
+      mt.e1 = ld_meta(p.rp + r1);
     } else {
-      mt.r0 = (int)__ldg(p.sr_ptr + sr);
-      mt.r1 = (int)__ldg(p.sr_ptr + sr + 1);
-      mt.e0 = (int)__ldg(p.sr_e + sr);
-      mt.e1 = (int)__ldg(p.sr_e + sr + 1);
+      mt.r0 = (int)ld_meta(p.sr_ptr + sr);
+      mt.r1 = (int)ld_meta(p.sr_ptr + sr + 1);
+      mt.e0 = (int)ld_meta(p.sr_e + sr);
+      mt.e1 = (int)ld_meta(p.sr_e + sr + 1);
     }
     return mt;
   };
@@ -447,7 +490,12 @@ __global__ void __launch_bounds__(512, 1) csrk_tma_kernel(const CsrkParams<T> p)
         unsigned char *rp_w = base + 16;
         unsigned char *ci_w = rp_w + (size_t)(p.cap_rows + 8) * 4;
         unsigned char *va_w = ci_w + (size_t)(p.cap_nnz + 8) * 4;
-        fence_proxy_async(); // earlier generic-proxy reads of this stage vs. the async writes
+        // No proxy fence here: the stage was only READ through the generic proxy, every one of
+        // those reads has returned (their values fed the FMAs whose sums were stored before the
+        // __syncwarp that precedes this call), and a write-after-read hand-over to the async
+        // proxy needs execution ordering only -- the same contract as a TMA pipeline's
+        // consumer-release / producer-acquire pair.  (A fence.proxy.async costs a MEMBAR.ALL.CTA
+        // that also waits for the y stores; it was 8 % of the kernel, profiles/r1_ab_control_path.txt.)
         mbar_arrive_expect_tx(bar, rp_bytes + ci_bytes + va_bytes);
         bulk_g2s(smem_u32(rp_w), p.rp + rb, rp_bytes, bar, policy);
         bulk_g2s(smem_u32(ci_w), p.ci + eb, ci_bytes, bar, policy);
@@ -458,63 +506,134 @@ __global__ void __launch_bounds__(512, 1) csrk_tma_kernel(const CsrkParams<T> p)
     }
   };
 
-  // ---- prologue: fill the ring
+  // ---- prologue: fill the ring, then keep the metadata of the next TWO tiles in registers
   int64_t sr;
   int filled = 0;
   for (; filled < S; ++filled) {
     if (!cur.next(sr)) break;
     issue(load_meta(sr), filled);
   }
-  bool have_next = cur.next(sr);
-  SrMeta next_meta;
-  next_meta.r0 = next_meta.r1 = next_meta.e0 = next_meta.e1 = 0;
-  if (have_next) next_meta = load_meta(sr); // in flight while the first stage is consumed
+  SrMeta mq0, mq1; // mq0: next tile to issue, mq1: the one after
+  mq0.r0 = mq0.r1 = mq0.e0 = mq0.e1 = 0;
+  mq1 = mq0;
+  bool have0 = cur.next(sr);
+  if (have0) mq0 = load_meta(sr);
+  bool have1 = have0 && cur.next(sr);
+  if (have1) mq1 = load_meta(sr);
+
+  int live = filled;
+  // re-arm stage `stg` with the next tile of this warp and pull one more tile's metadata
+  auto advance = [&](int stg) {
+    --live;
+    if (have0) {
+      issue(mq0, stg);
+      ++live;
+      mq0 = mq1;
+      have0 = have1;
+      have1 = have1 && cur.next(sr);
+      if (have1) mq1 = load_meta(sr);
+    }
+  };
 
   // ---- main loop
   int st = 0;
   uint32_t parity = 0;
-  bool halo_ready = (p.n_wait == 0);
-  for (int live = filled; live > 0;) {
+  // Tiles come to a warp in increasing index order, interior range first: the halo wait sits in
+  // front of the (wait_at)-th tile this warp consumes; -1 = never.
+  int consumed = 0, wait_at = -1;
+  if (p.k == 1 && p.n_wait > 0) {
+    const int64_t gw = (int64_t)blockIdx.x * W + w, GW = (int64_t)gridDim.x * W;
+    const int64_t n_int = p.tiles_before[1] > gw ? (p.tiles_before[1] - gw + GW - 1) / GW : 0;
+    wait_at = (int)n_int;
+  }
+  constexpr int NS = MAIN + TAIL; // register slots per lane in the single-pass path
+  const int sub = lane & (VEC - 1);
+  const int gid = lane / VEC;
+  while (live > 0) {
     const uint32_t bar = smem_u32(bars + st);
     mbar_wait(bar, parity);
     unsigned char *base = ring + (size_t)st * stage_bytes;
     const int *meta = reinterpret_cast<const int *>(base);
     const int r0 = meta[0], r1 = meta[1], e0 = meta[2], e1m = meta[3];
-    if (!halo_ready && (r0 < p.own_row_lo || r0 >= p.own_row_hi)) {
-      // first boundary tile of this warp: the halo part of x must have arrived.  The matrix
-      // data of this tile is already staged (it is local); only the gathers below need the halo.
-      if (lane < p.n_wait) {
-        const long long t0 = clock64();
-        for (;;) {
-          int v;
-          asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p.wait_flags + lane) : "memory");
-          if (v >= p.wait_step) break;
-          if (clock64() - t0 > 4000000000LL) {
-            atomicExch(p.timed_out, 1);
-            break;
-          }
-          __nanosleep(100);
-        }
-      }
-      __syncwarp();
-      halo_ready = true;
-    }
+    if (consumed == wait_at) halo_spin_wait(p.wait_flags, p.n_wait, p.wait_step, p.timed_out, lane);
+    ++consumed;
+    bool released = false;
     if (e1m >= 0) {
       const int *rp_w = reinterpret_cast<const int *>(base + 16);
       const int *ci_w = rp_w + (p.cap_rows + 8);
       const T *va_w = reinterpret_cast<const T *>(reinterpret_cast<const unsigned char *>(ci_w) +
                                                    (size_t)(p.cap_nnz + 8) * 4);
-      csrk_rows<T, VEC, MAIN, TAIL, int>(r0, r1, rp_w, r0 & ~3, ci_w, va_w, e0 & ~3, p.x, p.y, lane);
+      // Single-pass path: the tile has at most one row per lane group and every row fits the
+      // lane's NS register slots.  All of the stage is then read into registers FIRST, the stage
+      // is handed back to TMA at once (the next tile's copies fly during the x gathers instead
+      // of after them), and the gathers and FMAs run from registers.
+      bool single = (r1 - r0) <= 32 / VEC;
+      int rs = 0, re = 0;
+      const int r = r0 + gid;
+      const bool active = r < r1;
+      if (single) {
+        if (active) {
+          const int rbase = r0 & ~3, ebase = e0 & ~3;
+          rs = rp_w[r - rbase] - ebase;
+          re = rp_w[r + 1 - rbase] - ebase;
+        }
+        single = __all_sync(0xffffffffu, re - rs <= VEC * NS);
+      }
+      if (single) {
+        int c[NS];
+        T v[NS];
+        const int j0 = rs + sub, last = re - 1;
+        if (MAIN > 0 && j0 + (MAIN - 1) * VEC < re) {
+#pragma unroll
+          for (int u = 0; u < MAIN; ++u) {
+            c[u] = ci_w[j0 + u * VEC];
+            v[u] = va_w[j0 + u * VEC];
+          }
+#pragma unroll
+          for (int u = MAIN; u < NS; ++u) { // the few slots past the unmasked chunk
+            const int j = j0 + u * VEC;
+            const int jc = j < last ? j : last;
+            c[u] = ci_w[jc];
+            v[u] = va_w[jc];
+            if (j > last) v[u] = (T)0;
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < NS; ++u) {
+            c[u] = 0;
+            v[u] = (T)0;
+          }
+          if (re > rs) {
+#pragma unroll
+            for (int u = 0; u < NS; ++u) {
+              const int j = j0 + u * VEC;
+              const int jc = j < last ? j : last; // slots past the end re-read the row's last entry with value 0
+              c[u] = ci_w[jc];
+              const T t = va_w[jc];
+              v[u] = j > last ? (T)0 : t;
+            }
+          }
+        }
+        __syncwarp(); // every lane has its share of the stage in registers
+        advance(st);
+        released = true;
+        T xv[NS];
+#pragma unroll
+        for (int u = 0; u < NS; ++u) xv[u] = __ldg(p.x + c[u]);
+        T acc = 0;
+#pragma unroll
+        for (int u = 0; u < NS; ++u) acc += v[u] * xv[u];
+        acc = group_sum<T, VEC>(acc);
+        if (active && sub == 0) p.y[r] = acc;
+      } else {
+        csrk_rows<T, VEC, MAIN, TAIL, int>(r0, r1, rp_w, r0 & ~3, ci_w, va_w, e0 & ~3, p.x, p.y, lane);
+      }
     } else {
       csrk_rows<T, VEC, MAIN, TAIL, int64_t>(r0, r1, p.rp, 0, p.ci, p.val, (int64_t)0, p.x, p.y, lane);
     }
-    __syncwarp();
-    --live;
-    if (have_next) {
-      issue(next_meta, st);
-      ++live;
-      have_next = cur.next(sr);
-      if (have_next) next_meta = load_meta(sr);
+    if (!released) {
+      __syncwarp();
+      advance(st);
     }
     if (++st == S) {
       st = 0;
