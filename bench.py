@@ -258,18 +258,24 @@ def run_ours(args, rank, world, local_rank):
     y_local = torch.zeros(m_loc, dtype=torch.float64, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
 
-    def compute(a, b):
-        A.spmv_range(a, b, algo, d_x=x_local.data_ptr(), d_y=y_local.data_ptr(), stream=stream)
+    def compute(a, b, x_ptr=None):
+        A.spmv_range(a, b, algo, d_x=x_ptr or x_local.data_ptr(), d_y=y_local.data_ptr(), stream=stream)
 
     if world > 1:
         ranges = hd.gather_col_ranges((cmin, cmax))
         interior = A.interior_rows(lo - cmin, hi - cmin)
         peer = fused = None
+        x_bufs = [x_local]
         if args.exchange in ("peer", "peer-unfused"):
-            peer = hd.PeerHalo(hs, A.x_ptr(), 8, row_lo, ranges, rank)
+            # second x buffer (ping-pong by step parity, see PeerHalo), also cudaMalloc'ed so that it can be mapped
+            x2_ptr = hs.peer_alloc((cmax - cmin + 1 + 16) * 8)
+            x2 = hd.wrap_device_ptr(x2_ptr, cmax - cmin + 1, torch.float64)
+            x2.copy_(x_local)
+            x_bufs = [x_local, x2]
+            peer = hd.PeerHalo(hs, [A.x_ptr(), x2_ptr], 8, row_lo, ranges, rank)
             if args.exchange == "peer":
-                def fused(a, b, flags, n, step, timeout):
-                    A.spmv_halo(a, b, d_x=x_local.data_ptr(), d_y=y_local.data_ptr(), wait_flags=flags, n_wait=n,
+                def fused(a, b, flags, n, step, timeout, x_ptr):
+                    A.spmv_halo(a, b, d_x=x_ptr, d_y=y_local.data_ptr(), wait_flags=flags, n_wait=n,
                                 wait_step=step, timed_out=timeout, stream=stream)
         sh = hd.ShardedSpMV(row_lo, ranges, rank, x_local, compute, interior, peer=peer, fused=fused)
         if args.no_exchange:   # diagnosis only: local kernels without the halo traffic (x is static)
@@ -287,22 +293,51 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
             torch.cuda.synchronize()
 
+    tick = torch.zeros(1, device="cuda")
+
+    def rendezvous():
+        # The hosts leave dist.barrier() milliseconds apart; with a halo exchange the early ranks'
+        # first kernels would spend that skew spinning on their neighbours' flags inside the timed
+        # region.  A stream-ordered all-reduce completes on every GPU at the same moment (when the
+        # last host has enqueued it), so every rank's start event is recorded together.
+        if world > 1:
+            dist.all_reduce(tick)
+
+    if world > 1 and os.environ.get("HSPMV_SPIN_STATS") and sh.peer is not None and not args.no_exchange:
+        sh.peer.trace = []
     sampler = ClockSampler(local_rank) if rank == 0 else None
     n_warm = max(args.warmup, 3) if world == 1 else max(args.warmup, 10)   # NCCL P2P channels settle late
     for _ in range(n_warm):
         step()
     # ---- timed: K steps, device events, max over ranks
+    spin_diag = world > 1 and bool(os.environ.get("HSPMV_SPIN_STATS")) and sh.peer is not None
+    if spin_diag:
+        sh.peer.spin_reset()
     barrier()
     launches0 = hs.launch_count()
     t_wall0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rendezvous()
     e0.record()
+    t_host0 = time.perf_counter()
     for _ in range(args.steps):
         step()
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     launches = hs.launch_count() - launches0
+    if world > 1 and os.environ.get("HSPMV_SPIN_STATS"):
+        print("rank %d own ms/step %.4f (rows %d, nnz %d)" % (rank, ms / args.steps, m_loc, nnz_loc), flush=True)
+    if world > 1 and sh.peer is not None and sh.peer.trace is not None:
+        d = sh.peer.push_delays_ms()[-args.steps:] or [0.0]
+        print("rank %d push completes %.3f ms (median) / %.3f (max) after the kernel's launch point" % (
+            rank, sorted(d)[len(d) // 2], max(d)), flush=True)
+        sh.peer.trace = None
+    if spin_diag:
+        mx_us, mean_us, hist = sh.peer.spin_stats()
+        print("rank %d halo spin (timed steps): max %.1f us, mean %.1f us per warp-wait, histogram "
+              "[<4,<17,<67,<267,<1067,more us] %s" % (rank, mx_us, mean_us, hist), flush=True)
     barrier()
     kernel_name = A.last_kernel()
 
@@ -318,11 +353,14 @@ def run_ours(args, rank, world, local_rank):
         chk = float(y_host[:1000].abs().sum())
     else:
         def e2e_step():
-            x_local[lo - cmin: hi - cmin].copy_(x_host, non_blocking=True)
+            # the x buffer the coming step will read (ping-pong under the peer exchange)
+            xb = x_bufs[(sh.peer.step + 1) % 2] if (sh.peer is not None and not args.no_exchange) else x_bufs[0]
+            xb[lo - cmin: hi - cmin].copy_(x_host, non_blocking=True)
             step()
             y_host.copy_(y_local, non_blocking=True)
         e2e_step()
         barrier()
+        rendezvous()
         e0.record()
         for _ in range(e2e_steps):
             e2e_step()
@@ -364,14 +402,16 @@ def run_ours(args, rank, world, local_rank):
                        "kernel": kernel_name, "partition": "nnz-balanced row blocks" if world > 1 else "single GPU",
                        "halo_bytes_per_rank_per_step": halo_bytes, "overlap": world > 1 and not args.no_overlap,
                        "exchange": ("none" if args.no_exchange else args.exchange) if world > 1 else "n/a",
-                       "l2": "input (21.9 GB) >> L2 (126 MB): no flush needed"},
+                       "l2": "input (21.9 GB) >> L2 (126 MB): no flush needed",
+                       "start": "host barrier + synchronize, then a stream-ordered all-reduce so all ranks' start "
+                                "events coincide" if world > 1 else "synchronize"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                          "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
                          "frac_of_nominal_8TBs": achieved / 8000.0,
                          "algorithmic_bytes_per_launch": b_launch},
             "e2e": {"value": e2e_value, "unit": "GFLOP/s", "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 8,
                     "steps": e2e_steps, "checksum": chk},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:

@@ -1107,6 +1107,10 @@ int hspmv_stream_wait_ge(void *stream, const int *addr, int value) {
 int hspmv_stream_write(void *stream, int *addr, int value) {
   int rc = load_stream_memops();
   if (rc) return rc;
+  // default flags: the write is ordered after everything that precedes it in the stream (the
+  // peer copies / the kernel).  (CU_STREAM_WRITE_VALUE_NO_MEMORY_BARRIER is rejected with
+  // CUDA_ERROR_INVALID_VALUE by driver 580 through this entry point, and it would also allow
+  // the flag to pass the payload.)
   const int e = g_write_value(stream, (unsigned long long)(uintptr_t)addr, (unsigned int)value, 0);
   if (e) return fail(HSPMV_ECUDA, "cuStreamWriteValue32 failed with CUresult " + std::to_string(e));
   return HSPMV_OK;

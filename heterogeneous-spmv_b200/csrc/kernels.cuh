@@ -381,8 +381,8 @@ __device__ __forceinline__ void csrk_rows(int r0, int r1, const int *__restrict_
 // tile's matrix data is already staged (it is local); only the gathers after this need the halo.
 // Kept out of line: it runs once per warp per launch and must not perturb the main loop's code.
 static __device__ __noinline__ void halo_spin_wait(const int *flags, int n_wait, int step, int *timed_out, int lane) {
+  const long long t0 = clock64();
   if (lane < n_wait) {
-    const long long t0 = clock64();
     for (;;) {
       int v;
       asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + lane) : "memory");
@@ -395,6 +395,17 @@ static __device__ __noinline__ void halo_spin_wait(const int *flags, int n_wait,
     }
   }
   __syncwarp();
+  // diagnostics next to the timeout word: [1] longest spin of any warp so far (in 1024-cycle
+  // units), [2] number of warp-level waits, [3] total spin (1024-cycle units), [4..9] histogram
+  // of the spins: < 8, < 32, < 128, < 512, < 2048, >= 2048 units
+  if (lane == 0) {
+    const int kc = (int)((clock64() - t0) >> 10);
+    atomicMax(timed_out + 1, kc);
+    atomicAdd(timed_out + 2, 1);
+    atomicAdd(timed_out + 3, kc);
+    const int b = kc < 8 ? 0 : kc < 32 ? 1 : kc < 128 ? 2 : kc < 512 ? 3 : kc < 2048 ? 4 : 5;
+    atomicAdd(timed_out + 4 + b, 1);
+  }
 }
 
 template <typename T, int VEC, int MAIN, int TAIL>

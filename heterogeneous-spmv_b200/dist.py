@@ -61,100 +61,134 @@ class PeerHalo:
     no SM: the local SpMV kernel is persistent and owns every SM, so everything that must run
     NEXT to it is a copy-engine or command-processor operation.
 
-    Per step t, all stream-ordered, no host synchronisation:
-      comm stream : wait (cuStreamWaitValue32) until every receiver has acked step t-1
-                    -> peer copies of my boundary slices of x into the neighbours' halo regions
-                    -> write t into each neighbour's data flag (cuStreamWriteValue32)
-      main stream : ONE kernel (hspmv_spmv_halo): interior tiles, then each warp spins (bounded) on
-                    my data flags until they reach t, then the boundary tiles
-                    -> write t into each sender's ack flag
-    The ack keeps a neighbour from overwriting a halo this rank is still reading when x changes
-    between steps.  x_ptr must come from cudaMalloc (the matrix handle's own x vector).
-    Flag words (int32) per rank: [0,P) data flags by sender, [P,2P) ack flags by receiver,
-    [2P] spare, [2P+1] timeout indicator; the data flags this rank waits on are also mirrored
-    compactly at [2P+8, 2P+8+n_senders) so that the kernel can poll one word per lane."""
+    x is ping-ponged between two buffers (as an iterative solver does with x_k / x_{k+1}); step t
+    uses buffer t % 2.  Per step, all stream-ordered, no host synchronisation:
+      main stream : record "x of step t is ready" -> ONE kernel (hspmv_spmv_halo): interior tiles,
+                    then each warp spins (bounded) on my data flags until they reach t, then the
+                    boundary tiles
+      comm stream : wait for that event -> peer copies of my boundary slices of x[t%2] into the
+                    neighbours' halo regions of THEIR x[t%2] -> write t into their data flags
+                    (cuStreamWriteValue32)
+    No acknowledgement is needed: I overwrite a neighbour's halo of buffer b at step t+2 only
+    after my kernel of step t+1 has finished, and that kernel waited for the neighbour's flags of
+    step t+1, which the neighbour sent after ITS kernel of step t (the last reader of buffer b)
+    had finished.  (An earlier version sent acks and waited for them with cuStreamWaitValue32 on
+    the comm stream: a command-processor wait on a word written from another GPU woke up 0.2-0.5 ms
+    late while the persistent kernel was running -- profiles/r1_scaling.md.)
+    The buffers must come from cudaMalloc (hspmv_x_device / hspmv_peer_alloc).
+    Flag words (int32) per rank: [0, n_senders) data flags in sorted-sender order, [32] timeout
+    indicator, [33..35] spin diagnostics."""
 
-    def __init__(self, hs, x_ptr, itemsize, row_lo, col_ranges, rank, group=None):
+    def __init__(self, hs, x_ptrs, itemsize, row_lo, col_ranges, rank, group=None):
         self.hs = hs
         self.rank = rank
         self.P = P = len(row_lo) - 1
         self.itemsize = itemsize
-        self.x_ptr = x_ptr
+        self.x_ptrs = list(x_ptrs)
+        assert len(self.x_ptrs) == 2
         self.cmin = int(col_ranges[rank][0])
         self.recv, self.send = halo_plan(row_lo, col_ranges, rank)
         self.senders = sorted({q for q, _, _ in self.recv})
         self.receivers = sorted({q for q, _, _ in self.send})
-        self.flags = hs.peer_alloc(4 * (3 * P + 16))
-        mine = torch.frombuffer(bytearray(hs.peer_export(x_ptr) + hs.peer_export(self.flags)), dtype=torch.uint8).cuda()
-        allh = [torch.zeros(128, dtype=torch.uint8, device="cuda") for _ in range(P)]
+        assert len(self.senders) <= 32
+        self.flags = hs.peer_alloc(4 * 64)
+        blob = hs.peer_export(self.x_ptrs[0]) + hs.peer_export(self.x_ptrs[1]) + hs.peer_export(self.flags)
+        mine = torch.frombuffer(bytearray(blob), dtype=torch.uint8).cuda()
+        allh = [torch.zeros(192, dtype=torch.uint8, device="cuda") for _ in range(P)]
         dist.all_gather(allh, mine, group=group)
-        # which compact slot do I occupy in each receiver's wait list?  (its sorted sender list)
         senders_t = torch.zeros(P, dtype=torch.int64, device="cuda")
         for q in self.senders:
             senders_t[q] = 1
         all_senders = [torch.zeros(P, dtype=torch.int64, device="cuda") for _ in range(P)]
         dist.all_gather(all_senders, senders_t, group=group)
         self.peer_x, self.peer_flags, self.my_slot_at = {}, {}, {}
-        for q in sorted(set(self.senders) | set(self.receivers)):
+        for q in self.receivers:        # only the ranks I write to need to be mapped
             raw = bytes(allh[q].cpu().numpy().tobytes())
-            self.peer_x[q] = hs.peer_open(raw[:64])
-            self.peer_flags[q] = hs.peer_open(raw[64:])
-        for q in self.receivers:
+            self.peer_x[q] = (hs.peer_open(raw[:64]), hs.peer_open(raw[64:128]))
+            self.peer_flags[q] = hs.peer_open(raw[128:192])
             their_senders = [i for i in range(P) if int(all_senders[q][i])]
             self.my_slot_at[q] = their_senders.index(rank)
         self.peer_cmin = [int(c[0]) for c in col_ranges]
         self.step = 0
         self.comm = torch.cuda.Stream()
-        self.ready = torch.cuda.Event()
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.trace = None   # set to [] to collect (kernel-start, push-done) timing events per step
         self.halo_elems = sum(b - a for _, a, b in self.recv)
         dist.barrier(group=group)
 
     def _w(self, base_ptr, word):
         return base_ptr + 4 * word
 
+    def x_ptr(self, step=None):
+        """Device pointer of the x buffer that step `step` (default: the current one) reads."""
+        return self.x_ptrs[(self.step if step is None else step) % 2]
+
     def wait_words(self):
-        """(device pointer, count) of the compact data-flag words the fused kernel polls."""
-        return self._w(self.flags, 2 * self.P + 8), len(self.senders)
+        """(device pointer, count) of the data-flag words the fused kernel polls."""
+        return self.flags, len(self.senders)
 
     def timeout_word(self):
-        return self._w(self.flags, 2 * self.P + 1)
+        return self._w(self.flags, 32)
+
+    def begin(self):
+        """Step t starts: x[t % 2] is ready at this point of the main stream."""
+        self.step += 1
+        self.ready[self.step % 2].record(torch.cuda.current_stream())
+        if self.trace is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(torch.cuda.current_stream())
+            self.trace.append([e, None])
 
     def post(self):
-        """Start step t on the comm stream: my slices go to the neighbours, then their flags."""
-        hs, P, r = self.hs, self.P, self.rank
-        self.step += 1
-        t = self.step
-        self.ready.record(torch.cuda.current_stream())
-        self.comm.wait_event(self.ready)
+        """Comm stream of step t: my slices go to the neighbours, then their flags."""
+        hs, t = self.hs, self.step
+        b = t % 2
+        self.comm.wait_event(self.ready[b])
         cs = self.comm.cuda_stream
-        if t > 1:
-            for q in self.receivers:   # q has consumed what I sent at t-1
-                hs.stream_wait_ge(cs, self._w(self.flags, P + q), t - 1)
-        for q, a, b in self.send:      # global columns [a,b) of mine -> q's window
-            hs.memcpy_async(self.peer_x[q] + (a - self.peer_cmin[q]) * self.itemsize,
-                            self.x_ptr + (a - self.cmin) * self.itemsize, (b - a) * self.itemsize, cs)
+        for q, lo, hi in self.send:      # global columns [lo,hi) of mine -> q's window
+            hs.memcpy_async(self.peer_x[q][b] + (lo - self.peer_cmin[q]) * self.itemsize,
+                            self.x_ptrs[b] + (lo - self.cmin) * self.itemsize, (hi - lo) * self.itemsize, cs)
         for q in self.receivers:
-            hs.stream_write(cs, self._w(self.peer_flags[q], 2 * P + 8 + self.my_slot_at[q]), t)
+            hs.stream_write(cs, self._w(self.peer_flags[q], self.my_slot_at[q]), t)
+        if self.trace is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(self.comm)
+            self.trace[-1][1] = e
+
+    def push_delays_ms(self):
+        """per traced step: time from the kernel's launch point on the main stream to the
+        completion of this rank's pushes on the comm stream"""
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) for a, b in (self.trace or []) if b is not None]
 
     def wait_data(self):
         """Unfused variant: make the main stream wait for this step's halo (front-end wait)."""
         ms = torch.cuda.current_stream().cuda_stream
         for i in range(len(self.senders)):
-            self.hs.stream_wait_ge(ms, self._w(self.flags, 2 * self.P + 8 + i), self.step)
-
-    def ack(self):
-        ms = torch.cuda.current_stream().cuda_stream
-        for q in self.senders:
-            self.hs.stream_write(ms, self._w(self.peer_flags[q], self.P + self.rank), self.step)
+            self.hs.stream_wait_ge(ms, self._w(self.flags, i), self.step)
 
     def timed_out(self):
         flag = wrap_device_ptr(self.timeout_word(), 1, torch.int32)
         return bool(int(flag.item()))
 
+    def spin_stats(self):
+        """(longest warp spin us, mean warp spin us, histogram) at 1.965 GHz since the last reset;
+        histogram buckets: < 4, < 17, < 67, < 267, < 1067 us, longer."""
+        w = wrap_device_ptr(self.timeout_word(), 10, torch.int32).cpu().tolist()
+        mx, cnt, tot = w[1], max(w[2], 1), w[3]
+        return mx * 1024 / 1965.0, tot * 1024 / 1965.0 / cnt, w[4:10]
+
+    def spin_reset(self):
+        torch.cuda.synchronize()
+        wrap_device_ptr(self._w(self.flags, 33), 9, torch.int32).zero_()
+        torch.cuda.synchronize()
+
     def close(self):
         torch.cuda.synchronize()
-        for p in list(self.peer_x.values()) + list(self.peer_flags.values()):
-            self.hs.peer_close(p)
+        for q in list(self.peer_x):
+            for ptr in self.peer_x[q]:
+                self.hs.peer_close(ptr)
+            self.hs.peer_close(self.peer_flags[q])
         self.hs.peer_free(self.flags)
         self.peer_x, self.peer_flags = {}, {}
 
@@ -170,7 +204,8 @@ class ShardedSpMV:
 
     def __init__(self, row_lo, col_ranges, rank, x_local, compute, interior, group=None, peer=None, fused=None):
         self.peer = peer     # PeerHalo: NVLink peer copies + flags instead of NCCL send/recv
-        self.fused = fused   # fused(interior_lo, interior_hi, flags_ptr, n_flags, step, timeout_ptr): one launch per step
+        self.fused = fused   # fused(interior_lo, interior_hi, flags_ptr, n_flags, step, timeout_ptr, x_ptr): one launch per step
+        # (with a PeerHalo, compute(row_a, row_b, x_ptr) receives the x buffer of the step)
         self.rank = rank
         self.group = group
         self.lo, self.hi = int(row_lo[rank]), int(row_lo[rank + 1])
@@ -197,24 +232,27 @@ class ShardedSpMV:
     def step(self, overlap=True):
         """halo exchange + local SpMV.  With overlap, interior rows run while the halo is in flight."""
         if self.peer is not None and self.fused is not None:
-            self.peer.post()
+            # the kernel goes first: it waits for the halo by itself, and whatever the host does
+            # while enqueueing the exchange then happens while the kernel already runs
+            self.peer.begin()
             flags, n = self.peer.wait_words()
-            self.fused(self.row_a, self.row_b, flags, n, self.peer.step, self.peer.timeout_word())
-            self.peer.ack()
+            self.fused(self.row_a, self.row_b, flags, n, self.peer.step, self.peer.timeout_word(), self.peer.x_ptr())
+            self.peer.post()
             return
         if self.peer is not None:
+            self.peer.begin()
             self.peer.post()
+            xp = self.peer.x_ptr()
             if self.row_b > self.row_a:
-                self.compute(self.row_a, self.row_b)
+                self.compute(self.row_a, self.row_b, xp)
             self.peer.wait_data()
             if self.row_b > self.row_a:
                 if self.row_a > 0:
-                    self.compute(0, self.row_a)
+                    self.compute(0, self.row_a, xp)
                 if self.row_b < self.m:
-                    self.compute(self.row_b, self.m)
+                    self.compute(self.row_b, self.m, xp)
             else:
-                self.compute(0, self.m)
-            self.peer.ack()
+                self.compute(0, self.m, xp)
             return
         works = self.post_exchange()
         if overlap and self.row_b > self.row_a:
