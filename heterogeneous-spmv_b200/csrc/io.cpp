@@ -10,12 +10,26 @@
 // decimals through the exact fast path (<= 15 significant digits and a power of ten <= 22 are
 // both exact doubles, so one IEEE division gives the correctly rounded result -- the same value
 // strtod / fscanf("%lf") return); anything else falls back to strtod / strtof.
+//
+// the file is mmap'ed and parsed by all host threads.  The body is cut into
+// one piece per thread at whitespace, a first pass counts the tokens of every piece, the prefix
+// sum tells each piece which array slots its tokens belong to, and a second pass converts them in
+// place.  The writers format blocks of 2 M entries in parallel and write them in order; "%f" is
+// produced by an exact fixed-point fast path (FMA residual decides the rounding, anything within
+// 1e-6 of a tie goes through snprintf), so the bytes are those of the reference's fprintf.
 #include "host_index.h"
 
+#include <algorithm>
 #include <cerrno>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fcntl.h>
+#include <omp.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 namespace hspmv {
 
@@ -96,81 +110,226 @@ struct Scanner {
   }
 };
 
-bool slurp(const char *path, std::vector<char> &buf, std::string &err) {
-  FILE *fp = std::fopen(path, "rb");
-  if (!fp) {
-    err = std::string("cannot open ") + path + ": " + std::strerror(errno);
-    return false;
+inline bool is_ws(char c) { return c == ' ' || c == '\n' || c == '\t' || c == '\r'; }
+
+// Whole file in memory: mmap when the path is a regular file, fread otherwise (pipes, /dev/stdin).
+struct FileImage {
+  const char *data = nullptr;
+  size_t size = 0;
+  void *map = nullptr;
+  std::vector<char> heap;
+  ~FileImage() {
+    if (map) ::munmap(map, size);
   }
-  std::fseek(fp, 0, SEEK_END);
-  long sz = std::ftell(fp);
-  std::fseek(fp, 0, SEEK_SET);
-  if (sz < 0) sz = 0;
-  buf.resize((size_t)sz);
-  size_t got = sz ? std::fread(buf.data(), 1, (size_t)sz, fp) : 0;
-  std::fclose(fp);
-  if (got != (size_t)sz) {
-    err = std::string("short read on ") + path;
-    return false;
+  bool open(const char *path, std::string &err) {
+    int fd = ::open(path, O_RDONLY);
+    if (fd < 0) {
+      err = std::string("cannot open ") + path + ": " + std::strerror(errno);
+      return false;
+    }
+    struct stat st;
+    if (::fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+      void *m = ::mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+      if (m != MAP_FAILED) {
+        ::madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+        map = m;
+        data = (const char *)m;
+        size = (size_t)st.st_size;
+        ::close(fd);
+        return true;
+      }
+    }
+    char tmp[1 << 16];
+    for (;;) {
+      ssize_t got = ::read(fd, tmp, sizeof(tmp));
+      if (got < 0) {
+        err = std::string("read error on ") + path + ": " + std::strerror(errno);
+        ::close(fd);
+        return false;
+      }
+      if (got == 0) break;
+      heap.insert(heap.end(), tmp, tmp + got);
+    }
+    ::close(fd);
+    data = heap.data();
+    size = heap.size();
+    return true;
+  }
+};
+
+// One array of the file body: `count` tokens converted into dst.
+struct Section {
+  void *dst;
+  int kind; // 0: int32 minus base, 1: uint32, 2: double, 3: float
+  int64_t count;
+  int64_t base;
+};
+
+// Converts the tokens of [p,end) whose global token index starts at `k` into the sections.
+bool convert_tokens(const char *p, const char *end, int64_t k, const Section *secs, int nsec, int64_t total) {
+  Scanner s{p, end};
+  int si = 0;
+  int64_t sec_lo = 0;
+  while (si < nsec && k >= sec_lo + secs[si].count) sec_lo += secs[si++].count;
+  while (k < total) {
+    s.skip();
+    if (s.p >= end) break;
+    const Section &sc = secs[si];
+    const int64_t i = k - sec_lo;
+    if (sc.kind <= 1) {
+      int64_t t;
+      if (!s.next_int(t)) return false;
+      if (sc.kind == 0)
+        ((int32_t *)sc.dst)[i] = (int32_t)(t - sc.base);
+      else
+        ((u32 *)sc.dst)[i] = (u32)(t - sc.base);
+    } else if (sc.kind == 2) {
+      if (!s.next_real(((double *)sc.dst)[i])) return false;
+    } else {
+      if (!s.next_real(((float *)sc.dst)[i])) return false;
+    }
+    if (s.p < end && !is_ws(*s.p)) return false; // "12abc", a decimal where an index belongs, ...
+    ++k;
+    while (si < nsec && k >= sec_lo + secs[si].count) sec_lo += secs[si++].count;
   }
   return true;
 }
 
-template <typename I> bool read_ints(Scanner &s, I *dst, int64_t cnt, int64_t base) {
-  for (int64_t i = 0; i < cnt; ++i) {
-    int64_t t;
-    if (!s.next_int(t)) return false;
-    dst[i] = (I)(t - base);
+// Parses the body [p,end) -- p sits right behind the header -- into the sections, in parallel.
+bool parse_sections(const char *p, const char *end, const Section *secs, int nsec) {
+  int64_t total = 0;
+  for (int i = 0; i < nsec; ++i) total += secs[i].count;
+  const size_t len = (size_t)(end - p);
+  int T = (int)std::min<size_t>((size_t)omp_get_max_threads(), len / ((size_t)1 << 20) + 1);
+  if (T < 1) T = 1;
+  std::vector<const char *> cut((size_t)T + 1);
+  cut[0] = p;
+  cut[(size_t)T] = end;
+  for (int t = 1; t < T; ++t) {
+    const char *c = p + len * (size_t)t / (size_t)T;
+    if (c < cut[(size_t)t - 1]) c = cut[(size_t)t - 1];
+    while (c < end && !is_ws(*c)) ++c; // never split a token: every cut sits on whitespace
+    cut[(size_t)t] = c;
   }
-  return true;
+  std::vector<int64_t> first((size_t)T + 1, 0);
+#pragma omp parallel for num_threads(T) schedule(static, 1)
+  for (int t = 0; t < T; ++t) {
+    const char *c = cut[(size_t)t], *e = cut[(size_t)t + 1];
+    int64_t cnt = 0;
+    bool prev_ws = true; // every cut sits on whitespace (or right behind the header)
+    for (; c < e; ++c) {
+      const bool w = is_ws(*c);
+      cnt += (prev_ws && !w);
+      prev_ws = w;
+    }
+    first[(size_t)t + 1] = cnt;
+  }
+  for (int t = 0; t < T; ++t) first[(size_t)t + 1] += first[(size_t)t];
+  if (first[(size_t)T] < total) return false; // truncated
+  int bad = 0;
+#pragma omp parallel for num_threads(T) schedule(static, 1) reduction(| : bad)
+  for (int t = 0; t < T; ++t)
+    if (first[(size_t)t] < total &&
+        !convert_tokens(cut[(size_t)t], cut[(size_t)t + 1], first[(size_t)t], secs, nsec, total))
+      bad |= 1;
+  return !bad;
 }
 
-bool read_vals(Scanner &s, void *dst, int dtype, int64_t cnt) {
-  if (dtype == HSPMV_F64) {
-    double *d = (double *)dst;
-    for (int64_t i = 0; i < cnt; ++i)
-      if (!s.next_real(d[i])) return false;
-  } else {
-    float *d = (float *)dst;
-    for (int64_t i = 0; i < cnt; ++i)
-      if (!s.next_real(d[i])) return false;
-  }
-  return true;
+// ---- writers ----------------------------------------------------------------------------------
+inline char *put_uint(char *o, uint64_t v) {
+  char tmp[24];
+  int n = 0;
+  do {
+    tmp[n++] = (char)('0' + v % 10);
+    v /= 10;
+  } while (v);
+  while (n) *o++ = tmp[--n];
+  *o++ = ' ';
+  return o;
 }
 
-// appends tokens into a large buffer that is flushed to the FILE in chunks
+// "%f " (= "%.6f "): printf rounds the exact binary value half-to-even at the 6th decimal.
+// v * 1e6 = p + e exactly (FMA residual); n = rint(p); the exact scaled value is n + d with
+// d = (p - n) + e.  Unless d is within 1e-6 of +-0.5, n is the rounded integer.
+inline char *put_real6(char *o, double v) {
+  if (std::fabs(v) < 4.0e9) {
+    const double p = v * 1e6;
+    const double e = std::fma(v, 1e6, -p);
+    const double n = std::nearbyint(p);
+    const double d = (p - n) + e;
+    if (std::fabs(d) <= 0.499999) {
+      uint64_t q = (uint64_t)std::fabs(n);
+      if (std::signbit(v)) *o++ = '-';
+      const uint64_t ip = q / 1000000u;
+      uint32_t fp = (uint32_t)(q % 1000000u);
+      char tmp[24];
+      int k = 0;
+      uint64_t t = ip;
+      do {
+        tmp[k++] = (char)('0' + t % 10);
+        t /= 10;
+      } while (t);
+      while (k) *o++ = tmp[--k];
+      *o++ = '.';
+      for (int i = 5; i >= 0; --i) {
+        o[i] = (char)('0' + fp % 10);
+        fp /= 10;
+      }
+      o += 6;
+      *o++ = ' ';
+      return o;
+    }
+  }
+  return o + std::snprintf(o, 390, "%f ", v);
+}
+
 struct Writer {
   FILE *fp;
-  std::vector<char> buf;
-  size_t pos = 0;
-  explicit Writer(FILE *f) : fp(f), buf(1 << 22) {}
-  void room(size_t need) {
-    if (pos + need > buf.size()) flush();
-  }
-  void flush() {
-    if (pos) std::fwrite(buf.data(), 1, pos, fp);
-    pos = 0;
-  }
-  void put_uint(uint64_t v) {
-    room(24);
-    char tmp[24];
-    int n = 0;
-    do {
-      tmp[n++] = (char)('0' + v % 10);
-      v /= 10;
-    } while (v);
-    while (n) buf[pos++] = tmp[--n];
-    buf[pos++] = ' ';
-  }
-  void put_real6(double v) { // "%f " / "%.6f "
-    room(400);
-    pos += (size_t)std::snprintf(&buf[pos], 390, "%f ", v);
-  }
+  bool ok = true;
+  explicit Writer(FILE *f) : fp(f) {}
   void put_raw(const char *s) {
-    size_t n = std::strlen(s);
-    room(n);
-    std::memcpy(&buf[pos], s, n);
-    pos += n;
+    if (std::fputs(s, fp) < 0) ok = false;
+  }
+  // formats `cnt` entries through fmt(o, i) -> o' in parallel blocks, written in order
+  template <typename F> void put_array(int64_t cnt, size_t max_token, F fmt) {
+    const int64_t block = (int64_t)1 << 21;
+    const int T = std::max(1, omp_get_max_threads());
+    std::vector<std::vector<char>> bufs((size_t)T);
+    std::vector<size_t> used((size_t)T);
+    for (int64_t b0 = 0; b0 < cnt; b0 += block) {
+      const int64_t b1 = std::min(cnt, b0 + block);
+      const int64_t per = (b1 - b0 + T - 1) / T;
+#pragma omp parallel for num_threads(T) schedule(static, 1)
+      for (int t = 0; t < T; ++t) {
+        const int64_t lo = std::min(b1, b0 + per * t), hi = std::min(b1, lo + per);
+        std::vector<char> &buf = bufs[(size_t)t];
+        if (buf.size() < (size_t)per * max_token + 512) buf.resize((size_t)per * max_token + 512);
+        char *o = buf.data();
+        for (int64_t i = lo; i < hi; ++i) {
+          if ((size_t)(o - buf.data()) + 400 > buf.size()) { // a run of huge "%f" values
+            const size_t at = (size_t)(o - buf.data());
+            buf.resize(buf.size() * 2 + 1024);
+            o = buf.data() + at;
+          }
+          o = fmt(o, i);
+        }
+        used[(size_t)t] = (size_t)(o - buf.data());
+      }
+      for (int t = 0; t < T; ++t)
+        if (used[(size_t)t] && std::fwrite(bufs[(size_t)t].data(), 1, used[(size_t)t], fp) != used[(size_t)t]) ok = false;
+    }
+  }
+  template <typename I> void put_uints(const I *v, int64_t cnt, int64_t add) {
+    put_array(cnt, 12, [=](char *o, int64_t i) { return put_uint(o, (uint64_t)((int64_t)v[i] + add)); });
+  }
+  void put_reals(const void *v, int dtype, int64_t cnt) {
+    if (dtype == HSPMV_F64) {
+      const double *d = (const double *)v;
+      put_array(cnt, 24, [=](char *o, int64_t i) { return put_real6(o, d[i]); });
+    } else {
+      const float *d = (const float *)v;
+      put_array(cnt, 24, [=](char *o, int64_t i) { return put_real6(o, (double)d[i]); });
+    }
   }
 };
 
@@ -180,9 +339,9 @@ int read_csr_text(const char *path, int base, int dtype, int64_t *m, int64_t *n,
                   int32_t **rp, int32_t **ci, void **val, std::string &err) {
   if (!path || !m || !n || !nnz || !rp || !ci || !val || (dtype != HSPMV_F32 && dtype != HSPMV_F64))
     return HSPMV_EINVAL;
-  std::vector<char> buf;
-  if (!slurp(path, buf, err)) return HSPMV_EIO;
-  Scanner s{buf.data(), buf.data() + buf.size()};
+  FileImage img;
+  if (!img.open(path, err)) return HSPMV_EIO;
+  Scanner s{img.data, img.data + img.size};
   if (!s.next_int(*m) || !s.next_int(*n) || !s.next_int(*nnz) || *m < 0 || *nnz < 0) {
     err = std::string("bad header in ") + path;
     return HSPMV_EIO;
@@ -196,8 +355,8 @@ int read_csr_text(const char *path, int base, int dtype, int64_t *m, int64_t *n,
     *rp = *ci = nullptr; *val = nullptr;
     return HSPMV_ENOMEM;
   }
-  if (!read_ints(s, *rp, *m + 1, base) || !read_ints(s, *ci, *nnz, base) ||
-      !read_vals(s, *val, dtype, *nnz)) {
+  const Section secs[3] = {{*rp, 0, *m + 1, base}, {*ci, 0, *nnz, base}, {*val, dtype == HSPMV_F64 ? 2 : 3, *nnz, 0}};
+  if (!parse_sections(s.p, s.end, secs, 3)) {
     err = std::string("truncated or malformed body in ") + path;
     std::free(*rp); std::free(*ci); std::free(*val);
     *rp = *ci = nullptr; *val = nullptr;
@@ -217,15 +376,16 @@ int write_csr_text(const char *path, int base, int dtype, int64_t m, int64_t n, 
   char head[96];
   std::snprintf(head, sizeof(head), "%lld %lld %lld\n", (long long)m, (long long)n, (long long)nnz);
   w.put_raw(head);
-  for (int64_t i = 0; i <= m; ++i) w.put_uint((uint64_t)(rp[i] + base));
+  w.put_uints(rp, m + 1, base);
   w.put_raw("\n");
-  for (int64_t i = 0; i < nnz; ++i) w.put_uint((uint64_t)(ci[i] + base));
+  w.put_uints(ci, nnz, base);
   w.put_raw("\n");
-  for (int64_t i = 0; i < nnz; ++i)
-    w.put_real6(dtype == HSPMV_F64 ? ((const double *)val)[i] : (double)((const float *)val)[i]);
+  w.put_reals(val, dtype, nnz);
   w.put_raw("\n");
-  w.flush();
-  std::fclose(fp);
+  if (std::fclose(fp) != 0 || !w.ok) {
+    err = std::string("write error on ") + path;
+    return HSPMV_EIO;
+  }
   return HSPMV_OK;
 }
 
@@ -234,9 +394,9 @@ int read_csr3_text(const char *path, int dtype, int64_t *n_ssr, int64_t *n_sr, i
                    std::string &err) {
   if (!path || !n_ssr || !n_sr || !m || !n || !nnz || !ssr || !sr || !rp || !ci || !val)
     return HSPMV_EINVAL;
-  std::vector<char> buf;
-  if (!slurp(path, buf, err)) return HSPMV_EIO;
-  Scanner s{buf.data(), buf.data() + buf.size()};
+  FileImage img;
+  if (!img.open(path, err)) return HSPMV_EIO;
+  Scanner s{img.data, img.data + img.size};
   if (!s.next_int(*n_ssr) || !s.next_int(*n_sr) || !s.next_int(*m) || !s.next_int(*n) ||
       !s.next_int(*nnz) || *n_ssr < 0 || *n_sr < 0 || *m < 0 || *nnz < 0) {
     err = std::string("bad .csr3 header in ") + path;
@@ -249,10 +409,11 @@ int read_csr3_text(const char *path, int dtype, int64_t *n_ssr, int64_t *n_sr, i
   *ci = (u32 *)std::malloc(((size_t)*nnz + 1) * 4);
   *val = std::malloc(((size_t)*nnz + 1) * vs);
   bool good = *ssr && *sr && *rp && *ci && *val;
-  if (good)
-    good = read_ints(s, *ssr, *n_ssr + 1, 0) && read_ints(s, *sr, *n_sr + 1, 0) &&
-           read_ints(s, *rp, *m + 1, 0) && read_ints(s, *ci, *nnz, 0) &&
-           read_vals(s, *val, dtype, *nnz);
+  if (good) {
+    const Section secs[5] = {{*ssr, 1, *n_ssr + 1, 0}, {*sr, 1, *n_sr + 1, 0}, {*rp, 1, *m + 1, 0},
+                             {*ci, 1, *nnz, 0}, {*val, dtype == HSPMV_F64 ? 2 : 3, *nnz, 0}};
+    good = parse_sections(s.p, s.end, secs, 5);
+  }
   if (!good) {
     err = std::string("truncated or malformed .csr3 body in ") + path;
     std::free(*ssr); std::free(*sr); std::free(*rp); std::free(*ci); std::free(*val);
@@ -276,14 +437,15 @@ int write_csr3_text(const char *path, int dtype, int64_t n_ssr, int64_t n_sr, in
   std::snprintf(head, sizeof(head), "%lld %lld %lld %lld %lld \n", (long long)n_ssr,
                 (long long)n_sr, (long long)m, (long long)n, (long long)nnz);
   w.put_raw(head);
-  for (int64_t i = 0; i <= n_ssr; ++i) w.put_uint(ssr[i]);
-  for (int64_t i = 0; i <= n_sr; ++i) w.put_uint(sr[i]);
-  for (int64_t i = 0; i <= m; ++i) w.put_uint(rp[i]);
-  for (int64_t i = 0; i < nnz; ++i) w.put_uint(ci[i]);
-  for (int64_t i = 0; i < nnz; ++i)
-    w.put_real6(dtype == HSPMV_F64 ? ((const double *)val)[i] : (double)((const float *)val)[i]);
-  w.flush();
-  std::fclose(fp);
+  w.put_uints(ssr, n_ssr + 1, 0);
+  w.put_uints(sr, n_sr + 1, 0);
+  w.put_uints(rp, m + 1, 0);
+  w.put_uints(ci, nnz, 0);
+  w.put_reals(val, dtype, nnz);
+  if (std::fclose(fp) != 0 || !w.ok) {
+    err = std::string("write error on ") + path;
+    return HSPMV_EIO;
+  }
   return HSPMV_OK;
 }
 

@@ -78,7 +78,10 @@ int64_t hspmv_launch_count(void);
  * cuda-spmv-csrk/cuda/spmv.cu:46-93 (index_base 1: 1 is subtracted from every index),
  * cuda-spmv-csr/spmv.cu:11-73.  Grammar: "m n nnz", (m+1) row pointers, nnz column indices,
  * nnz values, whitespace separated.  dtype selects float or double storage of *val.
- * Arrays are allocated by the library (free with hspmv_free_host). */
+ * Arrays are allocated by the library (free with hspmv_free_host).  The file is mmap'ed and parsed
+ * by all host threads (OMP_NUM_THREADS); a malformed or missing token fails the call
+ * (HSPMV_EIO) instead of leaving the arrays half-filled as fscanf does.  Tokens beyond the
+ * announced counts are ignored, as in the reference readers. */
 int hspmv_read_csr_text(const char *path, int index_base, int dtype, int64_t *m, int64_t *n,
                         int64_t *nnz, int32_t **row_ptr, int32_t **col_idx, void **val);
 /* Writes the layout of helpers/converter.m:42-48 (also reformat-csr-to-csr3/spmv.cpp:38-62). */

@@ -157,6 +157,58 @@ def test_text_io_round_trip(tmp_path, hs, gen, oracle):
         hs.my_read_csr(str(tmp_path / "short.csr"))
 
 
+def test_parallel_parser_and_writer_on_a_multi_megabyte_file(tmp_path, hs, gen):
+    """the body is cut into one piece per host thread; every piece must land in the
+    right array slots, and the parallel writer must produce the bytes of fprintf("%d "/"%f ")."""
+    rp, ci, v = gen.stencil27(48, mode="varied")          # 110 k rows, 2.8 M nnz, ~40 MB of text
+    v = v + np.arange(len(v)) % 1000 * 1e-3                # non-dyadic decimals
+    p = str(tmp_path / "big.mtx.rcm.csr")
+    hs.my_write_csr(p, rp, ci, v, index_base=1)
+    assert os.path.getsize(p) > 8 << 20
+    with open(p) as f:
+        head = f.readline().split()
+        l_rp, l_ci, l_v = f.readline(), f.readline(), f.readline()
+    assert head == [str(len(rp) - 1), str(len(rp) - 1), str(len(ci))]
+    assert l_rp == " ".join(str(t + 1) for t in rp.tolist()) + " \n"
+    assert l_ci[:4000] == (" ".join(str(t + 1) for t in ci[:2000].tolist()) + " ")[:4000]
+    assert l_v.split() == ["%f" % t for t in v.tolist()]
+    m, n, nnz, r, c, w = hs.my_read_csr(p, index_base=1, dtype=np.float64)
+    assert np.array_equal(r, rp) and np.array_equal(c, ci)
+    assert np.array_equal(w, np.array([float("%f" % t) for t in v.tolist()]))
+    # a token that is not a number, in the middle of some thread's piece
+    data = open(p, "rb").read()
+    mid = data.index(b" ", len(data) // 2)
+    with open(str(tmp_path / "bad.csr"), "wb") as f:
+        f.write(data[:mid] + b" 12x" + data[mid:])
+    with pytest.raises(hs.HspmvError):
+        hs.my_read_csr(str(tmp_path / "bad.csr"), index_base=1)
+    with open(str(tmp_path / "cut.csr"), "wb") as f:
+        f.write(data[: len(data) - 4096])
+    with pytest.raises(hs.HspmvError):
+        hs.my_read_csr(str(tmp_path / "cut.csr"), index_base=1)
+
+
+def test_fixed_point_formatter_matches_printf(tmp_path, hs):
+    """put_real6 (csrc/io.cpp) must print what fprintf("%f ") prints, ties and huge values included."""
+    rng = np.random.default_rng(5)
+    k = rng.integers(-10**9, 10**9, 20000).astype(np.float64)
+    vals = np.concatenate([
+        k * 5e-7,                                   # decimal ties x.xxxxxx5 (inexact in binary: either side)
+        k * 5e-7 * (1 + 2.0 ** -52), k * 5e-7 * (1 - 2.0 ** -52),
+        np.array([0.0, -0.0, 1e-7, -1e-7, 4.9999999e-7, 5e-7, 5.0000001e-7, 1.5e-6, 2.5e-6, 0.9999995, 0.99999949,
+                  123456.7890125, 3.9e9, 4.1e9, 1e15, -1e15, 1e22, 2.0 ** 52 + 1, 1 / 3, 2 / 3, 1e-300]),
+        rng.standard_normal(20000) * 10.0 ** rng.integers(-8, 9, 20000),
+    ])
+    n = len(vals)
+    rp = np.array([0, n], dtype=np.int32)
+    ci = np.zeros(n, dtype=np.int32)
+    p = str(tmp_path / "fmt.csr")
+    hs.my_write_csr(p, rp, ci, vals, index_base=0)
+    toks = open(p).read().split("\n")[3].split()
+    want = ["%f" % t for t in vals.tolist()]
+    assert toks == want
+
+
 def test_csr3_round_trip_and_layout(tmp_path, hs, gen):
     rp, ci, v = gen.laplace2d_5pt(30, dtype=np.float32)
     o = hs.bandk_host(rp, ci, 3, [7, 8])
