@@ -6,6 +6,7 @@
 #include "kernels.cuh"
 #include "merge.cuh"
 #include "csrk_variants.h"
+#include "bandk_gpu.h"
 
 #include <atomic>
 #include <cstdio>
@@ -83,6 +84,7 @@ struct hspmv_matrix {
   bool stats_ready = false;
 
   int64_t sr_max_rows = 0, sr_max_nnz = 0; // largest super-row (exact stage capacity)
+  int64_t len_p90 = -1;                     // 90th percentile of the row lengths (ragged matrices only; lazily)
 
   // CSR_MERGE
   int64_t merge_tile = 0, merge_tiles = 0;
@@ -317,16 +319,30 @@ int run_csr_vector(hspmv_matrix *A, const T *x, T *y, cudaStream_t st, int64_t r
 }
 
 // largest compiled MAIN <= want_main for this vec (want_main <= 0: the fully masked loop)
-hspmv::CsrkVariant pick_variant(int vec, int want_main) {
+hspmv::CsrkVariant pick_variant(int vec, int want_main, int want_tail = 0) {
   hspmv::CsrkVariant best = {vec, 0, 4};
   bool have = false;
   for (int i = 0; i < hspmv::kNumCsrkVariants; ++i) {
     const hspmv::CsrkVariant &c = hspmv::kCsrkVariants[i];
     if (c.vec != vec) continue;
+    if (have && c.main == best.main) continue; // the first entry of a (vec, main) pair is its default
     if (!have || (c.main <= want_main && c.main > best.main) || (best.main > want_main && c.main < best.main)) {
       if (!have || c.main <= want_main || best.main > want_main) best = c;
       have = true;
     }
+  }
+  if (want_tail > 0) { // smallest compiled tail >= the request for that (vec, main), else the largest
+    hspmv::CsrkVariant alt = best;
+    bool found = false;
+    for (int i = 0; i < hspmv::kNumCsrkVariants; ++i) {
+      const hspmv::CsrkVariant &c = hspmv::kCsrkVariants[i];
+      if (c.vec != vec || c.main != best.main) continue;
+      if (c.tail >= want_tail ? (!found || alt.tail < want_tail || c.tail < alt.tail) : (!found || (alt.tail < want_tail && c.tail > alt.tail))) {
+        alt = c;
+        found = true;
+      }
+    }
+    best = alt;
   }
   return best;
 }
@@ -358,8 +374,33 @@ int run_csrk(hspmv_matrix *A, bool stream_mode, const T *x, T *y, cudaStream_t s
   if (rc0) return rc0;
   const double mean = A->m ? (double)A->nnz / (double)A->m : 1.0;
   const int64_t max_len = A->stats[8];
-  // lanes per row: one round of `chunk` gathers per lane should cover the mean row
+  // lanes per row: one round of gathers per lane should cover the typical row
   int vec = (int)A->opt[HSPMV_OPT_VEC];
+  int chunk = (int)A->opt[HSPMV_OPT_CHUNK];
+  int tail = (int)A->opt[HSPMV_OPT_TAIL];
+  // Ragged rows (config 3: 5-dof shell blocks, 35 +- 10 per row): an unmasked chunk sized for the
+  // mean row sends every shorter or longer row through extra rounds of gather latency.  One
+  // masked round of `tail` gathers per lane that covers the 90th-percentile row is 40 % faster
+  // (profiles/r1_sweep_ragged_cfg3.jsonl), with one row per lane group per tile so that the
+  // register-resident single-pass path applies.
+  const bool ragged = vec <= 0 && chunk == 0 && tail == 0 && (double)max_len > mean * 1.15 + 1.0;
+  int ragged_rpt = 0;
+  if (ragged) {
+    if (A->len_p90 < 0) {
+      std::vector<int32_t> rp;
+      int rc = ensure_host_rp(A, rp);
+      if (rc) return rc;
+      A->len_p90 = hspmv::row_len_percentile(A->m, rp.data(), 90);
+    }
+    const int64_t cover = A->len_p90 > 4 ? A->len_p90 : 4;
+    vec = 1;
+    while (vec < 32 && (double)cover / vec > 12.0) vec <<= 1;
+    tail = (int)((cover + vec - 1) / vec);
+    if (tail < 4) tail = 4;
+    chunk = -1;
+    ragged_rpt = 32 / vec;
+    while (ragged_rpt * mean < 200.0) ragged_rpt += 32 / vec; // keep a TMA tile above ~2.4 KB
+  }
   if (vec <= 0) { // smallest group whose lanes each get <= 14 nonzeros of a typical row (one unmasked chunk)
     vec = 1;
     while (vec < 32 && mean / vec > 14.0) vec <<= 1;
@@ -367,13 +408,12 @@ int run_csrk(hspmv_matrix *A, bool stream_mode, const T *x, T *y, cudaStream_t s
   // gathers a lane keeps in flight per unmasked chunk: the whole share of a typical row if it is
   // short enough (then a row costs one round of latency), else a divisor-ish of it.
   // HSPMV_OPT_CHUNK: > 0 requests that chunk, < 0 forces the fully masked loop.
-  int chunk = (int)A->opt[HSPMV_OPT_CHUNK];
   if (chunk == 0) {
     const int per_lane = (int)(mean / vec);           // floor: every lane of the group has that many
     chunk = per_lane <= 13 ? per_lane : (per_lane % 9 == 0 ? 9 : 8);
     if (chunk < 3) chunk = -1;
   }
-  const hspmv::CsrkVariant variant = pick_variant(vec, chunk);
+  const hspmv::CsrkVariant variant = pick_variant(vec, chunk, tail);
   int warps = (int)A->opt[HSPMV_OPT_WARPS];
   if (warps <= 0) warps = 16; // r1 sweep: occupancy matters more than stage size (profiles/)
   if (warps > 16) warps = 16;
@@ -417,6 +457,7 @@ int run_csrk(hspmv_matrix *A, bool stream_mode, const T *x, T *y, cudaStream_t s
   int64_t typical_rows, typical_nnz, worst_nnz;
   if (stream_mode) {
     int rpt = (int)A->opt[HSPMV_OPT_ROWS_PER_TILE];
+    if (rpt <= 0 && ragged_rpt > 0) rpt = ragged_rpt;
     if (rpt <= 0) { // whole passes of the warp, ~432 nonzeros per tile (r1 sweep: 16 warps x 2 stages of that)
       const int per_pass = 32 / vec;
       int passes = (int)(432.0 / ((mean > 1 ? mean : 1.0) * per_pass) + 0.5);
@@ -889,10 +930,115 @@ int hspmv_reorder_host(int64_t n, int64_t nnz, const uint32_t *perm, const uint3
   return HSPMV_OK;
 }
 
+} // extern "C"
+
+namespace {
+
+// CSR-k bookkeeping shared by the host and the device builder: maps, stats, stale caches
+int finish_csrk(hspmv_matrix *A, int k, std::vector<u32> &perm, std::vector<u32> &sr, std::vector<u32> &ssr) {
+  A->k = k;
+  A->h_perm.swap(perm);
+  A->h_sr.swap(sr);
+  A->h_ssr.swap(ssr);
+  A->n_sr = (int64_t)A->h_sr.size() - 1;
+  A->n_ssr = k == 3 ? (int64_t)A->h_ssr.size() - 1 : 0;
+  A->bins_ready = false;
+  A->merge_tile = 0;
+  free_pipe(A);
+  hspmv::row_stats(A->m, A->h_rp.data(), A->stats);
+  A->stats_ready = true;
+  return upload_csrk_maps(A);
+}
+
+const char *bandk_error(int rc) {
+  return rc == HSPMV_EUNSUPPORTED
+             ? "Band-k: a coarse vertex has no upper/diagonal entry (matrix must be structurally symmetric with a stored diagonal)"
+             : "Band-k: bad arguments (k must be 2 or 3)";
+}
+
+// Device builder: the O(nnz) steps (level-1 coarse graph, A' = P A P^T) run in HBM on the
+// resident arrays; only row_ptr, the coarse graph and the permutation cross PCIe.
+// Returns BANDK_USE_HOST when the host builder has to take over.
+int build_csrk_device(hspmv_matrix *A, int k, const int *sizes) {
+  const size_t vs = A->vsize();
+  if (A->h_rp.empty()) {
+    A->h_rp.resize((size_t)A->m + 1);
+    CU(cudaMemcpy(A->h_rp.data(), A->d_rp, (size_t)(A->m + 1) * 4, cudaMemcpyDeviceToHost));
+  }
+  if (A->nnz == 0 || A->h_rp[(size_t)A->m] != (int32_t)A->nnz) return hspmv::BANDK_USE_HOST;
+  int rc0 = ensure_stats(A);
+  if (rc0) return rc0;
+  if (A->stats[8] > hspmv::BANDK_MAX_ROW) return hspmv::BANDK_USE_HOST; // longest row vs the warp sorter
+  std::vector<u32> start;
+  hspmv::bandk_group_rows((const u32 *)A->h_rp.data(), A->m, hspmv::bandk_threshold(sizes[0], A->nnz, A->m), start);
+  if (start.back() != (u32)A->m) return hspmv::BANDK_USE_HOST; // trailing empty rows: the host path reports it
+  hspmv::CoarseGraph level1;
+  int64_t launches = 0;
+  int rc = hspmv::coarse_level1_device(A->m, A->nnz, (const u32 *)A->d_rp, (const u32 *)A->d_ci, start, A->dev.sms,
+                                       A->stream, level1, &launches);
+  g_launches.fetch_add(launches, std::memory_order_relaxed);
+  if (rc == hspmv::BANDK_USE_HOST) return rc;
+  if (rc == HSPMV_ECUDA) return fail(rc, std::string("Band-k device build: ") + cudaGetErrorString(cudaGetLastError()));
+  if (rc) return fail(rc, bandk_error(rc));
+  std::vector<u32> perm, sr, ssr;
+  rc = hspmv::bandk_finish(A->m, k, sizes, level1, start, perm, sr, ssr);
+  if (rc) return fail(rc, bandk_error(rc));
+
+  // reordered arrays next to the old ones, then swap
+  int *rp2 = nullptr, *ci2 = nullptr;
+  void *val2 = nullptr;
+  u32 *d_perm = nullptr;
+  auto drop = [&]() {
+    cudaFree(rp2);
+    cudaFree(ci2);
+    cudaFree(val2);
+    cudaFree(d_perm);
+    cudaGetLastError();
+  };
+  if (cudaMalloc(&rp2, (size_t)(A->m + 1 + PAD) * 4) != cudaSuccess || cudaMalloc(&ci2, (size_t)(A->nnz + PAD) * 4) != cudaSuccess ||
+      cudaMalloc(&val2, (size_t)(A->nnz + PAD) * vs) != cudaSuccess || cudaMalloc(&d_perm, (size_t)A->m * 4) != cudaSuccess) {
+    drop();
+    return hspmv::BANDK_USE_HOST;
+  }
+  cudaMemsetAsync((char *)rp2 + (size_t)(A->m + 1) * 4, 0, PAD * 4, A->stream);
+  cudaMemsetAsync((char *)ci2 + (size_t)A->nnz * 4, 0, PAD * 4, A->stream);
+  cudaMemsetAsync((char *)val2 + (size_t)A->nnz * vs, 0, PAD * vs, A->stream);
+  cudaMemcpyAsync(d_perm, perm.data(), (size_t)A->m * 4, cudaMemcpyHostToDevice, A->stream);
+  launches = 0;
+  rc = hspmv::reorder_device(A->dtype, A->m, A->nnz, d_perm, (const u32 *)A->d_rp, (const u32 *)A->d_ci, A->d_val,
+                             (u32 *)rp2, (u32 *)ci2, val2, A->dev.sms, A->stream, &launches);
+  g_launches.fetch_add(launches, std::memory_order_relaxed);
+  if (rc) {
+    drop();
+    if (rc == hspmv::BANDK_USE_HOST) return rc;
+    return fail(rc, std::string("Band-k device reorder: ") + cudaGetErrorString(cudaGetLastError()));
+  }
+  cudaFree(d_perm);
+  cudaFree(A->d_rp);
+  cudaFree(A->d_ci);
+  cudaFree(A->d_val);
+  A->d_rp = rp2;
+  A->d_ci = ci2;
+  A->d_val = val2;
+  CU(cudaMemcpy(A->h_rp.data(), A->d_rp, (size_t)(A->m + 1) * 4, cudaMemcpyDeviceToHost));
+  std::vector<int32_t>().swap(A->h_ci); // host copies of the un-reordered entries are stale now
+  std::vector<unsigned char>().swap(A->h_val);
+  return finish_csrk(A, k, perm, sr, ssr);
+}
+
+} // namespace
+
+extern "C" {
+
 int hspmv_build_csrk(hspmv_matrix *A, int k, const int *sup_row_sizes) {
   if (!A) return fail(HSPMV_EINVAL, "null handle");
   if (A->m != A->n) return fail(HSPMV_EINVAL, "Band-k needs a square matrix");
   if (A->k != 1) return fail(HSPMV_ESTATE, "matrix is already in CSR-k form");
+  if (k < 2 || k > 3 || !sup_row_sizes || A->m <= 0) return fail(HSPMV_EINVAL, bandk_error(HSPMV_EINVAL));
+  if (!A->opt[HSPMV_OPT_BANDK_HOST]) {
+    int rc = build_csrk_device(A, k, sup_row_sizes);
+    if (rc != hspmv::BANDK_USE_HOST) return rc;
+  }
   const size_t vs = A->vsize();
   // host copy of the CSR arrays: kept at creation, or fetched back from HBM
   if (A->h_rp.empty()) {
@@ -910,9 +1056,7 @@ int hspmv_build_csrk(hspmv_matrix *A, int k, const int *sup_row_sizes) {
   std::vector<u32> perm, sr, ssr;
   int rc = hspmv::bandk_build(A->m, A->nnz, (const u32 *)A->h_rp.data(), (const u32 *)A->h_ci.data(), k,
                               sup_row_sizes, perm, sr, ssr);
-  if (rc) return fail(rc, rc == HSPMV_EUNSUPPORTED
-                              ? "Band-k: a coarse vertex has no upper/diagonal entry (matrix must be structurally symmetric with a stored diagonal)"
-                              : "Band-k: bad arguments (k must be 2 or 3)");
+  if (rc) return fail(rc, bandk_error(rc));
   if (sr.back() != (u32)A->m) return fail(HSPMV_EUNSUPPORTED, "Band-k: trailing empty rows are not covered by a super-row");
   // A' = P A P^T on the host, then one upload of the REORDERED arrays
   std::vector<int32_t> rp2((size_t)A->m + 1), ci2((size_t)A->nnz);
@@ -931,17 +1075,7 @@ int hspmv_build_csrk(hspmv_matrix *A, int k, const int *sup_row_sizes) {
     CU(cudaMemcpy(A->d_ci, A->h_ci.data(), (size_t)A->nnz * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(A->d_val, A->h_val.data(), (size_t)A->nnz * vs, cudaMemcpyHostToDevice));
   }
-  A->k = k;
-  A->h_perm.swap(perm);
-  A->h_sr.swap(sr);
-  A->h_ssr.swap(ssr);
-  A->n_sr = (int64_t)A->h_sr.size() - 1;
-  A->n_ssr = k == 3 ? (int64_t)A->h_ssr.size() - 1 : 0;
-  A->bins_ready = false;
-  A->merge_tile = 0;
-  free_pipe(A);
-  hspmv::row_stats(A->m, A->h_rp.data(), A->stats);
-  return upload_csrk_maps(A);
+  return finish_csrk(A, k, perm, sr, ssr);
 }
 
 int hspmv_csrk_get(const hspmv_matrix *A, uint32_t *perm, uint32_t *sr_ptr, uint32_t *ssr_ptr) {

@@ -33,10 +33,7 @@ namespace hspmv {
 
 namespace {
 
-struct Coarse {
-  int64_t n = 0;
-  std::vector<u32> rp, adj, mult;
-};
+typedef CoarseGraph Coarse;
 
 // Greedy contiguous grouping (csrk.cpp:1278-1292): a group is closed by the vertex that makes
 // the running nnz reach the threshold; the next vertex opens a new group.
@@ -305,23 +302,40 @@ void expand_level(std::vector<u32> &map, const std::vector<u32> &perm_coarse,
 
 } // namespace
 
-int bandk_build(int64_t n, int64_t nnz, const u32 *rp, const u32 *adj, int k, const int *sizes,
-                std::vector<u32> &perm, std::vector<u32> &sr_ptr, std::vector<u32> &ssr_ptr) {
-  if (k < 2 || k > 3 || n <= 0 || !rp || !adj || !sizes) return HSPMV_EINVAL;
-  if (rp[n] != (u32)nnz) return HSPMV_EINVAL;
+// csrk.cpp:896-897: unsigned * long / long, truncated to int, compared as unsigned
+u32 bandk_threshold(int size, int64_t nnz, int64_t n) {
+  return (u32)(int)((long)(unsigned)size * (long)nnz / (long)n);
+}
 
+void bandk_group_rows(const u32 *rp, int64_t n, u32 T, std::vector<u32> &start) {
+  std::vector<u32> grp;
+  group_rows(rp, n, T, start, grp);
+}
+
+// Levels 1 .. k-1.  `first` (optional) is the level-1 coarse graph with its group starts in
+// `first_map`, built elsewhere (bandk_gpu.cu); without it level 1 is built here from (rp, adj).
+static int bandk_levels(int64_t n, int64_t nnz, const u32 *rp, const u32 *adj, int k, const int *sizes,
+                        CoarseGraph *first, std::vector<u32> *first_map, std::vector<u32> &perm,
+                        std::vector<u32> &sr_ptr, std::vector<u32> &ssr_ptr) {
   std::vector<std::vector<u32>> perms((size_t)k), maps((size_t)k);
   Coarse level[3];
 
   const u32 *cur_rp = rp, *cur_adj = adj;
   int64_t cur_n = n, cur_nnz = nnz;
   for (int lvl = 1; lvl < k; ++lvl) {
-    // csrk.cpp:896-897: unsigned * long / long, truncated to int, compared as unsigned
-    const int T = (int)((long)(unsigned)sizes[lvl - 1] * (long)cur_nnz / (long)cur_n);
-    std::vector<u32> grp;
-    group_rows(cur_rp, cur_n, (u32)T, maps[(size_t)lvl], grp);
-    int rc = build_coarse(cur_rp, cur_adj, maps[(size_t)lvl], grp, level[lvl]);
-    if (rc) return rc;
+    if (lvl == 1 && first) {
+      level[1].n = first->n;
+      level[1].rp.swap(first->rp);
+      level[1].adj.swap(first->adj);
+      level[1].mult.swap(first->mult);
+      maps[1].swap(*first_map);
+    } else {
+      const u32 T = bandk_threshold(sizes[lvl - 1], cur_nnz, cur_n);
+      std::vector<u32> grp;
+      group_rows(cur_rp, cur_n, T, maps[(size_t)lvl], grp);
+      int rc = build_coarse(cur_rp, cur_adj, maps[(size_t)lvl], grp, level[lvl]);
+      if (rc) return rc;
+    }
     std::vector<u32> o2n;
     rcm_order(level[lvl], perms[(size_t)lvl], o2n);
     if (lvl + 1 < k) { // the next level coarsens the renumbered graph
@@ -347,6 +361,19 @@ int bandk_build(int64_t n, int64_t nnz, const u32 *rp, const u32 *adj, int k, co
   else
     ssr_ptr.clear();
   return HSPMV_OK;
+}
+
+int bandk_build(int64_t n, int64_t nnz, const u32 *rp, const u32 *adj, int k, const int *sizes,
+                std::vector<u32> &perm, std::vector<u32> &sr_ptr, std::vector<u32> &ssr_ptr) {
+  if (k < 2 || k > 3 || n <= 0 || !rp || !adj || !sizes) return HSPMV_EINVAL;
+  if (rp[n] != (u32)nnz) return HSPMV_EINVAL;
+  return bandk_levels(n, nnz, rp, adj, k, sizes, nullptr, nullptr, perm, sr_ptr, ssr_ptr);
+}
+
+int bandk_finish(int64_t n, int k, const int *sizes, CoarseGraph &level1, std::vector<u32> &map1,
+                 std::vector<u32> &perm, std::vector<u32> &sr_ptr, std::vector<u32> &ssr_ptr) {
+  if (k < 2 || k > 3 || n <= 0 || !sizes) return HSPMV_EINVAL;
+  return bandk_levels(n, 0, nullptr, nullptr, k, sizes, &level1, &map1, perm, sr_ptr, ssr_ptr);
 }
 
 template <typename T>

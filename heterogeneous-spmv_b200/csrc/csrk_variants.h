@@ -12,16 +12,18 @@ struct CsrkVariant {
   int vec, main, tail;
 };
 
-// X(vec, main, tail).  main = 0: fully masked loop.
+// X(vec, main, tail).  main = 0: fully masked loop (ragged rows: one round of `tail` gathers per
+// lane covers vec * tail entries whatever the row length; the first entry of a (vec, main) pair
+// is the default, HSPMV_OPT_TAIL selects another).
 #define HSPMV_CSRK_VARIANTS_V1(X) \
-  X(1, 0, 4) X(1, 3, 2) X(1, 4, 2) X(1, 5, 2) X(1, 6, 2) X(1, 7, 4) X(1, 8, 4) X(1, 9, 4) X(1, 10, 4) X(1, 11, 4) X(1, 12, 4) X(1, 13, 4)
+  X(1, 0, 4) X(1, 0, 8) X(1, 0, 12) X(1, 3, 2) X(1, 4, 2) X(1, 5, 2) X(1, 6, 2) X(1, 7, 4) X(1, 8, 4) X(1, 9, 4) X(1, 10, 4) X(1, 11, 4) X(1, 12, 4) X(1, 13, 4)
 #define HSPMV_CSRK_VARIANTS_V2(X) \
-  X(2, 0, 8) X(2, 3, 2) X(2, 4, 2) X(2, 5, 2) X(2, 6, 2) X(2, 7, 2) X(2, 8, 2) X(2, 9, 2) X(2, 10, 1) X(2, 11, 1) X(2, 12, 1) X(2, 13, 1)
+  X(2, 0, 8) X(2, 0, 12) X(2, 3, 2) X(2, 4, 2) X(2, 5, 2) X(2, 6, 2) X(2, 7, 2) X(2, 8, 2) X(2, 9, 2) X(2, 10, 1) X(2, 11, 1) X(2, 12, 1) X(2, 13, 1)
 #define HSPMV_CSRK_VARIANTS_V4(X) \
-  X(4, 0, 8) X(4, 3, 1) X(4, 4, 2) X(4, 5, 2) X(4, 6, 1) X(4, 7, 2) X(4, 8, 2) X(4, 9, 2) X(4, 10, 1) X(4, 11, 1) X(4, 12, 1) X(4, 13, 1)
+  X(4, 0, 8) X(4, 0, 12) X(4, 0, 14) X(4, 3, 1) X(4, 4, 2) X(4, 5, 2) X(4, 6, 1) X(4, 7, 2) X(4, 8, 2) X(4, 9, 2) X(4, 10, 1) X(4, 11, 1) X(4, 12, 1) X(4, 13, 1)
 #define HSPMV_CSRK_VARIANTS_V8(X) \
-  X(8, 0, 4) X(8, 3, 1) X(8, 4, 2) X(8, 5, 2) X(8, 6, 2) X(8, 7, 2) X(8, 8, 2) X(8, 9, 2) X(8, 10, 1) X(8, 11, 1) X(8, 12, 1) X(8, 13, 1) \
-  X(16, 0, 4) X(16, 4, 2) X(16, 8, 2) X(16, 12, 1) X(32, 0, 4) X(32, 4, 2) X(32, 8, 2) X(32, 12, 1)
+  X(8, 0, 4) X(8, 0, 8) X(8, 0, 12) X(8, 3, 1) X(8, 4, 2) X(8, 5, 2) X(8, 6, 2) X(8, 7, 2) X(8, 8, 2) X(8, 9, 2) X(8, 10, 1) X(8, 11, 1) X(8, 12, 1) X(8, 13, 1) \
+  X(16, 0, 4) X(16, 0, 8) X(16, 4, 2) X(16, 8, 2) X(16, 12, 1) X(32, 0, 4) X(32, 4, 2) X(32, 8, 2) X(32, 12, 1)
 #define HSPMV_CSRK_VARIANTS(X) \
   HSPMV_CSRK_VARIANTS_V1(X) HSPMV_CSRK_VARIANTS_V2(X) HSPMV_CSRK_VARIANTS_V4(X) HSPMV_CSRK_VARIANTS_V8(X)
 

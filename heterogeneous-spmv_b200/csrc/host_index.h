@@ -14,6 +14,16 @@ typedef uint32_t u32;
 // ---- bandk.cpp
 int bandk_build(int64_t n, int64_t nnz, const u32 *rp, const u32 *adj, int k, const int *sizes,
                 std::vector<u32> &perm, std::vector<u32> &sr_ptr, std::vector<u32> &ssr_ptr);
+// pieces of bandk_build that the device builder (bandk_gpu.cu) reuses: the grouping threshold and
+// walk, and everything from the level-1 coarse graph on (RCM, level 2, uncoarsening)
+struct CoarseGraph {
+  int64_t n = 0;
+  std::vector<u32> rp, adj, mult;
+};
+u32 bandk_threshold(int size, int64_t nnz, int64_t n);
+void bandk_group_rows(const u32 *rp, int64_t n, u32 T, std::vector<u32> &start);
+int bandk_finish(int64_t n, int k, const int *sizes, CoarseGraph &level1, std::vector<u32> &map1,
+                 std::vector<u32> &perm, std::vector<u32> &sr_ptr, std::vector<u32> &ssr_ptr);
 void reorder_f32(int64_t n, const u32 *perm, const u32 *rp, const u32 *ci, const float *v,
                  u32 *rp2, u32 *ci2, float *v2);
 void reorder_f64(int64_t n, const u32 *perm, const u32 *rp, const u32 *ci, const double *v,
@@ -51,6 +61,7 @@ inline int bin_of_len(int64_t len) {
   return 7;
 }
 void row_stats(int64_t m, const int32_t *rp, int64_t out[10]);
+int64_t row_len_percentile(int64_t m, const int32_t *rp, int pct);
 // rows of each bin in ascending order, concatenated; bin_ptr[NUM_BINS+1]
 void bin_rows(int64_t m, const int32_t *rp, std::vector<int32_t> &rows, int64_t bin_ptr[NUM_BINS + 1]);
 // merge-path tile table: tile_row[t] = last row r with rp[r] <= t*tile (t = 0..n_tiles), i.e. the

@@ -55,6 +55,24 @@ void row_stats(int64_t m, const int32_t *rp, int64_t out[10]) {
   out[9] = out[0];
 }
 
+// smallest length L such that at least pct % of the rows have <= L entries
+int64_t row_len_percentile(int64_t m, const int32_t *rp, int pct) {
+  if (m <= 0) return 0;
+  const int64_t cap = 1 << 16;
+  std::vector<int64_t> hist((size_t)cap + 1, 0);
+  for (int64_t r = 0; r < m; ++r) {
+    const int64_t len = (int64_t)rp[r + 1] - rp[r];
+    ++hist[(size_t)(len < cap ? len : cap)];
+  }
+  const int64_t need = (m * pct + 99) / 100;
+  int64_t seen = 0;
+  for (int64_t l = 0; l <= cap; ++l) {
+    seen += hist[(size_t)l];
+    if (seen >= need) return l;
+  }
+  return cap;
+}
+
 void bin_rows(int64_t m, const int32_t *rp, std::vector<int32_t> &rows, int64_t bin_ptr[NUM_BINS + 1]) {
   int64_t cnt[NUM_BINS] = {0};
   for (int64_t r = 0; r < m; ++r) ++cnt[bin_of_len((int64_t)rp[r + 1] - rp[r])];

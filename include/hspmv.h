@@ -59,6 +59,8 @@ enum {
   HSPMV_OPT_MERGE_TILE = 8,   /* CSR_MERGE: nonzeros per CTA tile */
   HSPMV_OPT_THREADS = 9,      /* CSR_VECTOR / CSR_MERGE block size */
   HSPMV_OPT_NO_PIPELINE = 11, /* 1: hspmv_spmv_host copies, computes, copies back strictly in sequence */
+  HSPMV_OPT_TAIL = 13,        /* TMA kernels: masked gathers per lane per round (compiled: see csrc/csrk_variants.h); 0 = default */
+  HSPMV_OPT_BANDK_HOST = 12,  /* 1: hspmv_build_csrk runs entirely on the host (default: coarse graph + reorderA in HBM) */
   HSPMV_OPT_CHUNK = 10        /* TMA kernels: unmasked x gathers a lane keeps in flight per chunk; 0 = auto, < 0 = masked loop only */
 };
 

@@ -152,6 +152,57 @@ def test_csrk_matches_oracle(case, dtype, hs, oracle, gen):
         assert_within_bound(A.A.get_y(False), y_ref_perm, scale[o["perm"]], dtype, hs.ALGO_NAMES[algo])
 
 
+def _arrow(n, hub_deg, band, seed=3):
+    """symmetric band + one hub row/column of hub_deg entries + diagonal (long rows for the sorters)"""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    i = np.repeat(np.arange(n), band)
+    j = np.clip(i + rng.integers(1, 3 * band, len(i)), 0, n - 1)
+    hub = rng.choice(np.arange(1, n), hub_deg, replace=False)
+    i = np.concatenate([i, np.full(hub_deg, n // 3)])
+    j = np.concatenate([j, hub])
+    a = sp.coo_matrix((np.ones(len(i)), (i, j)), shape=(n, n)).tocsr()
+    a = (a + a.T + sp.identity(n)).tocsr()
+    a.sort_indices()
+    a.data[:] = 1.0 + (np.arange(a.nnz) % 7) * 0.25
+    return a.indptr.astype(np.int32), a.indices.astype(np.int32), a.data.astype(np.float64)
+
+
+@pytest.mark.parametrize("case", [
+    ("stencil27", {"g": 20, "mode": "varied"}, 2, [16]),
+    ("stencil27", {"g": 20, "mode": "varied"}, 3, [16, 16]),
+    ("laplace2d_5pt", {"g": 150, "rcm": True}, 3, [96, 8]),
+    ("shell_blocks", {"n": 30000}, 3, [12, 6]),
+    ("arrow", {"n": 6000, "hub_deg": 700, "band": 3}, 3, [8, 4]),     # 700-entry row: shared-memory sorters
+    ("arrow", {"n": 6000, "hub_deg": 1500, "band": 3}, 2, [8]),      # > 1024-entry row: host takes over
+    ("stencil27", {"g": 12}, 2, [400]),                              # 10.8 k entries per group: host takes over
+], ids=lambda c: "%s-k%d-%s" % (c[0], c[2], "x".join(map(str, c[3]))))
+def test_device_bandk_build_equals_host_build(case, hs, gen):
+    """hspmv_build_csrk builds the level-1 coarse graph and A' = P A P^T in HBM; every
+    array must equal what the host builder (HSPMV_OPT_BANDK_HOST, itself pinned to the reference) gives."""
+    g, kw, k, sizes = case
+    rp, ci, v = _arrow(**kw) if g == "arrow" else getattr(gen, g)(**kw)
+    out = []
+    for host in (0, 1):
+        A = hs.Matrix.from_csr(rp, ci, v, keep_host=bool(host))
+        A.set_option(hs.OPT_BANDK_HOST, host)
+        l0 = hs.launch_count()
+        A.build_csrk(k, sizes)
+        out.append((A.csrk(), A.download(), hs.launch_count() - l0, A.row_stats()))
+        x = gen.vector_x(len(rp) - 1, np.float64)
+        A.set_x(x)
+        A.spmv(hs.ALGO_CSRK)
+        out[-1] += (A.get_y(original_order=True),)
+    (cd, md, ld, sd, yd), (ch, mh, lh, sh, yh) = out
+    for key in ch:
+        assert np.array_equal(cd[key], ch[key]), key
+    for a, b, name in zip(md, mh, ("row_ptr", "col_idx", "val")):
+        assert np.array_equal(a, b), name
+    assert np.array_equal(sd, sh) and np.array_equal(yd, yh)
+    handed_over = (g == "arrow" and kw["hub_deg"] > 1024) or sizes[0] >= 400
+    assert (ld > lh) != handed_over, "device builder launches kernels unless it hands over (%d vs %d)" % (ld, lh)
+
+
 def test_csrk_against_golden_reference_vectors(hs, oracle, gen):
     """y from the reference's own OpenMP CSR-k / CSR runs, stored in tests/golden."""
     import importlib.util
