@@ -440,6 +440,12 @@ class Matrix:
         _check(lib().hspmv_spmv_timed(self.h, int(algo), int(warmup), int(iters), int(flush_l2), _p(ms)))
         return ms
 
+    def spmv_timed_batch(self, algo=ALGO_AUTO, warmup=5, iters=20):
+        """ms per launch of `iters` back-to-back launches between one pair of events"""
+        ms = C.c_float()
+        _check(lib().hspmv_spmv_timed_batch(self.h, int(algo), int(warmup), int(iters), C.byref(ms)))
+        return ms.value
+
     def spmv_host(self, x, algo=ALGO_AUTO, out=None):
         """End-to-end call with host buffers (setX + SpMV + getY)."""
         x = np.ascontiguousarray(x, dtype=self.dtype)

@@ -1298,6 +1298,30 @@ int hspmv_spmv_timed(hspmv_matrix *A, int algo, int warmup, int iters, int flush
   return HSPMV_OK;
 }
 
+int hspmv_spmv_timed_batch(hspmv_matrix *A, int algo, int warmup, int iters, float *ms_per_launch) {
+  if (!A || iters < 1 || !ms_per_launch) return fail(HSPMV_EINVAL, "bad arguments");
+  for (int i = 0; i < warmup; ++i) {
+    int rc = do_spmv(A, algo, nullptr, nullptr, A->stream);
+    if (rc) return rc;
+  }
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, A->stream));
+  for (int i = 0; i < iters; ++i) {
+    int rc = do_spmv(A, algo, nullptr, nullptr, A->stream);
+    if (rc) return rc;
+  }
+  CU(cudaEventRecord(e1, A->stream));
+  CU(cudaStreamSynchronize(A->stream));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_per_launch = ms / (float)iters;
+  return HSPMV_OK;
+}
+
 namespace {
 
 // Resolve AUTO the way dispatch() does; the pipelined host path needs a kernel that takes row ranges.

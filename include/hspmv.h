@@ -199,6 +199,10 @@ int hspmv_sync(hspmv_matrix *A);
  * cuda-spmv-csr/spmv.cu:240-260 / spmv-auto-ampere.cu:205-230. */
 int hspmv_spmv_timed(hspmv_matrix *A, int algo, int warmup, int iters, int flush_l2,
                      float *ms_out);
+/* `iters` launches back to back between ONE pair of events after `warmup` untimed ones (the
+ * measurement SURVEY.md 8(d) asks for; per-launch event pairs add ~5 us of launch latency to each
+ * sample, which matters for the 30-60 us launches of configs 1-2).  *ms_per_launch = total / iters. */
+int hspmv_spmv_timed_batch(hspmv_matrix *A, int algo, int warmup, int iters, float *ms_per_launch);
 /* End-to-end plugin call with HOST buffers: set_x (permute + H2D) -> kernel -> get_y (D2H,
  * original row order), synchronous.  This is setX + SpMV + getY of the reference drivers.
  * On large plain-CSR handles the three stages are pipelined over row chunks on three streams:
