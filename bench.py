@@ -414,6 +414,25 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms,
             "clocks": clocks,
         }
+        if world == 1 and not args.no_csrk:
+            # the same matrix in the reference's own formats: Band-k (coarse graph + reorderA in HBM, RCM of the
+            # coarse graph on the host), then the CSR-k kernel; 10 launches back to back after 3 warm-ups
+            formats = {"csr": {"gflops": value, "ms": ms_step}}
+            for k in (2, 3):
+                B = hs.Matrix.stencil(27, g, np.float64, 0)
+                sizes, _, _ = hs.auto_params(nnz_total, n, hs.ARCH_B200)
+                t0 = time.time()
+                B.build_csrk(k, sizes)
+                tb = time.time() - t0
+                B.fill_x_synthetic(0)
+                t = B.spmv_timed_batch(hs.ALGO_CSRK, warmup=3, iters=10)
+                i = B.info()
+                formats["csr%d" % k] = {"gflops": 2.0 * nnz_total / (t * 1e-3) / 1e9, "ms": t, "sizes": sizes[: k - 1],
+                                        "n_sr": i["n_sr"], "n_ssr": i["n_ssr"], "bandk_build_s": tb,
+                                        "gbs": (alg_bytes(n, n, nnz_total) + (i["n_sr"] + i["n_ssr"] + 2) * 4) / (t * 1e-3) / 1e9,
+                                        "kernel": B.last_kernel()}
+                B.close()
+            line["formats"] = formats
         if world == 1 and not args.no_cpu:
             cores = cpu_setup_threads()
             t, nnz_s, kind = cpu_time_sample(g, args.cpu_rows, 5, 20)
@@ -440,6 +459,7 @@ def main():
     ap.add_argument("--algo", default="stream", choices=["stream", "vector", "merge", "auto"])
     ap.add_argument("--cpu-rows", type=int, default=CPU_SAMPLE_ROWS)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-csrk", action="store_true", help="skip the CSR-2 / CSR-3 timings of the same matrix (N = 1 only)")
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "peer-unfused", "nccl"],
                     help="halo exchange: peer = copy-engine NVLink copies into IPC-mapped neighbour buffers + one fused "

@@ -446,6 +446,12 @@ class Matrix:
         _check(lib().hspmv_spmv_timed_batch(self.h, int(algo), int(warmup), int(iters), C.byref(ms)))
         return ms.value
 
+    def autotune(self, algo=ALGO_AUTO, effort=1):
+        """times the kernel shapes around the heuristic choice, keeps the fastest; returns its ms per launch"""
+        ms = C.c_float()
+        _check(lib().hspmv_autotune(self.h, int(algo), int(effort), C.byref(ms)))
+        return ms.value
+
     def spmv_host(self, x, algo=ALGO_AUTO, out=None):
         """End-to-end call with host buffers (setX + SpMV + getY)."""
         x = np.ascontiguousarray(x, dtype=self.dtype)

@@ -1425,6 +1425,58 @@ int spmv_host_pipelined(hspmv_matrix *A, int algo, const void *x_host, void *y_h
 
 } // namespace
 
+int hspmv_autotune(hspmv_matrix *A, int algo, int effort, float *best_ms) {
+  if (!A) return fail(HSPMV_EINVAL, "null handle");
+  const int resolved = resolve_algo(A, algo);
+  float ms = 0;
+  int rc;
+  if (resolved != HSPMV_ALGO_CSR_STREAM && resolved != HSPMV_ALGO_CSRK) { // nothing to choose between
+    rc = hspmv_spmv_timed_batch(A, resolved, 2, 5, &ms);
+    if (!rc && best_ms) *best_ms = ms;
+    return rc;
+  }
+  if ((rc = ensure_stats(A))) return rc;
+  const bool stream = resolved == HSPMV_ALGO_CSR_STREAM;
+  const double mean = A->m ? (double)A->nnz / (double)A->m : 1.0;
+  struct Cand {
+    int64_t vec, chunk, tail, rpt;
+  };
+  std::vector<Cand> cands;
+  cands.push_back({0, 0, 0, 0}); // the heuristic's own choice
+  int v0 = 1;
+  while (v0 < 32 && mean / v0 > 14.0) v0 <<= 1;
+  for (int vec = v0 > 1 ? v0 / 2 : 1; vec <= 32 && vec <= v0 * 2; vec <<= 1) {
+    const int per = (int)(mean / vec);
+    if (per >= 3 && per <= 13) cands.push_back({vec, per, 0, 0});
+    if (effort >= 2 && per - 1 >= 3 && per - 1 <= 13) cands.push_back({vec, per - 1, 0, 0});
+    for (int tail : {8, 12}) {
+      cands.push_back({vec, -1, tail, stream ? 32 / vec : 0});
+      if (effort >= 2 && stream) cands.push_back({vec, -1, tail, 2 * (32 / vec)});
+    }
+  }
+  const int keys[4] = {HSPMV_OPT_VEC, HSPMV_OPT_CHUNK, HSPMV_OPT_TAIL, HSPMV_OPT_ROWS_PER_TILE};
+  Cand best = {A->opt[keys[0]], A->opt[keys[1]], A->opt[keys[2]], A->opt[keys[3]]};
+  float best_t = -1;
+  for (const Cand &c : cands) {
+    const int64_t vals[4] = {c.vec, c.chunk, c.tail, c.rpt};
+    for (int i = 0; i < 4; ++i) A->opt[keys[i]] = vals[i];
+    if (hspmv_spmv_timed_batch(A, resolved, 2, 5, &ms) != HSPMV_OK) { // e.g. no compiled variant
+      cudaGetLastError();
+      continue;
+    }
+    if (best_t < 0 || ms < best_t) {
+      best_t = ms;
+      best = c;
+    }
+  }
+  const int64_t vals[4] = {best.vec, best.chunk, best.tail, best.rpt};
+  for (int i = 0; i < 4; ++i) A->opt[keys[i]] = vals[i];
+  if (best_t < 0) return fail(HSPMV_ECUDA, "autotune: no kernel shape ran");
+  rc = hspmv_spmv_timed_batch(A, resolved, 1, 3, &ms); // leaves last_kernel describing the winner
+  if (!rc && best_ms) *best_ms = ms < best_t ? ms : best_t;
+  return rc;
+}
+
 int hspmv_spmv_host(hspmv_matrix *A, int algo, const void *x_host, void *y_host) {
   if (!A || !x_host || !y_host) return fail(HSPMV_EINVAL, "null");
   const int resolved = resolve_algo(A, algo);

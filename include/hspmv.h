@@ -203,6 +203,13 @@ int hspmv_spmv_timed(hspmv_matrix *A, int algo, int warmup, int iters, int flush
  * measurement SURVEY.md 8(d) asks for; per-launch event pairs add ~5 us of launch latency to each
  * sample, which matters for the 30-60 us launches of configs 1-2).  *ms_per_launch = total / iters. */
 int hspmv_spmv_timed_batch(hspmv_matrix *A, int algo, int warmup, int iters, float *ms_per_launch);
+/* B200 autotuner (the reference tunes by sweeping its drivers from
+ * run_scripts/run_tuning.py:89 and by the per-architecture formulas of spmv-auto-*.cu:130-158).
+ * Times the compiled kernel shapes around the heuristic choice for THIS matrix (lanes per row,
+ * unmasked chunk vs masked one-round tail, rows per tile) with hspmv_spmv_timed_batch and leaves
+ * the fastest in the handle's options.  effort 1: ~10 candidates, 2: ~25.  The x / y contents
+ * are used as they are; y is overwritten.  *best_ms = ms per launch of the winner. */
+int hspmv_autotune(hspmv_matrix *A, int algo, int effort, float *best_ms);
 /* End-to-end plugin call with HOST buffers: set_x (permute + H2D) -> kernel -> get_y (D2H,
  * original row order), synchronous.  This is setX + SpMV + getY of the reference drivers.
  * On large plain-CSR handles the three stages are pipelined over row chunks on three streams:

@@ -65,6 +65,11 @@ def test_csr_ragged_empty_and_long_rows(dtype, hs, oracle, gen):
     check_csr(hs, oracle, gen, rp, ci, v, algos, what="long-rows")
     for vec in (1, 2, 4, 8, 16, 32):   # forced lane counts incl. mismatched ones
         check_csr(hs, oracle, gen, rp, ci, v, [hs.ALGO_CSR_VECTOR, hs.ALGO_CSR_STREAM], opts={hs.OPT_VEC: vec}, what="long-rows vec=%d" % vec)
+    # masked single-round shapes (HSPMV_OPT_TAIL), one row per lane group and several
+    for vec, tail, rpt in ((1, 12, 32), (2, 12, 16), (4, 12, 8), (4, 14, 24), (8, 8, 4), (8, 12, 12), (16, 8, 2), (32, 4, 1)):
+        check_csr(hs, oracle, gen, rp, ci, v, [hs.ALGO_CSR_STREAM],
+                  opts={hs.OPT_VEC: vec, hs.OPT_CHUNK: -1, hs.OPT_TAIL: tail, hs.OPT_ROWS_PER_TILE: rpt},
+                  what="long-rows masked vec=%d tail=%d rpt=%d" % (vec, tail, rpt))
     # tiny capacity: every tile takes the direct (non-staged) path; tiny merge tile: rows span many tiles
     check_csr(hs, oracle, gen, rp, ci, v, [hs.ALGO_CSR_STREAM, hs.ALGO_CSR_MERGE],
               opts={hs.OPT_STAGE_NNZ: 64, hs.OPT_MERGE_TILE: 64, hs.OPT_ROWS_PER_TILE: 7}, what="long-rows tiny tiles")
@@ -201,6 +206,46 @@ def test_device_bandk_build_equals_host_build(case, hs, gen):
     assert np.array_equal(sd, sh) and np.array_equal(yd, yh)
     handed_over = (g == "arrow" and kw["hub_deg"] > 1024) or sizes[0] >= 400
     assert (ld > lh) != handed_over, "device builder launches kernels unless it hands over (%d vs %d)" % (ld, lh)
+
+
+def test_ragged_rows_pick_the_masked_shape_and_batch_timer_runs(hs, oracle, gen):
+    """rows of 35 +- 10 (config-3 stand-in): AUTO must choose the masked one-round shape sized for the
+    90th-percentile row; hspmv_spmv_timed_batch must time launches without changing the result"""
+    rp, ci, v = gen.shell_blocks(40000)
+    lens = np.diff(rp)
+    x = gen.vector_x(len(rp) - 1, np.float64)
+    A = hs.Matrix.from_csr(rp, ci, v)
+    A.set_x(x)
+    ms = A.spmv_timed_batch(hs.ALGO_AUTO, warmup=2, iters=5)
+    assert 0 < ms < 50
+    k = A.last_kernel()
+    p90 = int(np.sort(lens)[(len(lens) * 90 + 99) // 100 - 1])
+    vec = 1
+    while vec < 32 and p90 / vec > 12:
+        vec *= 2
+    assert "vec=%d,main=0," % vec in k, (k, p90)
+    assert_within_bound(A.get_y(), oracle.csr_spmv(rp, ci, v, x), oracle.abs_rowsum(rp, ci, v, x), np.float64, k)
+
+
+def test_autotune_keeps_results_and_is_not_slower(hs, oracle, gen):
+    """hspmv_autotune picks among compiled kernel shapes by measurement"""
+    for (rp, ci, v), k, sizes in ((gen.stencil27(40), 1, None), (gen.shell_blocks(60000), 2, [16]), (gen.laplace2d_5pt(300, rcm=True), 3, [96, 8])):
+        n = len(rp) - 1
+        x = gen.vector_x(n, np.float64)
+        A = hs.Matrix.from_csr(rp, ci, v)
+        if k > 1:
+            A.build_csrk(k, sizes)
+        A.set_x(x)
+        before = min(A.spmv_timed_batch(hs.ALGO_AUTO, warmup=3, iters=10) for _ in range(3))
+        kernel0 = A.last_kernel()
+        tuned = A.autotune(hs.ALGO_AUTO, effort=2)
+        after = min(A.spmv_timed_batch(hs.ALGO_AUTO, warmup=3, iters=10) for _ in range(3))
+        assert after <= before * 1.10 + 0.002, (kernel0, before, A.last_kernel(), after, tuned)
+        A.set_y(np.full(n, np.nan))
+        A.spmv(hs.ALGO_AUTO)
+        assert_within_bound(A.get_y(original_order=True), oracle.csr_spmv(rp, ci, v, x), oracle.abs_rowsum(rp, ci, v, x),
+                            np.float64, "autotuned [%s]" % A.last_kernel())
+        A.close()
 
 
 def test_csrk_against_golden_reference_vectors(hs, oracle, gen):
