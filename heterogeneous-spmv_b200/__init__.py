@@ -266,21 +266,6 @@ def peer_free(dptr):
     _check(lib().hspmv_peer_free(C.c_void_p(dptr)))
 
 
-def peer_push(segments, step, scratch, stream):
-    """segments: list of (dst_peer_ptr, src_local_ptr, nbytes, flag_peer_ptr); one kernel launch."""
-    n = len(segments)
-    assert n <= 8
-    dst = (C.c_void_p * 8)(*[s[0] for s in segments])
-    src = (C.c_void_p * 8)(*[s[1] for s in segments])
-    nb = (C.c_int64 * 8)(*[s[2] for s in segments])
-    fl = (C.c_void_p * 8)(*[s[3] for s in segments])
-    _check(lib().hspmv_peer_push(n, dst, src, nb, fl, int(step), C.c_void_p(scratch), C.c_void_p(stream)))
-
-
-def peer_wait(flags_ptr, n_flags, step, timed_out_ptr, stream):
-    _check(lib().hspmv_peer_wait(C.c_void_p(flags_ptr), int(n_flags), int(step), C.c_void_p(timed_out_ptr), C.c_void_p(stream)))
-
-
 def memcpy_async(dst, src, nbytes, stream):
     _check(lib().hspmv_memcpy_async(C.c_void_p(dst), C.c_void_p(src), C.c_int64(nbytes), C.c_void_p(stream)))
 

@@ -264,12 +264,6 @@ void launch_vector_vec(hspmv_matrix *A, int vec, bool list, const int *rows, int
   }
 }
 
-int pow2_floor_clamped(int64_t v) {
-  int p = 1;
-  while (p < 32 && (int64_t)p * 2 <= v) p <<= 1;
-  return p;
-}
-
 // CSR_VECTOR: one contiguous launch when every row fits the chosen lane count in a few steps,
 // otherwise one launch per non-empty bin.
 template <typename T>
@@ -1611,39 +1605,6 @@ int hspmv_peer_alloc(int64_t bytes, void **dptr) {
 }
 int hspmv_peer_free(void *dptr) {
   if (dptr) CU(cudaFree(dptr));
-  return HSPMV_OK;
-}
-int hspmv_peer_push(int n_segs, void *const *dst, const void *const *src, const int64_t *bytes, int *const *flags,
-                    int step, void *scratch, void *stream) {
-  if (n_segs < 0 || n_segs > 8 || !scratch) return fail(HSPMV_EINVAL, "at most 8 segments per push");
-  hspmv::PushArgs a;
-  std::memset(&a, 0, sizeof(a));
-  int64_t total = 0;
-  for (int i = 0; i < n_segs; ++i) {
-    if (bytes[i] & 3) return fail(HSPMV_EINVAL, "segment size must be a multiple of 4 bytes");
-    a.dst[i] = dst[i];
-    a.src[i] = src[i];
-    a.bytes[i] = bytes[i];
-    a.flag[i] = flags ? flags[i] : nullptr;
-    total += bytes[i];
-  }
-  a.n_segs = n_segs;
-  a.step = step;
-  a.counter = (unsigned int *)scratch;
-  int grid = (int)((total / 8 + 255) / 256);
-  if (grid < 1) grid = 1;
-  if (grid > 32) grid = 32; // a few CTAs saturate one NVLink direction for MB-sized halos
-  hspmv::halo_push_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
-  LAUNCHED();
-  CU(cudaGetLastError());
-  return HSPMV_OK;
-}
-int hspmv_peer_wait(const int *flags, int n_flags, int step, int *timed_out, void *stream) {
-  if (!flags || n_flags < 0 || n_flags > 32 || !timed_out) return fail(HSPMV_EINVAL, "bad arguments");
-  if (n_flags == 0) return HSPMV_OK;
-  hspmv::flag_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags, n_flags, step, (long long)4e9, timed_out);
-  LAUNCHED();
-  CU(cudaGetLastError());
   return HSPMV_OK;
 }
 

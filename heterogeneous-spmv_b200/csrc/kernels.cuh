@@ -677,70 +677,6 @@ static __global__ void sr_offsets_kernel(int64_t n_sr, const uint32_t *__restric
        i += (int64_t)gridDim.x * blockDim.x)
     sr_e[i] = (uint32_t)rp[sr_ptr[i]];
 }
-// ------------------------------------------------------------------------------------------
-// NVLink halo exchange over peer memory (one process per GPU, buffers mapped with CUDA IPC)
-// ------------------------------------------------------------------------------------------
-// halo_push_kernel: every CTA copies its share of up to 8 segments from local memory straight
-// into the peers' x buffers (st.global on peer-mapped addresses -> NVLink), fences at system
-// scope, and the last CTA to finish publishes `step` in each peer's flag word.  The receiver's
-// flag_wait_kernel spins (bounded) on its own flag words.  No host synchronisation, no NCCL.
-struct PushArgs {
-  void *dst[8];
-  const void *src[8];
-  long long bytes[8];
-  int *flag[8];
-  int n_segs;
-  int step;
-  unsigned int *counter; // local scratch, zero between launches
-};
-
-static __global__ void __launch_bounds__(256) halo_push_kernel(PushArgs a) {
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long nth = (long long)gridDim.x * blockDim.x;
-  for (int s = 0; s < a.n_segs; ++s) {
-    const bool wide = ((((uintptr_t)a.dst[s]) | ((uintptr_t)a.src[s]) | (uintptr_t)a.bytes[s]) & 7) == 0;
-    if (wide) {
-      const long long n = a.bytes[s] >> 3;
-      const long long *src = (const long long *)a.src[s];
-      long long *dst = (long long *)a.dst[s];
-      for (long long i = tid; i < n; i += nth) dst[i] = src[i];
-    } else {
-      const long long n = a.bytes[s] >> 2;
-      const int *src = (const int *)a.src[s];
-      int *dst = (int *)a.dst[s];
-      for (long long i = tid; i < n; i += nth) dst[i] = src[i];
-    }
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int done = atomicAdd(a.counter, 1u);
-    if (done == gridDim.x - 1) {
-      *a.counter = 0;
-      __threadfence_system();
-      for (int s = 0; s < a.n_segs; ++s)
-        if (a.flag[s]) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(a.flag[s]), "r"(a.step) : "memory");
-    }
-  }
-}
-
-// waits until every flags[i] >= step (i < n <= 32); gives up after timeout_cycles and records it
-static __global__ void flag_wait_kernel(const int *flags, int n, int step, long long timeout_cycles, int *timed_out) {
-  const int i = threadIdx.x;
-  if (i < n) {
-    const long long t0 = clock64();
-    for (;;) {
-      int v;
-      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + i) : "memory");
-      if (v >= step) break;
-      if (clock64() - t0 > timeout_cycles) {
-        atomicExch(timed_out, 1);
-        break;
-      }
-      __nanosleep(200);
-    }
-  }
-}
 
 // Rows whose columns all lie in [own_lo, own_hi) are "interior" (need no halo).  Reports the last
 // non-interior row of the first half (+1) and the first non-interior row of the second half, so

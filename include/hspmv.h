@@ -256,12 +256,9 @@ int hspmv_interior_rows(const hspmv_matrix *A, int64_t own_col_lo, int64_t own_c
 /* ---- NVLink halo exchange over peer memory (one process per GPU) --------------------------
  * The reference has no multi-GPU code; this replaces what would otherwise be NCCL send/recv.
  * A buffer that came from cudaMalloc (hspmv_x_device(), hspmv_peer_alloc()) is exported as a
- * 64-byte CUDA-IPC handle, opened by the neighbour, and written directly:
- *   hspmv_peer_push  one kernel copies up to 8 segments into peers' memory (NVLink stores),
- *                    fences at system scope and then publishes `step` in each peer's flag word;
- *   hspmv_peer_wait  enqueues a (bounded) spin on local flag words until they reach `step`;
- *                    *timed_out (device int) is set if a peer never arrives.
- * Everything is stream-ordered; there is no host synchronisation inside a step. */
+ * 64-byte CUDA-IPC handle, opened by the neighbour, and written directly with copy-engine
+ * copies; a flag word per sender publishes the step.  Everything is stream-ordered; there is no
+ * host synchronisation inside a step (protocol: heterogeneous-spmv_b200/dist.py, PeerHalo). */
 int hspmv_peer_export(void *dptr, void *handle64);
 int hspmv_peer_open(const void *handle64, void **dptr);
 int hspmv_peer_close(void *dptr);
@@ -279,9 +276,6 @@ int hspmv_stream_wait_ge(void *stream, const int *addr, int value);
  * n_wait == 0 it is hspmv_spmv over the three ranges in that order. */
 int hspmv_spmv_halo(hspmv_matrix *A, int64_t interior_lo, int64_t interior_hi, const void *d_x, void *d_y,
                     const int *wait_flags, int n_wait, int wait_step, int *timed_out, void *stream);
-int hspmv_peer_push(int n_segs, void *const *dst, const void *const *src, const int64_t *bytes,
-                    int *const *flags, int step, void *scratch, void *stream);
-int hspmv_peer_wait(const int *flags, int n_flags, int step, int *timed_out, void *stream);
 
 /* ---- kernel-side index tables, exposed for the bit-exactness tests ------------------ */
 /* CSR_MERGE tile table: tile_row[t] = last row r with row_ptr[r] <= t*tile, t = 0..n_tiles
