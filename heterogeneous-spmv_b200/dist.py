@@ -4,9 +4,10 @@ The reference has no multi-GPU code; this is the new layer north_
 rows are split into contiguous nnz-balanced blocks (hspmv_partition_rows), every rank keeps only
 its block with row pointers rebased and column ids localised to the window [cmin,cmax] of x it
 references, and before each local SpMV the parts of that window owned by other ranks (the halo)
-are fetched with NCCL send/recv over NVLink.  Rows that reference no halo column (the interior,
-hspmv_interior_rows) are launched before the halo has arrived.  Power-law matrices, whose window
-is all of x, use replicated x instead (no per-step traffic while x is static).
+arrive over NVLink: copy-engine writes into IPC-mapped neighbour buffers (PeerHalo, the default)
+or NCCL send/recv (the baseline).  Rows that reference no halo column (the interior,
+hspmv_interior_rows) run before the halo has arrived.  Power-law matrices, whose window is all
+of x, use replicated x instead (ReplicatedSpMV: no per-step traffic while x is static).
 
 Nothing here computes on the CPU: `compute` defaults to the library's CUDA kernels; the CPU
 (gloo) tests inject the oracle only to exercise the plan and the exchange.
@@ -267,3 +268,36 @@ class ShardedSpMV:
             for w in works:
                 w.wait()
             self.compute(0, self.m)
+
+
+class ReplicatedSpMV:
+    """Power-law matrices (BASELINE config 4): a row block references columns all over x, so every
+    rank keeps a full replica of x, y is row-sharded, and a step is just the local SpMV -- no
+    collective while x is static.  When y feeds the next x (power iteration),
+    all_gather_y() rebuilds the replica: one all_gather of the padded row blocks.
+
+    compute() : enqueues / runs the local SpMV of the whole block against the replica.
+    """
+
+    def __init__(self, row_lo, rank, compute, group=None):
+        self.row_lo = [int(t) for t in row_lo]
+        self.rank = rank
+        self.group = group
+        self.compute = compute
+        self.lo, self.hi = self.row_lo[rank], self.row_lo[rank + 1]
+        self.m = self.hi - self.lo
+        self.pad = max(b - a for a, b in zip(self.row_lo[:-1], self.row_lo[1:]))
+
+    def step(self):
+        self.compute()
+
+    def all_gather_y(self, y_local, x_full):
+        """x_full[row_lo[q]:row_lo[q+1]] = rank q's y block, for every q"""
+        world = len(self.row_lo) - 1
+        mine = torch.zeros(self.pad, dtype=y_local.dtype, device=y_local.device)
+        mine[: self.m] = y_local
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine, group=self.group)
+        for q in range(world):
+            a, b = self.row_lo[q], self.row_lo[q + 1]
+            x_full[a:b] = parts[q][: b - a]

@@ -76,6 +76,54 @@ def _worker(rank, world, port, g, out_dir, overlap):
         dist.destroy_process_group()
 
 
+def _worker_replicated(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import oracle as O
+    import partition_oracle as PO
+    import heterogeneous_spmv_b200 as hs
+    from heterogeneous_spmv_b200 import dist as hd
+    from heterogeneous_spmv_b200 import generators as G
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rp, ci, v = G.rmat(12, 8)                      # power-law: every block's window is all of x
+        n = len(rp) - 1
+        row_lo = hs.partition_rows(rp, world)
+        assert np.array_equal(row_lo, PO.partition_rows(rp, world))
+        lo, hi = int(row_lo[rank]), int(row_lo[rank + 1])
+        nnz_blocks = [int(rp[row_lo[q + 1]] - rp[row_lo[q]]) for q in range(world)]
+        assert max(nnz_blocks) - min(nnz_blocks) <= int(np.diff(rp).max())       # nnz-balanced, not row-balanced
+        b_rp = (rp[lo:hi + 1] - rp[lo]).astype(np.int32)
+        b_ci, b_v = ci[rp[lo]:rp[hi]], v[rp[lo]:rp[hi]]
+        x_full = torch.from_numpy(G.vector_x(n).copy())
+        y_local = torch.full((hi - lo,), float("nan"), dtype=torch.float64)
+
+        def compute():
+            y_local[:] = torch.from_numpy(O.csr_spmv(b_rp, b_ci, b_v, x_full.numpy()))
+
+        sh = hd.ReplicatedSpMV(row_lo, rank, compute)
+        x0 = x_full.numpy().copy()
+        sh.step()
+        y1 = O.csr_spmv(rp, ci, v, x0)
+        assert np.array_equal(y_local.numpy(), y1[lo:hi])
+        sh.all_gather_y(y_local, x_full)               # y feeds the next x
+        assert np.array_equal(x_full.numpy(), y1)
+        sh.step()
+        assert np.array_equal(y_local.numpy(), O.csr_spmv(rp, ci, v, y1)[lo:hi])
+        open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_replicated_x_for_power_law(tmp_path):
+    port = 29600 + os.getpid() % 300
+    mp.spawn(_worker_replicated, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(str(tmp_path / "ok0")) and os.path.exists(str(tmp_path / "ok1"))
+
+
 @pytest.mark.parametrize("overlap", [True, False])
 def test_two_rank_halo_exchange(tmp_path, overlap):
     port = 29600 + (os.getpid() % 200) + (1 if overlap else 0)
