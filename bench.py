@@ -141,6 +141,20 @@ def cpu_setup_threads(force=False):
     return int(os.environ["OMP_NUM_THREADS"])
 
 
+def _force_omp_threads():
+    """torchrun exports OMP_NUM_THREADS=1 and libgomp may have read it before cpu_setup_threads()
+    ran (it reads the environment once, when it is loaded): set the team size of the libgomp
+    instance the CPU arm links to, and report what it will really use."""
+    import ctypes as C
+    want = int(os.environ.get("OMP_NUM_THREADS", "1"))
+    try:
+        gomp = C.CDLL("libgomp.so.1", mode=C.RTLD_GLOBAL)
+        gomp.omp_set_num_threads(want)
+        return int(gomp.omp_get_max_threads())
+    except OSError:
+        return want
+
+
 def cpu_sample_arrays(g, rows):
     """CSR arrays of rows [0,rows) of the stencil, fetched from the device generator when a GPU is
     present (fast), else built with numpy."""
@@ -170,6 +184,7 @@ def cpu_time_sample(g, rows, warmup, iters):
         t, _ = _ref_timed(O, rp, ci, v, x, warmup, iters)
         kind = "reference"
     else:
+        _force_omp_threads()
         t, _ = O.csr_spmv_timed(rp, ci, v, x, warmup, iters)   # (min; the port has no mean output)
         kind = "port"
     return t, int(len(ci)), kind
@@ -181,6 +196,7 @@ def _ref_timed(O, rp, ci, v, x, warmup, iters):
     import ctypes as C
     import numpy as np
     L = O.ref("csr", np.float64)
+    _force_omp_threads()
     y = np.zeros(len(rp) - 1)
     fp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
     ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")

@@ -83,6 +83,12 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def row_len_percentile(row_ptr, pct):
+    rp = np.ascontiguousarray(row_ptr, dtype=np.int32)
+    lib().hspmv_row_len_percentile_host.restype = C.c_int64
+    return int(lib().hspmv_row_len_percentile_host(C.c_int64(len(rp) - 1), _p(rp), int(pct)))
+
+
 def launch_count():
     return int(lib().hspmv_launch_count())
 

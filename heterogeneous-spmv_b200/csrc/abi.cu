@@ -1608,6 +1608,11 @@ int hspmv_peer_free(void *dptr) {
   return HSPMV_OK;
 }
 
+int64_t hspmv_row_len_percentile_host(int64_t m, const int32_t *row_ptr, int pct) {
+  if (!row_ptr || m < 0 || pct < 0 || pct > 100) return -1;
+  return hspmv::row_len_percentile(m, row_ptr, pct);
+}
+
 // tile table of the CSR_MERGE path, host restatement (for the bit-exactness tests)
 int hspmv_merge_tile_rows_host(int64_t m, const int32_t *row_ptr, int64_t tile, int32_t *tile_row) {
   if (!row_ptr || !tile_row || tile <= 0) return fail(HSPMV_EINVAL, "bad arguments");

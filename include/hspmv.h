@@ -283,6 +283,9 @@ int hspmv_spmv_halo(hspmv_matrix *A, int64_t interior_lo, int64_t interior_hi, c
 int hspmv_merge_tile_rows_host(int64_t m, const int32_t *row_ptr, int64_t tile, int32_t *tile_row);
 int hspmv_merge_tile_rows_device(const hspmv_matrix *A, int64_t *tile, int64_t *n_tiles,
                                  int32_t *tile_row);
+/* Smallest L such that at least pct % of the rows have <= L entries (the 90th percentile sizes the
+ * masked kernel shape for ragged matrices). */
+int64_t hspmv_row_len_percentile_host(int64_t m, const int32_t *row_ptr, int pct);
 /* CSR_VECTOR bins: rows[m] grouped by bin in ascending row order, bin_ptr[9]. */
 int hspmv_bin_rows_host(int64_t m, const int32_t *row_ptr, int32_t *rows, int64_t *bin_ptr);
 

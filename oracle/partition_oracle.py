@@ -102,3 +102,14 @@ def halo_plan(row_lo, col_ranges, rank):
         if a < b:
             send.append((q, a, b))
     return recv, send
+
+
+def row_len_percentile(rp, pct):
+    """smallest L with at least pct % of the rows of length <= L (include/hspmv.h:
+    hspmv_row_len_percentile_host)"""
+    lens = np.sort(np.diff(np.asarray(rp, dtype=np.int64)))
+    m = len(lens)
+    if m == 0:
+        return 0
+    need = (m * pct + 99) // 100
+    return int(lens[need - 1]) if need > 0 else 0

@@ -248,6 +248,13 @@ def test_partition_bit_exact(parts, hs, gen):
     assert set(a.tolist()) <= set(o["sr_ptr"].tolist())
 
 
+def test_row_length_percentile(hs, gen):
+    for rp, ci, v in (gen.stencil27(9), gen.random_ragged(5000, max_len=80), gen.shell_blocks(20000), gen.rmat(10, 8)):
+        for pct in (0, 1, 50, 90, 99, 100):
+            assert hs.row_len_percentile(rp, pct) == PO.row_len_percentile(rp, pct), pct
+    assert hs.row_len_percentile(np.array([0, 3], np.int32), 90) == 3
+
+
 def test_bins_and_tiles_bit_exact(hs, gen):
     lens = np.array([0, 1, 4, 5, 8, 9, 16, 17, 32, 33, 64, 65, 4096, 4097, 0, 3], dtype=np.int64)
     rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
