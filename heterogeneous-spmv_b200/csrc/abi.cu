@@ -79,6 +79,9 @@ struct hspmv_matrix {
   // CSR_VECTOR bins
   bool bins_ready = false;
   int *d_bin_rows = nullptr;
+  int *d_long_seg = nullptr, *d_long_ptr = nullptr; // last bin: {slot, e0, e1} per segment, segments per row
+  void *d_long_partial = nullptr;
+  int64_t n_long_seg = 0;
   int64_t bin_ptr[hspmv::NUM_BINS + 1] = {0};
   int64_t stats[10] = {0};
   bool stats_ready = false;
@@ -133,7 +136,8 @@ void free_pipe(hspmv_matrix *A) {
 void free_device(hspmv_matrix *A) {
   free_pipe(A);
   void *ptrs[] = {A->d_rp, A->d_ci, A->d_val, A->d_x, A->d_y, A->d_tmp, A->d_sr, A->d_ssr,
-                  A->d_sr_e, A->d_perm, A->d_bin_rows, A->d_tile_row, A->d_carry_row,
+                  A->d_sr_e, A->d_perm, A->d_bin_rows, A->d_long_seg, A->d_long_ptr, A->d_long_partial,
+                  A->d_tile_row, A->d_carry_row,
                   A->d_carry_val, A->d_flush};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -226,8 +230,35 @@ int ensure_bins(hspmv_matrix *A) {
   int rc = ensure_host_rp(A, rp);
   if (rc) return rc;
   hspmv::bin_rows(A->m, rp.data(), rows, A->bin_ptr);
+  if (A->d_bin_rows) cudaFree(A->d_bin_rows);
   CU(cudaMalloc(&A->d_bin_rows, (size_t)(A->m + 1) * 4));
   if (A->m) CU(cudaMemcpy(A->d_bin_rows, rows.data(), (size_t)A->m * 4, cudaMemcpyHostToDevice));
+  // rows of the last bin are cut into segments of LONG_SEG entries, one CTA each
+  const int64_t LONG_SEG = 16384;
+  std::vector<int32_t> seg, seg_ptr(1, 0);
+  for (int64_t i = A->bin_ptr[hspmv::NUM_BINS - 1]; i < A->bin_ptr[hspmv::NUM_BINS]; ++i) {
+    const int32_t r = rows[(size_t)i];
+    const int64_t e0 = rp[(size_t)r], e1 = rp[(size_t)r + 1];
+    const int64_t pieces = (e1 - e0 + LONG_SEG - 1) / LONG_SEG;
+    for (int64_t p = 0; p < pieces; ++p) {
+      seg.push_back((int32_t)(i - A->bin_ptr[hspmv::NUM_BINS - 1]));
+      seg.push_back((int32_t)(e0 + (e1 - e0) * p / pieces));
+      seg.push_back((int32_t)(e0 + (e1 - e0) * (p + 1) / pieces));
+    }
+    seg_ptr.push_back((int32_t)(seg.size() / 3));
+  }
+  for (void *q : {(void *)A->d_long_seg, (void *)A->d_long_ptr, A->d_long_partial})
+    if (q) cudaFree(q);
+  A->d_long_seg = A->d_long_ptr = nullptr;
+  A->d_long_partial = nullptr;
+  A->n_long_seg = (int64_t)seg.size() / 3;
+  if (A->n_long_seg) {
+    CU(cudaMalloc(&A->d_long_seg, seg.size() * 4));
+    CU(cudaMalloc(&A->d_long_ptr, seg_ptr.size() * 4));
+    CU(cudaMalloc(&A->d_long_partial, (size_t)A->n_long_seg * A->vsize()));
+    CU(cudaMemcpy(A->d_long_seg, seg.data(), seg.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(A->d_long_ptr, seg_ptr.data(), seg_ptr.size() * 4, cudaMemcpyHostToDevice));
+  }
   A->bins_ready = true;
   return HSPMV_OK;
 }
@@ -299,8 +330,12 @@ int run_csr_vector(hspmv_matrix *A, const T *x, T *y, cudaStream_t st, int64_t r
       hspmv::zero_rows_kernel<T><<<grid_for(cnt, 256, A->dev.sms * 8), 256, 0, st>>>(cnt, rows, y);
       LAUNCHED();
     } else if (b == hspmv::NUM_BINS - 1) {
-      hspmv::csr_blockrow_kernel<T><<<(int)(cnt < A->dev.sms * 8 ? cnt : A->dev.sms * 8), 256, 0, st>>>(
-          cnt, rows, A->d_rp, A->d_ci, (const T *)A->d_val, x, y);
+      const int64_t ns = A->n_long_seg;
+      hspmv::csr_longrow_kernel<T><<<(int)(ns < A->dev.sms * 8 ? ns : A->dev.sms * 8), 256, 0, st>>>(
+          ns, A->d_long_seg, A->d_ci, (const T *)A->d_val, x, (T *)A->d_long_partial);
+      LAUNCHED();
+      hspmv::longrow_reduce_kernel<T><<<grid_for(cnt, 256, A->dev.sms * 8), 256, 0, st>>>(cnt, rows, A->d_long_ptr,
+                                                                                         (const T *)A->d_long_partial, y);
       LAUNCHED();
     } else {
       launch_vector_vec<T>(A, bin_vec[b], true, rows, cnt, 0, x, y, st);

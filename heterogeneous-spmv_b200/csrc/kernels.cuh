@@ -3,7 +3,7 @@
 //   csr_vector_kernel   row-length-binned CSR: VEC lanes per row (1..32), 4 nonzeros per lane
 //                       per step through 128-bit loads, warp-shuffle reduction.
 //                       Replaces cuda_spmv, cuda-spmv-csr/spmv.cu:117-182 (thread per row).
-//   csr_blockrow_kernel one CTA per very long row (last bin).
+//   csr_longrow_kernel  rows of the last bin cut into segments, one CTA each + ordered reduce.
 //   csrk_tma_kernel     CSR-k: super-super-row -> CTA, super-row -> warp, row -> VEC lanes.
 //                       Each warp owns a private ring of shared-memory stages; one elected lane
 //                       brings the next super-row's row_ptr / col / val segments in with TMA
@@ -183,16 +183,16 @@ csr_vector_kernel(int64_t n_rows, const int *__restrict__ row_list, int64_t row_
   }
 }
 
-// one CTA per long row
+// Very long rows (a power-law hub holds 10^5 entries): one CTA per SEGMENT of a row, so that one
+// row does not serialise on one CTA; seg[3*s..] = {row slot, first entry, end entry}.  The partial
+// sums are added per row in segment order by longrow_reduce_kernel (deterministic, no atomics).
 template <typename T>
 __global__ void __launch_bounds__(256)
-csr_blockrow_kernel(int64_t n_rows, const int *__restrict__ row_list,
-                    const int *__restrict__ rp, const int *__restrict__ ci,
-                    const T *__restrict__ val, const T *__restrict__ x, T *__restrict__ y) {
+csr_longrow_kernel(int64_t n_seg, const int *__restrict__ seg, const int *__restrict__ ci,
+                   const T *__restrict__ val, const T *__restrict__ x, T *__restrict__ partial_out) {
   __shared__ T partial[8];
-  for (int64_t g = blockIdx.x; g < n_rows; g += gridDim.x) {
-    const int64_t r = row_list[g];
-    const int64_t e0 = rp[r], e1 = rp[r + 1];
+  for (int64_t g = blockIdx.x; g < n_seg; g += gridDim.x) {
+    const int64_t e0 = seg[3 * g + 1], e1 = seg[3 * g + 2];
     T acc = 0;
     for (int64_t b = (e0 & ~(int64_t)3) + 4 * (int64_t)threadIdx.x; b < e1; b += 4 * 256) {
       const int4 c = ld_stream(reinterpret_cast<const int4 *>(ci + b));
@@ -209,9 +209,19 @@ csr_blockrow_kernel(int64_t n_rows, const int *__restrict__ row_list,
       T s = 0;
 #pragma unroll
       for (int w = 0; w < 8; ++w) s += partial[w];
-      y[r] = s;
+      partial_out[g] = s;
     }
     __syncthreads();
+  }
+}
+
+template <typename T>
+__global__ void longrow_reduce_kernel(int64_t n_rows, const int *__restrict__ row_list, const int *__restrict__ seg_ptr,
+                                      const T *__restrict__ partial, T *__restrict__ y) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += (int64_t)gridDim.x * blockDim.x) {
+    T s = 0;
+    for (int g = seg_ptr[i]; g < seg_ptr[i + 1]; ++g) s += partial[g];
+    y[row_list[i]] = s;
   }
 }
 

@@ -230,6 +230,42 @@ def rmat(scale, edge_factor=16, dtype=np.float64, abcd=(0.57, 0.19, 0.19, 0.05),
     return rp.astype(np.int32), cols.astype(np.int32), val.astype(dtype)
 
 
+def rmat_torch(scale, edge_factor=16, dtype=np.float64, abcd=(0.57, 0.19, 0.19, 0.05), seed=12345, device="cuda",
+               chunk=1 << 26):
+    """Same construction as rmat() with torch on a device: the scale-24 case takes ~10 s on a GPU
+    instead of minutes in numpy.  Same distribution and value rule, a different random stream, so
+    the matrix differs from rmat()'s; test data only (torch is not used by the library)."""
+    import torch
+    n = 1 << scale
+    m = edge_factor * n
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    a, b, c, _ = abcd
+    keys = []
+    for lo in range(0, m, chunk):
+        cnt = min(chunk, m - lo)
+        r = torch.zeros(cnt, dtype=torch.int64, device=device)
+        cidx = torch.zeros(cnt, dtype=torch.int64, device=device)
+        for _ in range(scale):
+            u = torch.rand(cnt, generator=gen, device=device, dtype=torch.float64)
+            rbit = (u >= a + b).to(torch.int64)
+            cbit = (((u >= a) & (u < a + b)) | (u >= a + b + c)).to(torch.int64)
+            r = (r << 1) | rbit
+            cidx = (cidx << 1) | cbit
+        keys.append(torch.unique((r << scale) | cidx))
+        del r, cidx, u
+    key = torch.unique(torch.cat(keys))
+    del keys
+    rows = key >> scale
+    cols = key & (n - 1)
+    rp = torch.zeros(n + 1, dtype=torch.int64, device=device)
+    rp[1:] = torch.cumsum(torch.bincount(rows, minlength=n), 0)
+    q = ((31 * rows + 17 * cols) % 127) - 63
+    q = torch.where(q == 0, torch.ones_like(q), q)
+    val = q.to(torch.float64) / 64.0
+    return (rp.to(torch.int32).cpu().numpy(), cols.to(torch.int32).cpu().numpy(), val.cpu().numpy().astype(dtype))
+
+
 def random_ragged(n, max_len=40, dtype=np.float64, seed=7, empty_frac=0.1, diag=False):
     """Small irregular test matrix: ragged rows, some empty, unsorted-free, unique columns."""
     rng = np.random.default_rng(seed)

@@ -63,6 +63,14 @@ def test_csr_ragged_empty_and_long_rows(dtype, hs, oracle, gen):
     ci = np.concatenate([np.sort(rng.choice(n, size=l, replace=False)) for l in lens]).astype(np.int32)
     v = (rng.integers(1, 64, size=len(ci)) / 64.0).astype(dtype)
     check_csr(hs, oracle, gen, rp, ci, v, algos, what="long-rows")
+    # hub rows longer than one 16 K-entry segment of the long-row kernel (3 segments, 2, exactly 1)
+    n2 = 60000
+    lens2 = np.full(n2, 2, np.int64)
+    lens2[7], lens2[30000], lens2[59999] = 40001, 16385, 16384
+    rp2 = np.concatenate([[0], np.cumsum(lens2)]).astype(np.int32)
+    ci2 = np.concatenate([np.sort(rng.choice(n2, size=l, replace=False)) for l in lens2]).astype(np.int32)
+    v2 = (rng.integers(1, 64, size=len(ci2)) / 64.0).astype(dtype)
+    check_csr(hs, oracle, gen, rp2, ci2, v2, [hs.ALGO_CSR_VECTOR, hs.ALGO_AUTO, hs.ALGO_CSR_MERGE], what="hub-rows")
     for vec in (1, 2, 4, 8, 16, 32):   # forced lane counts incl. mismatched ones
         check_csr(hs, oracle, gen, rp, ci, v, [hs.ALGO_CSR_VECTOR, hs.ALGO_CSR_STREAM], opts={hs.OPT_VEC: vec}, what="long-rows vec=%d" % vec)
     # masked single-round shapes (HSPMV_OPT_TAIL), one row per lane group and several

@@ -33,6 +33,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="1,2,3,4")
     ap.add_argument("--rmat-scale", type=int, default=24)
+    ap.add_argument("--rmat-on-device", action="store_true", help="generate config 4 with torch on the GPU (seconds instead of minutes)")
     ap.add_argument("--out", default="")
     ap.add_argument("--dtypes", default="f64,f32")
     a = ap.parse_args()
@@ -53,7 +54,10 @@ def main():
             name, (rp, ci, v) = "cfg3b hostile banded runs n=1.5M", G.banded_shell(1_500_000)
             ksizes = [(2, None), (3, None)]
         else:
-            name, (rp, ci, v) = "cfg4 rmat scale %d ef 16" % a.rmat_scale, G.rmat(a.rmat_scale, 16)
+            if a.rmat_on_device:
+                name, (rp, ci, v) = "cfg4 rmat scale %d ef 16 (torch generator)" % a.rmat_scale, G.rmat_torch(a.rmat_scale, 16)
+            else:
+                name, (rp, ci, v) = "cfg4 rmat scale %d ef 16" % a.rmat_scale, G.rmat(a.rmat_scale, 16)
             ksizes = []           # Band-k needs a structurally symmetric matrix (reference quirk Q8)
         n = len(rp) - 1
         nnz = len(ci)
