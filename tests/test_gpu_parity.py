@@ -372,6 +372,48 @@ def test_end_to_end_host_call_and_spmv_h_compat(hs, oracle, gen):
     assert_within_bound(A.spmv_host(x), y_ref, scale, np.float64, "with L2 window")
 
 
+def _stencil27_ones_expected(g, lo=0, hi=None):
+    """A * 1 for the classic 27-point stencil (26 on the diagonal, -1 elsewhere): 27 - (points of the stencil
+    inside the grid) = 27 - cx*cy*cz with c = 2 on a boundary plane, 3 inside"""
+    hi = g ** 3 if hi is None else hi
+    idx = np.arange(lo, hi, dtype=np.int64)
+    out = np.ones(hi - lo, dtype=np.int64)
+    for _ in range(3):
+        c = idx % g
+        out *= np.where((c == 0) | (c == g - 1), 2, 3) if g > 1 else 1
+        idx //= g
+    return (27 - out).astype(np.float64)
+
+
+@pytest.mark.parametrize("fmt", ["csr", "csr2", "csr3"])
+def test_config5_full_size_closed_form(fmt, hs, gen):
+    """BASELINE config 5 at FULL size (27-point 400^3: 64 M rows, 1.72 G nnz, generated in HBM): with x = 1 every
+    y_i is a small integer known in closed form, so the whole 64 M-entry result is compared exactly; CSR-2 / CSR-3 go
+    through the Band-k build in HBM and come back in the original row order."""
+    g = 400
+    n = g ** 3
+    A = hs.Matrix.stencil(27, g, np.float64, 0)
+    info = A.info()
+    assert info["m"] == n and info["nnz"] == 1719374392 == (3 * g - 2) ** 3
+    if fmt != "csr":
+        k = int(fmt[-1])
+        sizes, _, _ = hs.auto_params(info["nnz"], n, hs.ARCH_B200)
+        A.build_csrk(k, sizes)
+        c = A.csrk()
+        assert np.array_equal(np.sort(c["perm"]), np.arange(n, dtype=np.uint32))            # a permutation
+        assert c["sr_ptr"][0] == 0 and c["sr_ptr"][-1] == n and np.all(np.diff(c["sr_ptr"].astype(np.int64)) > 0)
+        if k == 3:
+            assert c["ssr_ptr"][0] == 0 and c["ssr_ptr"][-1] == len(c["sr_ptr"]) - 1
+    A.set_x(np.ones(n))
+    A.set_y(np.full(n, np.nan))
+    A.spmv(hs.ALGO_AUTO)
+    y = A.get_y(original_order=True)
+    want = _stencil27_ones_expected(g)
+    assert np.array_equal(y, want), "%d rows differ [%s]" % (int(np.count_nonzero(y != want)), A.last_kernel())
+    assert float(y.sum()) == 27.0 * n - info["nnz"]
+    A.close()
+
+
 def test_linearity_and_scaling_properties_at_config2_size(hs, gen):
     """Size-independent properties at BASELINE config-2 size (27-pt 100^3, 26.5 M nnz), generated
     in HBM: A(ax+by) = aAx + bAy, classic stencil rows sum to {<=0 interior = 0}, all kernels agree."""
