@@ -584,11 +584,12 @@ __global__ void __launch_bounds__(512, 1) csrk_tma_kernel(const CsrkParams<T> p)
       const int *ci_w = rp_w + (p.cap_rows + 8);
       const T *va_w = reinterpret_cast<const T *>(reinterpret_cast<const unsigned char *>(ci_w) +
                                                    (size_t)(p.cap_nnz + 8) * 4);
-      // Single-pass path: the tile has at most one row per lane group and every row fits the
-      // lane's NS register slots.  All of the stage is then read into registers FIRST, the stage
-      // is handed back to TMA at once (the next tile's copies fly during the x gathers instead
-      // of after them), and the gathers and FMAs run from registers.
-      bool single = (r1 - r0) <= 32 / VEC;
+      // Single-pass path: the tile has at most one row per lane group.  The first VEC * NS entries
+      // of every row are read into registers FIRST, the stage is handed back to TMA at once (the
+      // next tile's copies fly during the x gathers instead of after them), and the gathers and
+      // FMAs run from registers.  The rare row that is longer has its excess consumed straight
+      // from the stage before the release (one extra round of gathers for that tile only).
+      const bool single = (r1 - r0) <= 32 / VEC;
       int rs = 0, re = 0;
       const int r = r0 + gid;
       const bool active = r < r1;
@@ -598,12 +599,28 @@ __global__ void __launch_bounds__(512, 1) csrk_tma_kernel(const CsrkParams<T> p)
           rs = rp_w[r - rbase] - ebase;
           re = rp_w[r + 1 - rbase] - ebase;
         }
-        single = __all_sync(0xffffffffu, re - rs <= VEC * NS);
-      }
-      if (single) {
         int c[NS];
         T v[NS];
         const int j0 = rs + sub, last = re - 1;
+        T acc = 0;
+        if (!__all_sync(0xffffffffu, re - rs <= VEC * NS)) {
+          for (int j = j0 + NS * VEC; __any_sync(0xffffffffu, j < re); j += 4 * VEC) {
+            int cx[4];
+            T vx[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int jj = j + u * VEC;
+              const bool in = jj < re;
+              cx[u] = ci_w[in ? jj : 0];
+              vx[u] = in ? va_w[jj] : (T)0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const T xg = __ldg(p.x + cx[u]);
+              if (j + u * VEC < re) acc += vx[u] * xg; // predicated: an idle slot must not meet an inf in x
+            }
+          }
+        }
         if (MAIN > 0 && j0 + (MAIN - 1) * VEC < re) {
 #pragma unroll
           for (int u = 0; u < MAIN; ++u) {
@@ -641,9 +658,9 @@ __global__ void __launch_bounds__(512, 1) csrk_tma_kernel(const CsrkParams<T> p)
         T xv[NS];
 #pragma unroll
         for (int u = 0; u < NS; ++u) xv[u] = __ldg(p.x + c[u]);
-        T acc = 0;
 #pragma unroll
         for (int u = 0; u < NS; ++u) acc += v[u] * xv[u];
+        if (re <= rs) acc = (T)0; // empty row: its idle slots multiplied 0 by x[0], which may be inf
         acc = group_sum<T, VEC>(acc);
         if (active && sub == 0) p.y[r] = acc;
       } else {

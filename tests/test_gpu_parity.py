@@ -104,6 +104,27 @@ def test_x_with_inf_outside_the_row_pattern(hs, oracle, gen):
     assert unused.size > 0
     x[unused] = np.inf
     check_csr(hs, oracle, gen, rp, ci, v, [hs.ALGO_CSR_VECTOR, hs.ALGO_CSR_STREAM, hs.ALGO_CSR_MERGE], x=x, what="inf")
+    # column 0 unused and x[0] = inf: idle slots of empty rows and of short rows park on index 0;
+    # every masked shape, with rows longer than one round of the shape (the excess loop) as well
+    rp2, ci2, v2 = gen.random_ragged(900, max_len=70, dtype=np.float64, seed=12)
+    ci2 = (ci2 + 1).astype(np.int32)
+    x2 = np.concatenate([[np.inf], gen.vector_x(900)])
+    y_ref = oracle.csr_spmv(rp2, ci2, v2, x2)
+    assert np.all(np.isfinite(y_ref))
+    scale = oracle.abs_rowsum(rp2, ci2, v2, np.where(np.isfinite(x2), x2, 0.0))
+    A = hs.Matrix.from_csr(rp2, ci2, v2, n_cols=901)
+    A.set_x(x2)
+    for opts in ({}, {hs.OPT_VEC: 4, hs.OPT_CHUNK: -1, hs.OPT_TAIL: 8, hs.OPT_ROWS_PER_TILE: 8},
+                 {hs.OPT_VEC: 1, hs.OPT_CHUNK: -1, hs.OPT_TAIL: 12, hs.OPT_ROWS_PER_TILE: 32},
+                 {hs.OPT_VEC: 2, hs.OPT_CHUNK: 5, hs.OPT_ROWS_PER_TILE: 16}, {hs.OPT_VEC: 8, hs.OPT_CHUNK: 3, hs.OPT_ROWS_PER_TILE: 4}):
+        for k_ in (hs.OPT_VEC, hs.OPT_CHUNK, hs.OPT_TAIL, hs.OPT_ROWS_PER_TILE):
+            A.set_option(k_, 0)
+        for k_, val in opts.items():
+            A.set_option(k_, val)
+        for algo in (hs.ALGO_CSR_STREAM, hs.ALGO_CSR_VECTOR, hs.ALGO_AUTO):
+            A.set_y(np.full(900, np.nan))
+            A.spmv(algo)
+            assert_within_bound(A.get_y(), y_ref, scale, np.float64, "inf at x[0] %s [%s]" % (opts, A.last_kernel()))
 
 
 CSRK_CASES = [
