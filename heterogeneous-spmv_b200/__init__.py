@@ -104,13 +104,19 @@ def set_device(i):
 
 
 # ------------------------------------------------------------------------------ file formats
-def my_read_csr(fname, index_base=0, dtype=np.float64):
+def my_read_csr(fname, index_base=0, dtype=np.float64, cache=False):
     """(m, n, nnz, row_start, col_idx, val) -- the reference's my_read_csr.  index_base=0 is the
-    spmv-csr / cuda-spmv-csr reader, index_base=1 the spmv-csrk / cuda-spmv-csrk reader."""
+    spmv-csr / cuda-spmv-csr reader, index_base=1 the spmv-csrk / cuda-spmv-csrk reader.
+    cache=True goes through the binary side file <fname>.hspmvbin and appends cache_hit."""
     m, n, nnz = C.c_int64(), C.c_int64(), C.c_int64()
     rp, ci, val = C.c_void_p(), C.c_void_p(), C.c_void_p()
-    _check(lib().hspmv_read_csr_text(fname.encode(), int(index_base), _dt(dtype), C.byref(m), C.byref(n),
-                                     C.byref(nnz), C.byref(rp), C.byref(ci), C.byref(val)))
+    hit = C.c_int(0)
+    if cache:
+        _check(lib().hspmv_read_csr_cached(fname.encode(), int(index_base), _dt(dtype), C.byref(m), C.byref(n),
+                                           C.byref(nnz), C.byref(rp), C.byref(ci), C.byref(val), C.byref(hit)))
+    else:
+        _check(lib().hspmv_read_csr_text(fname.encode(), int(index_base), _dt(dtype), C.byref(m), C.byref(n),
+                                         C.byref(nnz), C.byref(rp), C.byref(ci), C.byref(val)))
     try:
         row = np.ctypeslib.as_array(C.cast(rp, C.POINTER(C.c_int32)), (m.value + 1,)).copy()
         col = np.ctypeslib.as_array(C.cast(ci, C.POINTER(C.c_int32)), (nnz.value + 1,))[: nnz.value].copy()
@@ -119,6 +125,8 @@ def my_read_csr(fname, index_base=0, dtype=np.float64):
     finally:
         for p in (rp, ci, val):
             lib().hspmv_free_host(p)
+    if cache:
+        return m.value, n.value, nnz.value, row, col, v, bool(hit.value)
     return m.value, n.value, nnz.value, row, col, v
 
 

@@ -753,6 +753,12 @@ int hspmv_read_csr_text(const char *path, int index_base, int dtype, int64_t *m,
   int rc = hspmv::read_csr_text(path, index_base, dtype, m, n, nnz, row_ptr, col_idx, val, err);
   return rc ? fail(rc, err) : rc;
 }
+int hspmv_read_csr_cached(const char *path, int index_base, int dtype, int64_t *m, int64_t *n, int64_t *nnz,
+                          int32_t **row_ptr, int32_t **col_idx, void **val, int *cache_hit) {
+  std::string err;
+  int rc = hspmv::read_csr_cached(path, index_base, dtype, m, n, nnz, row_ptr, col_idx, val, cache_hit, err);
+  return rc ? fail(rc, err.empty() ? "read_csr_cached: bad arguments" : err) : rc;
+}
 int hspmv_write_csr_text(const char *path, int index_base, int dtype, int64_t m, int64_t n,
                          int64_t nnz, const int32_t *row_ptr, const int32_t *col_idx, const void *val) {
   std::string err;

@@ -32,6 +32,8 @@ void reorder_f64(int64_t n, const u32 *perm, const u32 *rp, const u32 *ci, const
 // ---- io.cpp
 int read_csr_text(const char *path, int base, int dtype, int64_t *m, int64_t *n, int64_t *nnz,
                   int32_t **rp, int32_t **ci, void **val, std::string &err);
+int read_csr_cached(const char *path, int base, int dtype, int64_t *m, int64_t *n, int64_t *nnz,
+                    int32_t **rp, int32_t **ci, void **val, int *cache_hit, std::string &err);
 int write_csr_text(const char *path, int base, int dtype, int64_t m, int64_t n, int64_t nnz,
                    const int32_t *rp, const int32_t *ci, const void *val, std::string &err);
 int read_csr3_text(const char *path, int dtype, int64_t *n_ssr, int64_t *n_sr, int64_t *m,

@@ -365,6 +365,108 @@ int read_csr_text(const char *path, int base, int dtype, int64_t *m, int64_t *n,
   return HSPMV_OK;
 }
 
+// ---- binary side file ------------------------------------------------------------------------
+namespace {
+struct BinHeader { // 64 bytes
+  char magic[8];   // "HSPMVBIN"
+  int32_t version, dtype, base, pad;
+  int64_t m, n, nnz;
+  int64_t text_size, text_mtime_ns;
+};
+
+bool text_identity(const char *path, int64_t &size, int64_t &mtime_ns) {
+  struct stat st;
+  if (::stat(path, &st) != 0) return false;
+  size = (int64_t)st.st_size;
+  mtime_ns = (int64_t)st.st_mtim.tv_sec * 1000000000LL + (int64_t)st.st_mtim.tv_nsec;
+  return true;
+}
+
+bool read_all(int fd, void *dst, size_t bytes) {
+  char *p = (char *)dst;
+  while (bytes) {
+    ssize_t got = ::read(fd, p, bytes < ((size_t)1 << 30) ? bytes : ((size_t)1 << 30));
+    if (got <= 0) return false;
+    p += got;
+    bytes -= (size_t)got;
+  }
+  return true;
+}
+
+bool write_all(int fd, const void *src, size_t bytes) {
+  const char *p = (const char *)src;
+  while (bytes) {
+    ssize_t put = ::write(fd, p, bytes < ((size_t)1 << 30) ? bytes : ((size_t)1 << 30));
+    if (put <= 0) return false;
+    p += put;
+    bytes -= (size_t)put;
+  }
+  return true;
+}
+} // namespace
+
+int read_csr_cached(const char *path, int base, int dtype, int64_t *m, int64_t *n, int64_t *nnz,
+                    int32_t **rp, int32_t **ci, void **val, int *cache_hit, std::string &err) {
+  if (!path || !m || !n || !nnz || !rp || !ci || !val || (dtype != HSPMV_F32 && dtype != HSPMV_F64))
+    return HSPMV_EINVAL;
+  if (cache_hit) *cache_hit = 0;
+  const std::string side = std::string(path) + ".hspmvbin";
+  const size_t vs = dtype == HSPMV_F64 ? 8 : 4;
+  int64_t tsize = 0, tmtime = 0;
+  if (!text_identity(path, tsize, tmtime)) {
+    err = std::string("cannot open ") + path + ": " + std::strerror(errno);
+    return HSPMV_EIO;
+  }
+  int fd = ::open(side.c_str(), O_RDONLY);
+  if (fd >= 0) {
+    BinHeader h;
+    bool ok = read_all(fd, &h, sizeof(h)) && !std::memcmp(h.magic, "HSPMVBIN", 8) && h.version == 1 &&
+              h.dtype == dtype && h.base == base && h.text_size == tsize && h.text_mtime_ns == tmtime &&
+              h.m >= 0 && h.nnz >= 0;
+    if (ok) {
+      *rp = (int32_t *)std::malloc(((size_t)h.m + 1) * 4);
+      *ci = (int32_t *)std::malloc(((size_t)h.nnz + 1) * 4);
+      *val = std::malloc(((size_t)h.nnz + 1) * vs);
+      ok = *rp && *ci && *val && read_all(fd, *rp, ((size_t)h.m + 1) * 4) &&
+           read_all(fd, *ci, (size_t)h.nnz * 4) && read_all(fd, *val, (size_t)h.nnz * vs);
+      if (ok) {
+        ::close(fd);
+        *m = h.m;
+        *n = h.n;
+        *nnz = h.nnz;
+        if (cache_hit) *cache_hit = 1;
+        return HSPMV_OK;
+      }
+      std::free(*rp); std::free(*ci); std::free(*val);
+      *rp = *ci = nullptr; *val = nullptr;
+    }
+    ::close(fd); // stale or damaged: fall through to the text
+  }
+  int rc = read_csr_text(path, base, dtype, m, n, nnz, rp, ci, val, err);
+  if (rc) return rc;
+  // best effort: a read-only directory just means no cache
+  const std::string tmp = side + ".tmp";
+  fd = ::open(tmp.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+  if (fd >= 0) {
+    BinHeader h;
+    std::memset(&h, 0, sizeof(h));
+    std::memcpy(h.magic, "HSPMVBIN", 8);
+    h.version = 1;
+    h.dtype = dtype;
+    h.base = base;
+    h.m = *m;
+    h.n = *n;
+    h.nnz = *nnz;
+    h.text_size = tsize;
+    h.text_mtime_ns = tmtime;
+    const bool ok = write_all(fd, &h, sizeof(h)) && write_all(fd, *rp, ((size_t)*m + 1) * 4) &&
+                    write_all(fd, *ci, (size_t)*nnz * 4) && write_all(fd, *val, (size_t)*nnz * vs);
+    ::close(fd);
+    if (!ok || ::rename(tmp.c_str(), side.c_str()) != 0) ::unlink(tmp.c_str());
+  }
+  return HSPMV_OK;
+}
+
 int write_csr_text(const char *path, int base, int dtype, int64_t m, int64_t n, int64_t nnz,
                    const int32_t *rp, const int32_t *ci, const void *val, std::string &err) {
   FILE *fp = std::fopen(path, "wb");

@@ -16,6 +16,7 @@ struct Options {
   int base = -1;       // --base 0|1 overrides the driver's native index base
   int algo = HSPMV_ALGO_AUTO;
   int k = 0;           // --k 2|3
+  bool cache = false;  // --cache: keep / use the binary side file <matrix>.hspmvbin
   std::vector<const char *> pos;
 };
 
@@ -24,6 +25,7 @@ inline Options parse(int argc, char **argv) {
   for (int i = 1; i < argc; ++i) {
     if (!std::strcmp(argv[i], "--fp32")) o.fp32 = true;
     else if (!std::strcmp(argv[i], "--fp64")) o.fp32 = false;
+    else if (!std::strcmp(argv[i], "--cache")) o.cache = true;
     else if (!std::strcmp(argv[i], "--base") && i + 1 < argc) o.base = std::atoi(argv[++i]);
     else if (!std::strcmp(argv[i], "--k") && i + 1 < argc) o.k = std::atoi(argv[++i]);
     else if (!std::strcmp(argv[i], "--algo") && i + 1 < argc) {
@@ -60,6 +62,15 @@ template <typename T> inline void test_spmv(const HostCsr &A, const T *x, T *y) 
     for (int64_t j = A.rp[r]; j < A.rp[r + 1]; ++j) acc += v[j] * x[A.ci[j]];
     y[r] = acc;
   }
+}
+
+// text reader of the drivers, optionally through the binary side file
+inline int read_matrix(const Options &o, const char *path, int base, HostCsr &H) {
+  if (!o.cache) return hspmv_read_csr_text(path, base, H.dtype, &H.m, &H.n, &H.nnz, &H.rp, &H.ci, &H.val);
+  int hit = 0;
+  int rc = hspmv_read_csr_cached(path, base, H.dtype, &H.m, &H.n, &H.nnz, &H.rp, &H.ci, &H.val, &hit);
+  if (!rc) std::printf("Matrix from %s\n", hit ? "the binary side file" : "text (side file written)");
+  return rc;
 }
 
 struct Times {

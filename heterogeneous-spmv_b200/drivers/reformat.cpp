@@ -20,7 +20,7 @@ int main(int argc, char **argv) {
   }
   HostCsr H;
   H.dtype = o.fp32 ? HSPMV_F32 : HSPMV_F64;
-  CHECK(hspmv_read_csr_text(o.pos[0], o.base < 0 ? 0 : o.base, H.dtype, &H.m, &H.n, &H.nnz, &H.rp, &H.ci, &H.val));
+  CHECK(read_matrix(o, o.pos[0], o.base < 0 ? 0 : o.base, H));
   int sizes[2] = {0, 0};
   int k = to_csr3 ? 3 : 2;
   if (to_csr3) {

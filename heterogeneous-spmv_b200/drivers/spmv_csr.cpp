@@ -28,7 +28,7 @@ int main(int argc, char **argv) {
   HostCsr H;
   H.dtype = o.fp32 ? HSPMV_F32 : HSPMV_F64;
   std::printf("Before Read\n");
-  CHECK(hspmv_read_csr_text(o.pos[0], o.base < 0 ? 0 : o.base, H.dtype, &H.m, &H.n, &H.nnz, &H.rp, &H.ci, &H.val));
+  CHECK(read_matrix(o, o.pos[0], o.base < 0 ? 0 : o.base, H));
   std::printf("After Read\n");
   const int N = std::atoi(o.pos[1]);
   int rc = o.fp32 ? run<float>(o, H, N) : run<double>(o, H, N);

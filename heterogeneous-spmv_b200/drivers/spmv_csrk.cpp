@@ -76,7 +76,7 @@ int main(int argc, char **argv) {
   }
   HostCsr H;
   H.dtype = o.fp32 ? HSPMV_F32 : HSPMV_F64;
-  CHECK(hspmv_read_csr_text(o.pos[0], o.base < 0 ? 1 : o.base, H.dtype, &H.m, &H.n, &H.nnz, &H.rp, &H.ci, &H.val));
+  CHECK(read_matrix(o, o.pos[0], o.base < 0 ? 1 : o.base, H));
   std::printf("size %d %d %d \n", (int)H.m, (int)H.n, (int)H.nnz);
   const int N = std::atoi(o.pos[1]);
   int sizes[2] = {0, 0}, k;

@@ -86,6 +86,14 @@ int64_t hspmv_launch_count(void);
  * announced counts are ignored, as in the reference readers. */
 int hspmv_read_csr_text(const char *path, int index_base, int dtype, int64_t *m, int64_t *n,
                         int64_t *nnz, int32_t **row_ptr, int32_t **col_idx, void **val);
+/* Same result as hspmv_read_csr_text, through a binary side file `<path>.hspmvbin` (64-byte header
+ * with the text file's size and mtime, then the three arrays): loaded with one read per array when
+ * it matches the text file, index base and dtype; otherwise the text is parsed and the side file
+ * (re)written, best effort.  *cache_hit (optional) tells which happened.  The reference harness
+ * re-parses the same text file on every run (run_scripts/run_cuda.py:84-92). */
+int hspmv_read_csr_cached(const char *path, int index_base, int dtype, int64_t *m, int64_t *n,
+                          int64_t *nnz, int32_t **row_ptr, int32_t **col_idx, void **val,
+                          int *cache_hit);
 /* Writes the layout of helpers/converter.m:42-48 (also reformat-csr-to-csr3/spmv.cpp:38-62). */
 int hspmv_write_csr_text(const char *path, int index_base, int dtype, int64_t m, int64_t n,
                          int64_t nnz, const int32_t *row_ptr, const int32_t *col_idx,

@@ -188,6 +188,35 @@ def test_parallel_parser_and_writer_on_a_multi_megabyte_file(tmp_path, hs, gen):
         hs.my_read_csr(str(tmp_path / "cut.csr"), index_base=1)
 
 
+def test_binary_side_file_cache(tmp_path, hs, gen):
+    """second and later reads of a text matrix come from <file>.hspmvbin; a changed text
+    file, another index base or another dtype invalidate it"""
+    rp, ci, v = gen.stencil27(9, mode="varied")
+    p = str(tmp_path / "c.mtx.rcm.csr")
+    hs.my_write_csr(p, rp, ci, v, index_base=1)
+    a = hs.my_read_csr(p, index_base=1, cache=True)
+    assert a[-1] is False and os.path.exists(p + ".hspmvbin")
+    b = hs.my_read_csr(p, index_base=1, cache=True)
+    assert b[-1] is True
+    for u, w in zip(a[:6], b[:6]):
+        assert np.array_equal(u, w)
+    assert np.array_equal(b[3], rp) and np.array_equal(b[4], ci) and np.array_equal(b[5], v)
+    assert hs.my_read_csr(p, index_base=1, dtype=np.float32, cache=True)[-1] is False      # other dtype: re-parsed, rewritten
+    assert hs.my_read_csr(p, index_base=1, dtype=np.float32, cache=True)[-1] is True
+    v2 = v.copy()
+    v2[0] += 1.0
+    hs.my_write_csr(p, rp, ci, v2, index_base=1)                                            # text changed (mtime/size)
+    os.utime(p, ns=(os.stat(p).st_atime_ns, os.stat(p).st_mtime_ns + 5_000_000))
+    c = hs.my_read_csr(p, index_base=1, dtype=np.float32, cache=True)
+    assert c[-1] is False and c[5][0] == np.float32(v2[0])
+    with open(p + ".hspmvbin", "r+b") as f:                                                 # damaged side file
+        f.truncate(100)
+    d = hs.my_read_csr(p, index_base=1, dtype=np.float32, cache=True)
+    assert d[-1] is False and np.array_equal(d[4], ci)
+    with pytest.raises(hs.HspmvError):
+        hs.my_read_csr(str(tmp_path / "missing.csr"), cache=True)
+
+
 def test_fixed_point_formatter_matches_printf(tmp_path, hs):
     """put_real6 (csrc/io.cpp) must print what fprintf("%f ") prints, ties and huge values included."""
     rng = np.random.default_rng(5)
