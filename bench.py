@@ -257,15 +257,38 @@ def run_ours(args, rank, world, local_rank):
             "auto": hs.ALGO_AUTO}[args.algo]
 
     # ---- this rank's block
-    row_lo = partition_stencil(g, world)
-    lo, hi = row_lo[rank], row_lo[rank + 1]
-    if world > 1:   # column window of this block = the part of x it needs (owned rows + halo)
-        probe = hs.Matrix.stencil(27, g, np.float64, 0, row_lo=lo, row_hi=hi)
-        cmin, cmax = probe.col_range()
-        probe.close()
+    fmt_k = {"csr": 1, "csr2": 2, "csr3": 3}[args.format]
+    if fmt_k == 1:
+        row_lo = partition_stencil(g, world)
+        lo, hi = row_lo[rank], row_lo[rank + 1]
+        if world > 1:   # column window of this block = the part of x it needs (owned rows + halo)
+            probe = hs.Matrix.stencil(27, g, np.float64, 0, row_lo=lo, row_hi=hi)
+            cmin, cmax = probe.col_range()
+            probe.close()
+        else:
+            cmin, cmax = 0, n - 1
+        A = hs.Matrix.stencil(27, g, np.float64, 0, row_lo=lo, row_hi=hi, col_shift=cmin, n_cols=cmax - cmin + 1)
     else:
-        cmin, cmax = 0, n - 1
-    A = hs.Matrix.stencil(27, g, np.float64, 0, row_lo=lo, row_hi=hi, col_shift=cmin, n_cols=cmax - cmin + 1)
+        # CSR-k: every rank builds the same Band-k-reordered matrix in its own HBM (22 GB, deterministic), the
+        # rows are cut nnz-balanced at super-(super-)row boundaries, and the rank keeps its shard
+        full = hs.Matrix.stencil(27, g, np.float64, 0)
+        sizes, _, _ = hs.auto_params(nnz_total, n, hs.ARCH_B200)
+        full.build_csrk(fmt_k, sizes)
+        maps = full.csrk()
+        align = maps["sr_ptr"] if fmt_k == 2 else maps["sr_ptr"][maps["ssr_ptr"]]
+        row_lo = [int(t) for t in hs.partition_rows(full.row_ptr(), world, align_ptr=align)]
+        del maps, align
+        lo, hi = row_lo[rank], row_lo[rank + 1]
+        if world > 1:
+            wide = full.slice_rows(lo, hi)
+            cmin, cmax = wide.col_range()
+            wide.close()
+            A = full.slice_rows(lo, hi, cmin, cmax - cmin + 1)
+            full.close()
+        else:
+            cmin, cmax = 0, n - 1
+            A = full
+        algo = hs.ALGO_CSRK
     info = A.info()
     m_loc, nnz_loc = info["m"], info["nnz"]
     # x lives in the handle's own cudaMalloc'ed vector so that neighbours can map it (CUDA IPC)
@@ -275,11 +298,15 @@ def run_ours(args, rank, world, local_rank):
     stream = torch.cuda.current_stream().cuda_stream
 
     def compute(a, b, x_ptr=None):
-        A.spmv_range(a, b, algo, d_x=x_ptr or x_local.data_ptr(), d_y=y_local.data_ptr(), stream=stream)
+        if fmt_k == 1:
+            A.spmv_range(a, b, algo, d_x=x_ptr or x_local.data_ptr(), d_y=y_local.data_ptr(), stream=stream)
+        else:   # the CSR-k kernel walks whole super-rows: the shard runs as one launch once its halo is in
+            assert (a, b) == (0, m_loc)
+            A.spmv(algo, d_x=x_ptr or x_local.data_ptr(), d_y=y_local.data_ptr(), stream=stream)
 
     if world > 1:
         ranges = hd.gather_col_ranges((cmin, cmax))
-        interior = A.interior_rows(lo - cmin, hi - cmin)
+        interior = A.interior_rows(lo - cmin, hi - cmin) if fmt_k == 1 else (0, 0)
         peer = fused = None
         x_bufs = [x_local]
         if args.exchange in ("peer", "peer-unfused"):
@@ -289,7 +316,7 @@ def run_ours(args, rank, world, local_rank):
             x2.copy_(x_local)
             x_bufs = [x_local, x2]
             peer = hd.PeerHalo(hs, [A.x_ptr(), x2_ptr], 8, row_lo, ranges, rank)
-            if args.exchange == "peer":
+            if args.exchange == "peer" and fmt_k == 1:
                 def fused(a, b, flags, n, step, timeout, x_ptr):
                     A.spmv_halo(a, b, d_x=x_ptr, d_y=y_local.data_ptr(), wait_flags=flags, n_wait=n,
                                 wait_step=step, timed_out=timeout, stream=stream)
@@ -405,9 +432,9 @@ def run_ours(args, rank, world, local_rank):
             "metric": "fp64 SpMV GFLOP/s", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": n_warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "stencil27_g%d_csr" % g, "n": n, "nnz": nnz_total, "format": "csr",
+            "config": {"workload": "stencil27_g%d_%s" % (g, args.format), "n": n, "nnz": nnz_total, "format": args.format,
                        "kernel": kernel_name, "partition": "nnz-balanced row blocks" if world > 1 else "single GPU",
-                       "halo_bytes_per_rank_per_step": halo_bytes, "overlap": world > 1 and not args.no_overlap,
+                       "halo_bytes_per_rank_per_step": halo_bytes, "overlap": world > 1 and not args.no_overlap and fmt_k == 1,
                        "exchange": ("none" if args.no_exchange else args.exchange) if world > 1 else "n/a",
                        "l2": "input (21.9 GB) >> L2 (126 MB): no flush needed",
                        "start": "host barrier + synchronize, then a stream-ordered all-reduce so all ranks' start "
@@ -422,7 +449,7 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms,
             "clocks": clocks,
         }
-        if world == 1 and not args.no_csrk:
+        if world == 1 and not args.no_csrk and fmt_k == 1:
             # the same matrix in the reference's own formats: Band-k (coarse graph + reorderA in HBM, RCM of the
             # coarse graph on the host), then the CSR-k kernel; 10 launches back to back after 3 warm-ups
             formats = {"csr": {"gflops": value, "ms": ms_step}}
@@ -466,6 +493,9 @@ def main():
     ap.add_argument("--g", type=int, default=G_DEFAULT, help="grid edge of the 27-point stencil (400 = BASELINE config 5)")
     ap.add_argument("--algo", default="stream", choices=["stream", "vector", "merge", "auto"])
     ap.add_argument("--cpu-rows", type=int, default=CPU_SAMPLE_ROWS)
+    ap.add_argument("--format", default="csr", choices=["csr", "csr2", "csr3"],
+                    help="csr (default, the headline), or the Band-k-reordered matrix as CSR-2 / CSR-3 (sharded at "
+                         "super-row / super-super-row boundaries when N > 1)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-csrk", action="store_true", help="skip the CSR-2 / CSR-3 timings of the same matrix (N = 1 only)")
     ap.add_argument("--no-overlap", action="store_true")

@@ -355,6 +355,18 @@ class Matrix:
         _check(lib().hspmv_download_csr(self.h, _p(rp), _p(ci), _p(v)))
         return rp, ci, v
 
+    def slice_rows(self, row_lo, row_hi, col_lo=0, n_cols=0):
+        """rows [row_lo,row_hi) as a new handle, columns [col_lo, col_lo+n_cols) relocated to 0 (n_cols=0: all)"""
+        out = C.c_void_p()
+        _check(lib().hspmv_slice_rows(self.h, C.c_int64(row_lo), C.c_int64(row_hi), C.c_int64(col_lo), C.c_int64(n_cols),
+                                      C.byref(out)))
+        return Matrix(out, self.dtype)
+
+    def row_ptr(self):
+        rp = np.zeros(self.info()["m"] + 1, np.int32)
+        _check(lib().hspmv_download_csr(self.h, _p(rp), None, None))
+        return rp
+
     def row_stats(self):
         out = np.zeros(10, np.int64)
         _check(lib().hspmv_row_stats(self.h, _p(out)))

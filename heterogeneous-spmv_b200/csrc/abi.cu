@@ -8,6 +8,7 @@
 #include "csrk_variants.h"
 #include "bandk_gpu.h"
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -1580,6 +1581,93 @@ int hspmv_block_col_range(const int32_t *row_ptr, const int32_t *col_idx, int64_
   int rc = hspmv::block_col_range(row_ptr, col_idx, row_lo, row_hi, col_min, col_max);
   return rc ? fail(rc, "block_col_range: bad arguments") : rc;
 }
+int hspmv_slice_rows(const hspmv_matrix *A, int64_t row_lo, int64_t row_hi, int64_t col_lo, int64_t n_cols,
+                     hspmv_matrix **out) {
+  if (!A || !out) return fail(HSPMV_EINVAL, "null");
+  if (row_lo < 0 || row_lo > row_hi || row_hi > A->m) return fail(HSPMV_EINVAL, "bad row range");
+  if (n_cols <= 0) {
+    col_lo = 0;
+    n_cols = A->n;
+  }
+  if (col_lo < 0 || col_lo + n_cols > A->n) return fail(HSPMV_EINVAL, "bad column window");
+  // CSR-k: the cut must not split a super-row (k = 2) / super-super-row (k = 3)
+  int64_t s0 = 0, s1 = 0, t0 = 0, t1 = 0;
+  if (A->k >= 2) {
+    auto find = [](const std::vector<u32> &v, int64_t x) -> int64_t {
+      auto it = std::lower_bound(v.begin(), v.end(), (u32)x);
+      return (it != v.end() && *it == (u32)x) ? (int64_t)(it - v.begin()) : -1;
+    };
+    s0 = find(A->h_sr, row_lo);
+    s1 = find(A->h_sr, row_hi);
+    if (s0 < 0 || s1 < 0) return fail(HSPMV_EINVAL, "slice bounds are not super-row boundaries");
+    if (A->k == 3) {
+      t0 = find(A->h_ssr, s0);
+      t1 = find(A->h_ssr, s1);
+      if (t0 < 0 || t1 < 0) return fail(HSPMV_EINVAL, "slice bounds are not super-super-row boundaries");
+    }
+  }
+  int e[2] = {0, 0};
+  CU(cudaMemcpy(&e[0], A->d_rp + row_lo, 4, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(&e[1], A->d_rp + row_hi, 4, cudaMemcpyDeviceToHost));
+  hspmv_matrix *B = nullptr;
+  int rc = new_handle(&B, A->dtype, row_hi - row_lo, n_cols, (int64_t)e[1] - e[0]);
+  if (rc) return rc;
+  if ((rc = alloc_matrix_arrays(B)) || (rc = alloc_vectors(B))) {
+    hspmv_destroy(B);
+    return rc;
+  }
+  int *d_bad = nullptr;
+  cudaError_t ce = cudaMalloc(&d_bad, 4);
+  if (ce == cudaSuccess) ce = cudaMemsetAsync(d_bad, 0, 4, B->stream);
+  if (ce == cudaSuccess) {
+    hspmv::rebase_kernel<<<grid_for(B->m + 1, 256, B->dev.sms * 16), 256, 0, B->stream>>>(B->m + 1, A->d_rp + row_lo, e[0], e[1] - e[0] + 1,
+                                                                                     B->d_rp, d_bad);
+    LAUNCHED();
+    if (B->nnz) {
+      hspmv::rebase_kernel<<<grid_for(B->nnz, 256, B->dev.sms * 16), 256, 0, B->stream>>>(B->nnz, A->d_ci + e[0], (int)col_lo, (int)n_cols,
+                                                                                     B->d_ci, d_bad);
+      LAUNCHED();
+      ce = cudaMemcpyAsync(B->d_val, (const char *)A->d_val + (size_t)e[0] * A->vsize(), (size_t)B->nnz * A->vsize(),
+                           cudaMemcpyDeviceToDevice, B->stream);
+    }
+  }
+  int bad = 0;
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, B->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(B->stream);
+  cudaFree(d_bad);
+  if (ce != cudaSuccess || bad) {
+    hspmv_destroy(B);
+    if (bad) return fail(HSPMV_EINVAL, "the row block references a column outside the window");
+    return fail(HSPMV_ECUDA, std::string("slice_rows: ") + cudaGetErrorString(ce));
+  }
+  B->h_rp.resize((size_t)B->m + 1);
+  ce = cudaMemcpy(B->h_rp.data(), B->d_rp, (size_t)(B->m + 1) * 4, cudaMemcpyDeviceToHost);
+  if (ce != cudaSuccess) {
+    hspmv_destroy(B);
+    return fail(HSPMV_ECUDA, std::string("slice_rows: ") + cudaGetErrorString(ce));
+  }
+  hspmv::row_stats(B->m, B->h_rp.data(), B->stats);
+  B->stats_ready = true;
+  if (A->k >= 2) {
+    B->k = A->k;
+    B->h_sr.resize((size_t)(s1 - s0) + 1);
+    for (int64_t i = s0; i <= s1; ++i) B->h_sr[(size_t)(i - s0)] = A->h_sr[(size_t)i] - (u32)row_lo;
+    B->n_sr = s1 - s0;
+    if (A->k == 3) {
+      B->h_ssr.resize((size_t)(t1 - t0) + 1);
+      for (int64_t i = t0; i <= t1; ++i) B->h_ssr[(size_t)(i - t0)] = A->h_ssr[(size_t)i] - (u32)s0;
+      B->n_ssr = t1 - t0;
+    }
+    if (B->n_sr > 0 && (rc = upload_csrk_maps(B))) {
+      hspmv_destroy(B);
+      return rc;
+    }
+    if (B->n_sr == 0) B->k = 1; // an empty slice has no super-rows to walk
+  }
+  *out = B;
+  return HSPMV_OK;
+}
+
 int hspmv_col_range_device(const hspmv_matrix *A, int64_t *col_min, int64_t *col_max) {
   if (!A || !col_min || !col_max) return fail(HSPMV_EINVAL, "null");
   int *d = nullptr;

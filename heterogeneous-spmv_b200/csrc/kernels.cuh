@@ -705,6 +705,16 @@ static __global__ void sr_offsets_kernel(int64_t n_sr, const uint32_t *__restric
     sr_e[i] = (uint32_t)rp[sr_ptr[i]];
 }
 
+// hspmv_slice_rows: dst[i] = src[i] - sub; *bad is raised when a result leaves [0, limit)
+static __global__ void rebase_kernel(int64_t n, const int *__restrict__ src, int sub, int limit, int *__restrict__ dst,
+                                     int *__restrict__ bad) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int t = src[i] - sub;
+    dst[i] = t;
+    if (t < 0 || t >= limit) *bad = 1;
+  }
+}
+
 // Rows whose columns all lie in [own_lo, own_hi) are "interior" (need no halo).  Reports the last
 // non-interior row of the first half (+1) and the first non-interior row of the second half, so
 // that [row_a, row_b) is a contiguous all-interior range.  One warp per row.

@@ -255,6 +255,15 @@ int hspmv_block_col_range(const int32_t *row_ptr, const int32_t *col_idx, int64_
 int hspmv_col_range_device(const hspmv_matrix *A, int64_t *col_min, int64_t *col_max);
 
 
+/* New handle with rows [row_lo,row_hi) of A, copied inside HBM; columns [col_lo, col_lo + n_cols)
+ * become [0, n_cols) (n_cols <= 0: keep all columns, col_lo = 0).  HSPMV_EINVAL if the block
+ * references a column outside the window.  For a CSR-k handle the bounds must be super-row
+ * boundaries (k = 2) / super-super-row boundaries (k = 3) -- what hspmv_partition_rows returns with
+ * align_ptr -- and the slice is again CSR-k, with sr_ptr / ssr_ptr rebased; x and y of a slice are
+ * in A's (reordered) numbering, there is no permutation attached.  This is how one rank's shard of
+ * a Band-k-reordered matrix is cut out. */
+int hspmv_slice_rows(const hspmv_matrix *A, int64_t row_lo, int64_t row_hi, int64_t col_lo, int64_t n_cols,
+                     hspmv_matrix **out);
 /* Contiguous range [row_a,row_b) of rows whose column indices all lie in [own_col_lo,own_col_hi)
  * (local column ids): row_a = 1 + last row of the first half that references a column outside,
  * row_b = first such row of the second half.  Rows outside the range wait for the x halo. */

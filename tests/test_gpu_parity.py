@@ -357,6 +357,55 @@ def test_device_generators_match_numpy(dtype, hs, gen):
     assert_within_bound(B.get_y(), y_ref, sc, dtype, "row block")
 
 
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_slice_rows_shards_of_a_csrk_matrix(k, hs, oracle, gen):
+    """a rank's shard of a Band-k-reordered matrix = rows between super-(super-)row boundaries
+    (hspmv_partition_rows with align_ptr), cut out in HBM with its column window; the shards' products,
+    concatenated, equal the whole matrix's"""
+    rp, ci, v = gen.stencil27(22, mode="varied")
+    n = len(rp) - 1
+    x = gen.vector_x(n)
+    A = hs.Matrix.from_csr(rp, ci, v)
+    align = None
+    if k > 1:
+        A.build_csrk(k, [12, 5])
+        c = A.csrk()
+        align = c["sr_ptr"] if k == 2 else c["sr_ptr"][c["ssr_ptr"]]
+    A.set_x(x)                     # permuted inside for k > 1
+    A.spmv(hs.ALGO_AUTO)
+    y_full = A.get_y(original_order=False)
+    xp = x[A.csrk()["perm"]] if k > 1 else x
+    rp_dev = A.row_ptr()
+    parts = 3
+    row_lo = hs.partition_rows(rp_dev, parts, align_ptr=align)
+    assert row_lo[0] == 0 and row_lo[-1] == n
+    if align is not None:
+        assert np.all(np.isin(row_lo, align))
+    got = []
+    for q in range(parts):
+        lo, hi = int(row_lo[q]), int(row_lo[q + 1])
+        wide = A.slice_rows(lo, hi)
+        cmin, cmax = wide.col_range()
+        wide.close()
+        B = A.slice_rows(lo, hi, cmin, cmax - cmin + 1)
+        i = B.info()
+        assert i["m"] == hi - lo and i["n"] == cmax - cmin + 1 and i["k"] == (k if hi > lo else 1)
+        assert np.array_equal(B.row_ptr(), rp_dev[lo:hi + 1] - rp_dev[lo])
+        B.set_x(xp[cmin:cmax + 1])
+        B.set_y(np.full(hi - lo, np.nan))
+        B.spmv(hs.ALGO_AUTO)
+        assert ("k=%d" % k) in B.last_kernel()
+        got.append(B.get_y(original_order=False))
+        if cmax - cmin + 1 > 3:
+            with pytest.raises(hs.HspmvError):
+                A.slice_rows(lo, hi, cmin + 1, cmax - cmin)       # window too narrow
+        B.close()
+    assert np.array_equal(np.concatenate(got), y_full)
+    if k > 1:
+        with pytest.raises(hs.HspmvError):
+            A.slice_rows(int(align[1]) - 1 if align[1] > 1 else 1, n)   # not a super-row boundary
+
+
 def test_merge_tile_table_device_equals_host(hs, gen):
     rp, ci, v = gen.rmat(12, 8)
     A = hs.Matrix.from_csr(rp, ci, v)
