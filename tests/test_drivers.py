@@ -68,6 +68,13 @@ def test_drivers_on_gpu(tmp_path, gen):
         for auto in ("volta", "ampere", "b200"):
             r = subprocess.run([os.path.join(BIN, "cuda-spmv-csrk", "cuda", "spmv-auto-" + auto), f1, "3"] + extra, capture_output=True, text=True)
             assert scrape(r.stdout)["wrong"] == 0 and "using ssrs" in r.stdout
+            assert ("Tuned: csrk_tma" in r.stdout) == (auto == "b200")     # the B200 flavour measures, the others use formulas
+    # --cache: the second run of the harness on the same file loads the binary side file
+    exe = os.path.join(BIN, "cuda-spmv-csr", "spmv.exe")
+    r1 = subprocess.run([exe, f0, "2", "--cache"], capture_output=True, text=True)
+    r2 = subprocess.run([exe, f0, "2", "--cache"], capture_output=True, text=True)
+    assert "Matrix from text" in r1.stdout and "Matrix from the binary side file" in r2.stdout
+    assert scrape(r1.stdout)["wrong"] == 0 and scrape(r2.stdout)["wrong"] == 0 and os.path.exists(f0 + ".hspmvbin")
     # a 0-based file fed to the 1-based reader is rejected, not mis-read silently
     r = subprocess.run([os.path.join(BIN, "cuda-spmv-csrk", "cuda", "spmv"), f0, "2", "16"], capture_output=True, text=True)
     assert "Error" in r.stdout
