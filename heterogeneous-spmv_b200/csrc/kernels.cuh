@@ -658,15 +658,8 @@ __global__ void __launch_bounds__(512, 1) csrk_tma_kernel(const CsrkParams<T> p)
         T xv[NS];
 #pragma unroll
         for (int u = 0; u < NS; ++u) xv[u] = __ldg(p.x + c[u]);
-        T acc_odd = 0; // two chains: the FMAs of a lane are otherwise one dependent chain of NS
 #pragma unroll
-        for (int u = 0; u < NS; ++u) {
-          if (u & 1)
-            acc_odd += v[u] * xv[u];
-          else
-            acc += v[u] * xv[u];
-        }
-        acc += acc_odd;
+        for (int u = 0; u < NS; ++u) acc += v[u] * xv[u]; // same order as csrk_rows: a row's sum does not depend on the tiling
         if (re <= rs) acc = (T)0; // empty row: its idle slots multiplied 0 by x[0], which may be inf
         acc = group_sum<T, VEC>(acc);
         if (active && sub == 0) p.y[r] = acc;
