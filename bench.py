@@ -396,6 +396,23 @@ def run_ours(args, rank, world, local_rank):
     y_host = torch.empty(m_loc, dtype=torch.float64).pin_memory()
     e2e_steps = max(3, min(args.steps, 10))
     A.spmv_host_ptr(x_host.data_ptr(), y_host.data_ptr(), algo)          # warm-up (first touch of the pinned pages)
+    e2e_mode = "pipelined"
+    if world > 1:
+        # All ranks copy through one host: whether overlapping the two PCIe directions (pipelined call) beats
+        # strictly sequential copies depends on how much bandwidth the host side has left at this N (measured on
+        # this pool: pipelined wins at N = 2, loses at N = 4).  Two untimed-for-the-record calls of each mode,
+        # max over ranks, pick one mode for everybody, then measure.
+        trial = []
+        for mode in (0, 1):
+            A.set_option(hs.OPT_NO_PIPELINE, mode)
+            A.spmv_host_ptr(x_host.data_ptr(), y_host.data_ptr(), algo)
+            barrier()
+            trial.append(A.spmv_host_timed(x_host.data_ptr(), y_host.data_ptr(), 2, algo))
+        t = torch.tensor(trial, dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sequential = bool(t[1] < t[0])
+        A.set_option(hs.OPT_NO_PIPELINE, 1 if sequential else 0)
+        e2e_mode = "sequential" if sequential else "pipelined"
     barrier()
     rendezvous()
     torch.cuda.synchronize()
@@ -444,7 +461,9 @@ def run_ours(args, rank, world, local_rank):
                          "frac_of_nominal_8TBs": achieved / 8000.0,
                          "algorithmic_bytes_per_launch": b_launch},
             "e2e": {"value": e2e_value, "unit": "GFLOP/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": n * 8,
-                    "call": "hspmv_spmv_host (pipelined H2D / row-chunk kernels / D2H) on every rank's window of x",
+                    "call": "hspmv_spmv_host on every rank's window of x (%s: %s)" % (
+                        e2e_mode, "H2D pieces / row-chunk kernels / D2H chunks overlapped" if e2e_mode == "pipelined"
+                        else "H2D, kernel, D2H in sequence -- faster than the overlapped form at this N on this host"),
                     "steps": e2e_steps, "checksum": chk},
             "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms,
             "clocks": clocks,
