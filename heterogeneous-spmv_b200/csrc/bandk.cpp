@@ -21,6 +21,9 @@
 #include "host_index.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <utility>
 #include <vector>
@@ -34,6 +37,20 @@ namespace hspmv {
 namespace {
 
 typedef CoarseGraph Coarse;
+
+// HSPMV_BANDK_TRACE=1 prints the wall time of every phase of the build to stderr
+struct Phase {
+  const char *name;
+  std::chrono::steady_clock::time_point t0;
+  bool on;
+  explicit Phase(const char *n) : name(n), t0(std::chrono::steady_clock::now()), on(std::getenv("HSPMV_BANDK_TRACE") != nullptr) {}
+  ~Phase() {
+    if (on) {
+      std::chrono::duration<double> d = std::chrono::steady_clock::now() - t0;
+      std::fprintf(stderr, "[bandk] %-28s %8.3f s\n", name, d.count());
+    }
+  }
+};
 
 // Greedy contiguous grouping (csrk.cpp:1278-1292): a group is closed by the vertex that makes
 // the running nnz reach the threshold; the next vertex opens a new group.
@@ -332,13 +349,21 @@ static int bandk_levels(int64_t n, int64_t nnz, const u32 *rp, const u32 *adj, i
     } else {
       const u32 T = bandk_threshold(sizes[lvl - 1], cur_nnz, cur_n);
       std::vector<u32> grp;
-      group_rows(cur_rp, cur_n, T, maps[(size_t)lvl], grp);
+      {
+        Phase ph("group rows");
+        group_rows(cur_rp, cur_n, T, maps[(size_t)lvl], grp);
+      }
+      Phase ph("coarse graph (host)");
       int rc = build_coarse(cur_rp, cur_adj, maps[(size_t)lvl], grp, level[lvl]);
       if (rc) return rc;
     }
     std::vector<u32> o2n;
-    rcm_order(level[lvl], perms[(size_t)lvl], o2n);
+    {
+      Phase ph("RCM of the coarse graph");
+      rcm_order(level[lvl], perms[(size_t)lvl], o2n);
+    }
     if (lvl + 1 < k) { // the next level coarsens the renumbered graph
+      Phase ph("relabel");
       relabel(level[lvl], perms[(size_t)lvl], o2n);
       cur_rp = level[lvl].rp.data();
       cur_adj = level[lvl].adj.data();
@@ -348,6 +373,7 @@ static int bandk_levels(int64_t n, int64_t nnz, const u32 *rp, const u32 *adj, i
   }
 
   // level-(k-1) ... level-1: rewrite the maps, compose down to rows (csrk.cpp:1015-1034)
+  Phase ph("uncoarsen");
   if (k == 3) expand_level(maps[2], perms[2], perms[1]);
   perms[0].resize((size_t)n);
 #pragma omp parallel for schedule(static)
