@@ -30,6 +30,8 @@ CASES = {
     "st27_12_k3": ("stencil27", {"g": 12}, 3, [20, 10]),
     "shell4k_k3": ("banded_shell", {"n": 4000, "band": 120}, 3, [9, 12]),
     "shell4k_k2": ("banded_shell", {"n": 4000, "band": 120}, 2, [24]),
+    "blocks3k_k2": ("shell_blocks", {"n": 3000, "node_band": 60}, 2, [16]),       # config-3 stand-in: 5-dof node blocks
+    "blocks3k_k3": ("shell_blocks", {"n": 3000, "node_band": 60}, 3, [12, 6]),
 }
 
 
@@ -40,7 +42,10 @@ def crc(a):
 def main():
     assert O.have_ref(), "oracle/_ref is missing: make -C oracle ref"
     out_dir = os.path.dirname(os.path.abspath(__file__))
+    only = set(sys.argv[1:])          # python make_golden.py [case ...]: regenerate just those
     for name, (gen, kw, k, sizes) in CASES.items():
+        if only and name not in only:
+            continue
         rec = {"k": np.int32(k), "sizes": np.array(sizes, np.int32)}
         for dt, tag in ((np.float32, "f32"), (np.float64, "f64")):
             rp, ci, v = getattr(G, gen)(dtype=dt, **kw)
