@@ -188,6 +188,48 @@ def test_parallel_parser_and_writer_on_a_multi_megabyte_file(tmp_path, hs, gen):
         hs.my_read_csr(str(tmp_path / "cut.csr"), index_base=1)
 
 
+def test_reader_accepts_any_whitespace_layout(tmp_path, hs, gen):
+    """the reference readers are fscanf("%d ") loops: any mix of blanks, tabs, CR/LF and blank lines between
+    tokens is the same file; tokens beyond the announced counts are ignored"""
+    rng = np.random.default_rng(99)
+    seps = [" ", "  ", "\t", "\n", "\r\n", " \n ", "\n\n", "\t \t"]
+    for trial in range(25):
+        rp, ci, v = gen.random_ragged(int(rng.integers(1, 60)), max_len=int(rng.integers(1, 12)), seed=int(rng.integers(1 << 30)))
+        n = len(rp) - 1
+        v = np.round(v * rng.choice([1.0, 1e3, 1e-3]), 6)
+        base = int(rng.integers(0, 2))
+        toks = [str(n), str(n), str(len(ci))] + [str(t + base) for t in rp] + [str(t + base) for t in ci]
+        toks += [rng.choice(["%f", "%.6f", "%g", "%.3e", "%r"]) % float(t) for t in v]
+        text = rng.choice(["", "\n", "  "]) + "".join(t + rng.choice(seps) for t in toks)
+        if trial % 3 == 0:
+            text += " 7 8 9 trailing junk is never reached"
+        p = str(tmp_path / ("w%d.csr" % trial))
+        with open(p, "w", newline="") as f:
+            f.write(text)
+        m2, n2, nnz2, r, c, w = hs.my_read_csr(p, index_base=base)
+        assert (m2, n2, nnz2) == (n, n, len(ci)) and np.array_equal(r, rp) and np.array_equal(c, ci)
+        want = np.array([float(t) for t in toks[3 + n + 1 + len(ci):]])
+        assert np.array_equal(w, want), trial
+
+
+@pytest.mark.parametrize("parts", [1, 2, 5, 16])
+def test_partition_rule_on_random_row_pointers(parts, hs):
+    rng = np.random.default_rng(parts)
+    for _ in range(30):
+        m = int(rng.integers(1, 400))
+        lens = rng.integers(0, 30, m) * (rng.random(m) < 0.8)
+        if rng.random() < 0.3:
+            lens[int(rng.integers(0, m))] = 5000                       # one dominant row
+        rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+        got = hs.partition_rows(rp, parts)
+        assert np.array_equal(got, PO.partition_rows(rp, parts))
+        assert got[0] == 0 and got[-1] == m and np.all(np.diff(got) >= 0)
+        step = int(rng.integers(1, 9))
+        align = np.unique(np.concatenate([np.arange(0, m, step), [m]])).astype(np.uint32)
+        got = hs.partition_rows(rp, parts, align_ptr=align)
+        assert np.array_equal(got, PO.partition_rows(rp, parts, align)) and np.all(np.isin(got, align))
+
+
 def test_binary_side_file_cache(tmp_path, hs, gen):
     """second and later reads of a text matrix come from <file>.hspmvbin; a changed text
     file, another index base or another dtype invalidate it"""
