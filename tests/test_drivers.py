@@ -2,6 +2,7 @@
 import os
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -48,6 +49,36 @@ def test_usage_lines_match_the_reference():
     assert r.returncode == 0 and "inputfile num_runs super_super_row_size super_row_size" in r.stdout
     r = subprocess.run([os.path.join(BIN, "cuda-spmv-csrk", "cuda", "spmv-auto-ampere"), "x"], capture_output=True, text=True)
     assert r.returncode == 0 and "inputfile num_runs" in r.stdout
+
+
+def test_run_scripts_compatible_runner_records(tmp_path):
+    """heterogeneous-spmv_b200/run_scripts/run_b200.py scrapes and records like run_scripts/run_cuda.py:110-125 and
+    run_tuning.py:125; a stand-in driver that prints the protocol lets this run without a GPU"""
+    fake_bin = tmp_path / "bin"
+    for sub, name in (("cuda-spmv-csr", "spmv.exe"), ("cuda-spmv-csrk/cuda", "spmv-auto-b200"), ("cuda-spmv-csrk/cuda", "spmv")):
+        d = fake_bin / sub
+        d.mkdir(parents=True, exist_ok=True)
+        exe = d / name
+        exe.write_text("#!/bin/sh\necho \"banner $@\"\necho \"TimeMin: 1.5e-04\"\necho \"TimeMax: 3e-04\"\necho \"TimeAvg: 2e-04\"\necho \"Number Wrong: 0 \"\n")
+        exe.chmod(0o755)
+    mats = tmp_path / "mats"
+    mats.mkdir()
+    for n in ("b.mtx.rcm.csr", "a.mtx.rcm.csr", "a.mtx.rcm.csr.hspmvbin"):
+        (mats / n).write_text("1 1 1\n")
+    runner = os.path.join(ROOT, "heterogeneous-spmv_b200", "run_scripts", "run_b200.py")
+    rec = tmp_path / "rec.csv"
+    common = [sys.executable, runner, "--matrices", str(mats), "--bin", str(fake_bin), "--record", str(rec), "--out", str(tmp_path / "runs"),
+              "--threads", "16", "--runs", "7"]
+    for kernel, extra in (("cuda-spmv-csr", []), ("cuda-spmv-csrk", ["--extra", "--fp32 --cache"]), ("tuning", ["--sizes", "16,24"])):
+        r = subprocess.run(common + ["--kernel", kernel] + extra, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    lines = rec.read_text().splitlines()
+    assert lines[0] == "cuda-spmv-csr, a.mtx.rcm.csr, cuda, 1, 16,  1.5e-04,  3e-04,  2e-04, "          # run_cuda.py:125
+    assert lines[1].startswith("cuda-spmv-csr, b.mtx.rcm.csr") and lines[2].startswith("cuda-spmv-csrk, a.mtx.rcm.csr")
+    assert lines[4] == "cuda-spmv-csrk/cuda, a.mtx.rcm.csr, cuda, 1, 16, (16),  1.5e-04,  3e-04,  2e-04, "  # run_tuning.py:125
+    assert len(lines) == 2 + 2 + 4 and not any("hspmvbin" in t for t in lines)
+    out = (tmp_path / "runs" / "cuda-spmv-csrk" / "a.mtx.rcm.csr_cuda_1_16.txt").read_text()
+    assert "a.mtx.rcm.csr 7 --fp32 --cache" in out
 
 
 @pytest.mark.gpu
