@@ -230,6 +230,35 @@ def test_partition_rule_on_random_row_pointers(parts, hs):
         assert np.array_equal(got, PO.partition_rows(rp, parts, align)) and np.all(np.isin(got, align))
 
 
+def test_halo_plan_on_random_partitions():
+    """dist.halo_plan against the independent restatement, plus its two global properties: what r receives
+    from q is exactly what q sends to r, and the received pieces tile the part of r's window it does not own"""
+    import importlib
+    hd = importlib.import_module("heterogeneous_spmv_b200.dist")
+    rng = np.random.default_rng(4)
+    for _ in range(200):
+        P = int(rng.integers(1, 9))
+        n = int(rng.integers(P, 500))
+        cuts = np.sort(rng.choice(np.arange(1, n), size=P - 1, replace=False)) if P > 1 else np.zeros(0, np.int64)
+        row_lo = [0] + [int(c) for c in cuts] + [n]
+        ranges = []
+        for r in range(P):
+            lo, hi = row_lo[r], row_lo[r + 1]
+            reach = int(rng.integers(0, n))                           # band, or everything (power-law)
+            ranges.append((max(0, lo - reach), min(n - 1, hi - 1 + reach)))
+        plans = [hd.halo_plan(row_lo, ranges, r) for r in range(P)]
+        for r in range(P):
+            assert plans[r] == PO.halo_plan(row_lo, ranges, r)
+            recv, send = plans[r]
+            for q, a, b in recv:
+                assert (r, a, b) in plans[q][1]                       # q sends exactly that piece to r
+            got = sorted((a, b) for _, a, b in recv)
+            cmin, cmax = ranges[r]
+            want = [(a, b) for a, b in ((cmin, row_lo[r]), (row_lo[r + 1], cmax + 1)) if a < b]
+            flat = [i for a, b in got for i in range(a, b)]
+            assert flat == [i for a, b in want for i in range(a, b)]
+
+
 def test_binary_side_file_cache(tmp_path, hs, gen):
     """second and later reads of a text matrix come from <file>.hspmvbin; a changed text
     file, another index base or another dtype invalidate it"""
