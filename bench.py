@@ -229,6 +229,55 @@ def run_reference(args, rank):
     }), flush=True)
 
 
+def config2_cpu_reference(g2=100, sizes=(8, 16, 32, 64)):
+    """BASELINE configs[1], CPU side: the compiled reference's CSRk_Graph::SpMV k = 2 (spmv-csrk/csrk.cpp:165-223) on
+    the 27-point g2^3 stencil, best over a few super-row sizes, all host threads; None without oracle/_ref."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    if not O.have_ref():
+        return None
+    from heterogeneous_spmv_b200 import generators as G
+    cores = cpu_setup_threads()
+    rp, ci, v = G.stencil27(g2)
+    x = G.vector_x(len(rp) - 1, np.float64)
+    O.ref("csrk", np.float64)
+    _force_omp_threads()
+    best = None
+    for s in sizes:
+        R = O.RefCSRk(rp, ci, v, 2, [s])
+        t, _ = R.spmv_timed(x, 5, 20)
+        R.close()
+        if best is None or t < best[0]:
+            best = (t, s)
+    return {"gflops": 2.0 * len(ci) / best[0] / 1e9, "ms": best[0] * 1e3, "sizes": [best[1]], "cores": cores,
+            "kind": "reference", "sizes_tried": list(sizes)}
+
+
+def config2_line(hs, np, no_cpu):
+    """BASELINE configs[1]: CSR-k k = 2 on the 27-point 100^3 stencil with a tuned super-row size on one B200 (Band-k
+    built in HBM, kernel shape autotuned, 20 launches back to back), beside the reference's OpenMP spmv-csrk."""
+    g2 = 100
+    n2, nnz2 = g2 ** 3, (3 * g2 - 2) ** 3
+    best = None
+    for s in (8, 16, 32):
+        B = hs.Matrix.stencil(27, g2, np.float64, 0)
+        B.build_csrk(2, [s])
+        B.fill_x_synthetic(0)
+        B.autotune(hs.ALGO_CSRK, 1)
+        t = B.spmv_timed_batch(hs.ALGO_CSRK, warmup=5, iters=20)
+        i = B.info()
+        if best is None or t < best["ms"]:
+            best = {"ms": t, "sizes": [s], "n_sr": i["n_sr"], "kernel": B.last_kernel()}
+        B.close()
+    best["gflops"] = 2.0 * nnz2 / (best["ms"] * 1e-3) / 1e9
+    best["gbs"] = (nnz2 * 12 + (n2 + 1) * 4 + 2 * n2 * 8 + (best["n_sr"] + 1) * 4) / (best["ms"] * 1e-3) / 1e9
+    out = {"workload": "stencil27_g100_csr2", "n": n2, "nnz": nnz2, "ours": best}
+    if not no_cpu:
+        out["cpu_reference"] = config2_cpu_reference(g2)
+    return out
+
+
 # ----------------------------------------------------------------------------- our arm
 def run_ours(args, rank, world, local_rank):
     import numpy as np
@@ -487,6 +536,10 @@ def run_ours(args, rank, world, local_rank):
                                         "kernel": B.last_kernel()}
                 B.close()
             line["formats"] = formats
+            try:    # an extra, never the reason for a missing bench line
+                line["config2"] = config2_line(hs, np, args.no_cpu)
+            except Exception as e:      # noqa: BLE001
+                line["config2"] = {"error": "%s: %s" % (type(e).__name__, e)}
         if world == 1 and not args.no_cpu:
             cores = cpu_setup_threads()
             t, nnz_s, kind = cpu_time_sample(g, args.cpu_rows, 5, 20)
