@@ -67,6 +67,42 @@ def test_bandk_host_bit_exact(case, hs, oracle, gen):
             assert np.array_equal(p, q)
 
 
+def test_bandk_random_symmetric_graphs_against_oracle_and_reference(hs, oracle):
+    """60 random structurally symmetric matrices with a diagonal (disconnected pieces, hubs, many equal
+    multiplicities -> RCM tie order): product builder == oracle restatement == the compiled reference."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(2024)
+    for trial in range(60):
+        n = int(rng.integers(2, 400))
+        density = float(rng.choice([0.002, 0.01, 0.05, 0.2]))
+        a = sp.random(n, n, density=density, random_state=int(rng.integers(1 << 30)), format="csr")
+        if trial % 5 == 0:                                   # a hub row/column
+            h = int(rng.integers(0, n))
+            a = a.tolil()
+            a[h, rng.choice(n, size=max(1, n // 3), replace=False)] = 1.0
+            a = a.tocsr()
+        if trial % 7 == 0:                                   # two blocks that never touch
+            half = n // 2
+            a = sp.block_diag([a[:half, :half], a[half:, half:]], format="csr")
+        a = (a + a.T + sp.identity(n)).tocsr()
+        a.sort_indices()
+        rp, ci = a.indptr.astype(np.int32), a.indices.astype(np.int32)
+        k = int(rng.integers(2, 4))
+        sizes = [int(rng.integers(1, 12)), int(rng.integers(1, 8))][: k - 1]
+        got = hs.bandk_host(rp, ci, k, sizes)
+        want = oracle.bandk_build(rp, ci, k, sizes)
+        for key in want:
+            assert np.array_equal(got[key], want[key]), (trial, key, n, k, sizes)
+        if oracle.have_ref() and trial % 4 == 0:
+            R = oracle.RefCSRk(rp, ci, np.ones(len(ci), np.float32), k, sizes)
+            maps = R.maps()
+            perm = R.matrix()[0]
+            R.close()
+            assert np.array_equal(perm, got["perm"]) and np.array_equal(maps[0], got["sr_ptr"]), (trial, "reference")
+            if k == 3:
+                assert np.array_equal(maps[1], got["ssr_ptr"]), (trial, "reference ssr")
+
+
 def test_bandk_golden_vectors(hs, gen):
     import importlib.util
     gold = os.path.join(os.path.dirname(__file__), "golden")
