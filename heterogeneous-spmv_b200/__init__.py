@@ -288,6 +288,15 @@ def stream_write(stream, addr, value):
     _check(lib().hspmv_stream_write(C.c_void_p(stream), C.c_void_p(addr), int(value)))
 
 
+def fill_x_segments(d_x, dtype, segments, global_offset, scale, stream=None):
+    """x_i = vector_x(global_offset + i) * scale on up to 8 ranges [(lo, hi), ...] of a device vector, one launch."""
+    segs = [(int(a), int(b)) for a, b in segments]
+    lo = (C.c_int64 * max(len(segs), 1))(*[a for a, _ in segs])
+    hi = (C.c_int64 * max(len(segs), 1))(*[b for _, b in segs])
+    _check(lib().hspmv_fill_x_segments(C.c_void_p(d_x), _dt(dtype), len(segs), lo, hi, C.c_int64(global_offset),
+                                       C.c_double(scale), C.c_void_p(stream)))
+
+
 def stream_wait_ge(stream, addr, value):
     _check(lib().hspmv_stream_wait_ge(C.c_void_p(stream), C.c_void_p(addr), int(value)))
 
@@ -494,6 +503,116 @@ class Matrix:
             self.close()
         except Exception:
             pass
+
+
+class MultiGPU:
+    """hspmv_mg_*: the matrix row-sharded over several devices of ONE process (csrc/mg.cu).  x and y are host
+    vectors in the ORIGINAL numbering; halo entries of x only ever travel GPU to GPU inside spmv()."""
+
+    def __init__(self, handle, dtype):
+        self.h = handle
+        self.dtype = np.dtype(dtype)
+
+    @staticmethod
+    def _mg_check(rc):
+        if rc:
+            lib().hspmv_mg_last_error.restype = C.c_char_p
+            raise HspmvError("hspmv_mg error %d: %s" % (rc, lib().hspmv_mg_last_error().decode()))
+
+    @staticmethod
+    def _sizes(k, sizes):
+        return (C.c_int * 2)(*(list(sizes or []) + [0, 0])[:2]) if k > 1 else None
+
+    @classmethod
+    def from_csr(cls, devices, row_ptr, col_idx, val, n_cols=None, index_base=0, k=1, sup_row_sizes=None):
+        row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int32)
+        col_idx = np.ascontiguousarray(col_idx, dtype=np.int32)
+        val = np.ascontiguousarray(val)
+        m = len(row_ptr) - 1
+        dev = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        cls._mg_check(lib().hspmv_mg_create_csr(C.byref(h), dev, len(devices), C.c_int64(m), C.c_int64(m if n_cols is None else n_cols),
+                                                C.c_int64(len(col_idx)), _p(row_ptr), _p(col_idx), _p(val), _dt(val.dtype),
+                                                int(index_base), int(k), cls._sizes(k, sup_row_sizes)))
+        return cls(h, val.dtype)
+
+    @classmethod
+    def stencil(cls, devices, kind, g, dtype=np.float64, mode=0, k=1, sup_row_sizes=None):
+        dev = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        cls._mg_check(lib().hspmv_mg_create_stencil(C.byref(h), dev, len(devices), int(kind), C.c_int64(g), _dt(dtype), int(mode),
+                                                    int(k), cls._sizes(k, sup_row_sizes)))
+        return cls(h, dtype)
+
+    def info(self):
+        nd, dt, k, rep = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        m, n, nnz = C.c_int64(), C.c_int64(), C.c_int64()
+        self._mg_check(lib().hspmv_mg_info(self.h, C.byref(nd), C.byref(m), C.byref(n), C.byref(nnz), C.byref(dt), C.byref(k), C.byref(rep)))
+        return {"n_dev": nd.value, "m": m.value, "n": n.value, "nnz": nnz.value, "dtype": dt.value, "k": k.value,
+                "replicated": bool(rep.value)}
+
+    def partition(self):
+        nd = self.info()["n_dev"]
+        dev = (C.c_int * nd)()
+        row_lo = np.zeros(nd + 1, np.int64)
+        cmin, cmax, nnz, halo = (np.zeros(nd, np.int64) for _ in range(4))
+        self._mg_check(lib().hspmv_mg_partition_query(self.h, dev, _p(row_lo), _p(cmin), _p(cmax), _p(nnz), _p(halo)))
+        return {"devices": list(dev), "row_lo": row_lo, "col_min": cmin, "col_max": cmax, "nnz": nnz, "halo_elems": halo}
+
+    def perm(self):
+        p = np.zeros(self.info()["m"], np.uint32)
+        self._mg_check(lib().hspmv_mg_get_perm(self.h, _p(p)))
+        return p
+
+    def shard_kernel(self, d=0):
+        lib().hspmv_mg_shard.restype = C.c_void_p
+        return lib().hspmv_last_kernel(C.c_void_p(lib().hspmv_mg_shard(self.h, int(d)))).decode()
+
+    def set_x(self, x):
+        x = np.ascontiguousarray(x, dtype=self.dtype)
+        assert len(x) == self.info()["n"]
+        self._mg_check(lib().hspmv_mg_set_x(self.h, _p(x)))
+
+    def poison_halos(self):
+        self._mg_check(lib().hspmv_mg_poison_halos(self.h))
+
+    def spmv(self):
+        self._mg_check(lib().hspmv_mg_spmv(self.h))
+
+    def sync(self):
+        self._mg_check(lib().hspmv_mg_sync(self.h))
+
+    def get_y(self):
+        y = np.zeros(self.info()["m"], self.dtype)
+        self._mg_check(lib().hspmv_mg_get_y(self.h, _p(y)))
+        return y
+
+    def spmv_timed(self, warmup=3, iters=10):
+        ms = np.zeros(iters, np.float32)
+        self._mg_check(lib().hspmv_mg_spmv_timed(self.h, int(warmup), int(iters), _p(ms)))
+        return ms
+
+    def spmv_timed_batch(self, warmup=3, iters=10):
+        ms = C.c_float()
+        self._mg_check(lib().hspmv_mg_spmv_timed_batch(self.h, int(warmup), int(iters), C.byref(ms)))
+        return ms.value
+
+    def close(self):
+        if self.h:
+            lib().hspmv_mg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def device_count():
+    c = C.c_int()
+    _check(lib().hspmv_device_count(C.byref(c)))
+    return c.value
 
 
 # ------------------------------------------------------------------------------ reference-named API

@@ -746,6 +746,7 @@ int hspmv_device_info(int *sm_count, int64_t *l2_bytes, int64_t *hbm_bytes, int 
   return HSPMV_OK;
 }
 int64_t hspmv_launch_count(void) { return g_launches.load(); }
+int hspmv_omp_spmv_cache_size(void);
 
 // ---- files ----------------------------------------------------------------------------
 int hspmv_read_csr_text(const char *path, int index_base, int dtype, int64_t *m, int64_t *n,
@@ -1199,6 +1200,30 @@ int hspmv_fill_x_synthetic(hspmv_matrix *A, int64_t global_offset) {
   return HSPMV_OK;
 }
 
+int hspmv_fill_x_segments(void *d_x, int dtype, int n_seg, const int64_t *lo, const int64_t *hi, int64_t global_offset,
+                          double scale, void *stream) {
+  if (!d_x || n_seg < 0 || n_seg > 8 || (n_seg && (!lo || !hi)) || (dtype != HSPMV_F32 && dtype != HSPMV_F64))
+    return fail(HSPMV_EINVAL, "bad arguments");
+  hspmv::FillSegs segs;
+  segs.n = n_seg;
+  int64_t longest = 0;
+  for (int i = 0; i < n_seg; ++i) {
+    if (lo[i] < 0 || hi[i] < lo[i]) return fail(HSPMV_EINVAL, "bad segment");
+    segs.lo[i] = lo[i];
+    segs.hi[i] = hi[i];
+    longest = std::max(longest, hi[i] - lo[i]);
+  }
+  if (!longest) return HSPMV_OK;
+  const int grid = grid_for(longest, 256, 148 * 16);
+  if (dtype == HSPMV_F64)
+    hspmv::vector_x_segments_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(segs, global_offset, scale, (double *)d_x);
+  else
+    hspmv::vector_x_segments_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(segs, global_offset, scale, (float *)d_x);
+  LAUNCHED();
+  CU(cudaGetLastError());
+  return HSPMV_OK;
+}
+
 // ---- hot path ---------------------------------------------------------------------------
 int hspmv_set_option(hspmv_matrix *A, int option, int64_t value) {
   if (!A || option < 1 || option > 15) return fail(HSPMV_EINVAL, "bad option");
@@ -1533,24 +1558,81 @@ int hspmv_spmv_host(hspmv_matrix *A, int algo, const void *x_host, void *y_host)
 const char *hspmv_last_kernel(const hspmv_matrix *A) { return A ? A->last_kernel.c_str() : ""; }
 
 // ---- spmv.h compatibility ------------------------------------------------------------------
+// omp_spmv(m, n, nnz, row_start, col_idx, val, x, y) carries no handle, so the uploaded matrix is
+// cached.  The key is the arrays' identity AND a content fingerprint (all of row_start, 4096
+// evenly spaced samples of col_idx and val, both ends included), checked on every call: a caller
+// that refills the arrays in place, or frees them and allocates another matrix at the same
+// addresses, gets a fresh upload instead of the stale device matrix.  At most COMPAT_CACHE_MAX
+// matrices stay resident (least recently used goes first).
 namespace {
-typedef std::tuple<const void *, const void *, const void *, int, int, int> CacheKey;
-std::map<CacheKey, hspmv_matrix *> g_cache;
+struct CompatKey {
+  const void *rs, *ci, *val;
+  int m, nnz, dtype;
+  bool operator<(const CompatKey &o) const {
+    return std::tie(rs, ci, val, m, nnz, dtype) < std::tie(o.rs, o.ci, o.val, o.m, o.nnz, o.dtype);
+  }
+};
+struct CompatEntry {
+  hspmv_matrix *A;
+  uint64_t print, used;
+};
+std::map<CompatKey, CompatEntry> g_cache;
 std::mutex g_cache_mu;
+uint64_t g_cache_clock = 0;
+constexpr size_t COMPAT_CACHE_MAX = 4;
+
+uint64_t fnv(uint64_t h, const void *p, size_t bytes) {
+  const unsigned char *b = (const unsigned char *)p;
+  for (size_t i = 0; i < bytes; ++i) h = (h ^ b[i]) * 1099511628211ull;
+  return h;
+}
+uint64_t compat_fingerprint(int dtype, int m, int nnz, const int *rs, const int *ci, const void *val) {
+  const size_t vs = dtype == HSPMV_F64 ? 8 : 4;
+  uint64_t h = 1469598103934665603ull;
+  // row_start in 64-bit words (fast), the odd tail by bytes
+  const size_t words = ((size_t)m + 1) / 2;
+  const uint64_t *w = (const uint64_t *)rs;
+  for (size_t i = 0; i < words; ++i) h = (h ^ w[i]) * 1099511628211ull;
+  h = fnv(h, rs + words * 2, ((size_t)m + 1 - words * 2) * 4);
+  if (nnz > 0) {
+    const int64_t samples = nnz < 4096 ? nnz : 4096;
+    for (int64_t s = 0; s < samples; ++s) {
+      const int64_t j = samples > 1 ? (int64_t)(nnz - 1) * s / (samples - 1) : 0;
+      h = fnv(h, ci + j, 4);
+      h = fnv(h, (const char *)val + (size_t)j * vs, vs);
+    }
+  }
+  return h;
+}
 
 int compat_spmv(int dtype, int m, int n, int nnz, const int *rs, const int *ci, const void *val,
                 const void *x, void *y) {
+  if (!rs || m < 0 || nnz < 0 || (nnz && (!ci || !val))) return fail(HSPMV_EINVAL, "null CSR array");
   std::lock_guard<std::mutex> lock(g_cache_mu);
-  CacheKey key(rs, ci, val, m, nnz, dtype);
+  const CompatKey key{rs, ci, val, m, nnz, dtype};
+  const uint64_t print = compat_fingerprint(dtype, m, nnz, rs, ci, val);
   hspmv_matrix *A = nullptr;
   auto it = g_cache.find(key);
+  if (it != g_cache.end() && it->second.print != print) { // same addresses, different matrix
+    hspmv_destroy(it->second.A);
+    g_cache.erase(it);
+    it = g_cache.end();
+  }
   if (it == g_cache.end()) {
+    while (g_cache.size() >= COMPAT_CACHE_MAX) {
+      auto old = g_cache.begin();
+      for (auto j = g_cache.begin(); j != g_cache.end(); ++j)
+        if (j->second.used < old->second.used) old = j;
+      hspmv_destroy(old->second.A);
+      g_cache.erase(old);
+    }
     // the reference's omp_spmv indexes x with column ids < m for its square inputs; n is unused there
     int rc = hspmv_create_csr(&A, m, n > 0 ? n : m, nnz, rs, ci, val, dtype, 0, 0);
     if (rc) return rc;
-    g_cache[key] = A;
+    g_cache[key] = CompatEntry{A, print, ++g_cache_clock};
   } else {
-    A = it->second;
+    A = it->second.A;
+    it->second.used = ++g_cache_clock;
   }
   return hspmv_spmv_host(A, HSPMV_ALGO_AUTO, x, y);
 }
@@ -1564,9 +1646,13 @@ int hspmv_omp_spmv_f32(int m, int n, int nnz, const int *row_start, const int *c
                        const float *x, float *y) {
   return compat_spmv(HSPMV_F32, m, n, nnz, row_start, col_idx, val, x, y);
 }
+int hspmv_omp_spmv_cache_size(void) {
+  std::lock_guard<std::mutex> lock(g_cache_mu);
+  return (int)g_cache.size();
+}
 void hspmv_omp_spmv_cache_clear(void) {
   std::lock_guard<std::mutex> lock(g_cache_mu);
-  for (auto &kv : g_cache) hspmv_destroy(kv.second);
+  for (auto &kv : g_cache) hspmv_destroy(kv.second.A);
   g_cache.clear();
 }
 

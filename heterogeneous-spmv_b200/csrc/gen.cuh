@@ -101,4 +101,19 @@ __global__ void vector_x_kernel(int64_t n, int64_t offset, T *__restrict__ x) {
     x[i] = (T)(1.0 + (double)((i + offset) % 97) / 128.0);
 }
 
+
+// x_i = (1 + ((i + offset) mod 97)/128) * scale on up to 8 index ranges [lo, hi) of one vector, in one launch
+// (hspmv_fill_x_segments: the per-step x update of the multi-GPU parity runs)
+struct FillSegs {
+  int n;
+  int64_t lo[8], hi[8];
+};
+template <typename T>
+__global__ void vector_x_segments_kernel(FillSegs segs, int64_t offset, double scale, T *__restrict__ x) {
+  for (int s = 0; s < segs.n; ++s)
+    for (int64_t i = segs.lo[s] + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < segs.hi[s];
+         i += (int64_t)gridDim.x * blockDim.x)
+      x[i] = (T)((1.0 + (double)((i + offset) % 97) / 128.0) * scale);
+}
+
 } // namespace hspmv

@@ -129,6 +129,16 @@ __device__ __forceinline__ Quad<double> load_quad(const double *base, int64_t id
   return q;
 }
 
+// x gathers.  COH = false: read-only path (ld.global.nc), for x that nobody writes while the kernel
+// runs.  COH = true: the tile reads the x halo that a neighbour GPU wrote over NVLink DURING this
+// launch (hspmv_spmv_halo); ld.global.nc is outside the memory model there, and an interior tile
+// may already have pulled the sector that straddles the own/halo boundary into L1, so these
+// gathers go to L2 (ld.global.cg), the point of coherence for peer writes, ordered behind the
+// ld.acquire.sys of halo_spin_wait by the __syncwarp that follows it.
+template <bool COH, typename T> __device__ __forceinline__ T ld_x(const T *p) {
+  return COH ? __ldcg(p) : __ldg(p);
+}
+
 template <typename T, int VEC> __device__ __forceinline__ T group_sum(T v) {
 #pragma unroll
   for (int o = VEC >> 1; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o, VEC);
@@ -332,7 +342,7 @@ __host__ __device__ inline size_t csrk_stage_bytes(int cap_nnz, int cap_rows, si
 //         the row's own column set (0 * x[c] only meets an x entry this row references anyway).
 // MAIN = 0 disables the unmasked loop.  Index type I: int for the staged path (offsets into the
 // shared-memory window), int64_t for the unstaged path (global nonzero indices).
-template <typename T, int VEC, int MAIN, int TAIL, typename I>
+template <typename T, int VEC, int MAIN, int TAIL, typename I, bool COH = false>
 __device__ __forceinline__ void csrk_rows(int r0, int r1, const int *__restrict__ rp_w, int rbase,
                                           const int *__restrict__ ci_w, const T *__restrict__ val_w,
                                           I ebase, const T *__restrict__ x, T *__restrict__ y,
@@ -360,7 +370,7 @@ __device__ __forceinline__ void csrk_rows(int r0, int r1, const int *__restrict_
           v[u] = val_w[j + u * VEC];
         }
 #pragma unroll
-        for (int u = 0; u < MAIN; ++u) xv[u] = __ldg(x + c[u]);
+        for (int u = 0; u < MAIN; ++u) xv[u] = ld_x<COH>(x + c[u]);
 #pragma unroll
         for (int u = 0; u < MAIN; ++u) acc += v[u] * xv[u];
       }
@@ -378,7 +388,7 @@ __device__ __forceinline__ void csrk_rows(int r0, int r1, const int *__restrict_
         if (jj > last) v[u] = (T)0;
       }
 #pragma unroll
-      for (int u = 0; u < TAIL; ++u) xv[u] = __ldg(x + c[u]);
+      for (int u = 0; u < TAIL; ++u) xv[u] = ld_x<COH>(x + c[u]);
 #pragma unroll
       for (int u = 0; u < TAIL; ++u) acc += v[u] * xv[u];
     }
@@ -577,6 +587,7 @@ __global__ void __launch_bounds__(512, 1) csrk_tma_kernel(const CsrkParams<T> p)
     const int *meta = reinterpret_cast<const int *>(base);
     const int r0 = meta[0], r1 = meta[1], e0 = meta[2], e1m = meta[3];
     if (consumed == wait_at) halo_spin_wait(p.wait_flags, p.n_wait, p.wait_step, p.timed_out, lane);
+    const bool halo_tile = wait_at >= 0 && consumed >= wait_at; // warp-uniform: this tile gathers from the halo
     ++consumed;
     bool released = false;
     if (e1m >= 0) {
@@ -616,7 +627,7 @@ __global__ void __launch_bounds__(512, 1) csrk_tma_kernel(const CsrkParams<T> p)
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              const T xg = __ldg(p.x + cx[u]);
+              const T xg = halo_tile ? ld_x<true>(p.x + cx[u]) : ld_x<false>(p.x + cx[u]);
               if (j + u * VEC < re) acc += vx[u] * xg; // predicated: an idle slot must not meet an inf in x
             }
           }
@@ -656,16 +667,25 @@ __global__ void __launch_bounds__(512, 1) csrk_tma_kernel(const CsrkParams<T> p)
         advance(st);
         released = true;
         T xv[NS];
+        if (halo_tile) {
 #pragma unroll
-        for (int u = 0; u < NS; ++u) xv[u] = __ldg(p.x + c[u]);
+          for (int u = 0; u < NS; ++u) xv[u] = ld_x<true>(p.x + c[u]);
+        } else {
+#pragma unroll
+          for (int u = 0; u < NS; ++u) xv[u] = ld_x<false>(p.x + c[u]);
+        }
 #pragma unroll
         for (int u = 0; u < NS; ++u) acc += v[u] * xv[u]; // same order as csrk_rows: a row's sum does not depend on the tiling
         if (re <= rs) acc = (T)0; // empty row: its idle slots multiplied 0 by x[0], which may be inf
         acc = group_sum<T, VEC>(acc);
         if (active && sub == 0) p.y[r] = acc;
+      } else if (halo_tile) {
+        csrk_rows<T, VEC, MAIN, TAIL, int, true>(r0, r1, rp_w, r0 & ~3, ci_w, va_w, e0 & ~3, p.x, p.y, lane);
       } else {
         csrk_rows<T, VEC, MAIN, TAIL, int>(r0, r1, rp_w, r0 & ~3, ci_w, va_w, e0 & ~3, p.x, p.y, lane);
       }
+    } else if (halo_tile) {
+      csrk_rows<T, VEC, MAIN, TAIL, int64_t, true>(r0, r1, p.rp, 0, p.ci, p.val, (int64_t)0, p.x, p.y, lane);
     } else {
       csrk_rows<T, VEC, MAIN, TAIL, int64_t>(r0, r1, p.rp, 0, p.ci, p.val, (int64_t)0, p.x, p.y, lane);
     }

@@ -57,6 +57,19 @@ def wrap_device_ptr(ptr, count, dtype=torch.float64):
     return torch.as_tensor(_Holder(), device="cuda")
 
 
+class AsymmetricHalo(RuntimeError):
+    """the ack-less ping-pong protocol needs senders == receivers on every rank"""
+
+
+def halo_is_symmetric(row_lo, col_ranges):
+    """True when, on every rank, the set of ranks it receives from equals the set it sends to."""
+    for r in range(len(row_lo) - 1):
+        recv, send = halo_plan(row_lo, col_ranges, r)
+        if {q for q, _, _ in recv} != {q for q, _, _ in send}:
+            return False
+    return True
+
+
 class PeerHalo:
     """Halo exchange straight into the neighbours' x buffers over NVLink (CUDA IPC), no NCCL and
     no SM: the local SpMV kernel is persistent and owns every SM, so everything that must run
@@ -73,7 +86,11 @@ class PeerHalo:
     No acknowledgement is needed: I overwrite a neighbour's halo of buffer b at step t+2 only
     after my kernel of step t+1 has finished, and that kernel waited for the neighbour's flags of
     step t+1, which the neighbour sent after ITS kernel of step t (the last reader of buffer b)
-    had finished.  (An earlier version sent acks and waited for them with cuStreamWaitValue32 on
+    had finished.  That argument needs every rank I push to to be one of my senders as well
+    (otherwise nothing makes me wait for it): the constructor checks it on the all-gathered plans
+    and raises AsymmetricHalo, and the caller falls back to an exchange with acknowledgements
+    (NCCL send/recv).  begin() also makes the main stream wait for my own pushes of step t-2, the
+    last readers of the buffer that the caller is about to fill with x of step t.  (An earlier version sent acks and waited for them with cuStreamWaitValue32 on
     the comm stream: a command-processor wait on a word written from another GPU woke up 0.2-0.5 ms
     late while the persistent kernel was running -- profiles/r1_scaling.md.)
     The buffers must come from cudaMalloc (hspmv_x_device / hspmv_peer_alloc).
@@ -91,6 +108,8 @@ class PeerHalo:
         self.recv, self.send = halo_plan(row_lo, col_ranges, rank)
         self.senders = sorted({q for q, _, _ in self.recv})
         self.receivers = sorted({q for q, _, _ in self.send})
+        if not halo_is_symmetric(row_lo, col_ranges):      # same answer on every rank: all raise together
+            raise AsymmetricHalo("rank %d receives from %s but sends to %s" % (rank, self.senders, self.receivers))
         assert len(self.senders) <= 32
         self.flags = hs.peer_alloc(4 * 64)
         blob = hs.peer_export(self.x_ptrs[0]) + hs.peer_export(self.x_ptrs[1]) + hs.peer_export(self.flags)
@@ -113,6 +132,7 @@ class PeerHalo:
         self.step = 0
         self.comm = torch.cuda.Stream()
         self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.pushed = [None, None]      # comm-stream events: my pushes out of buffer b are complete
         self.trace = None   # set to [] to collect (kernel-start, push-done) timing events per step
         self.halo_elems = sum(b - a for _, a, b in self.recv)
         dist.barrier(group=group)
@@ -130,6 +150,13 @@ class PeerHalo:
 
     def timeout_word(self):
         return self._w(self.flags, 32)
+
+    def reuse_buffer(self):
+        """Call BEFORE writing x of the next step into its buffer: the main stream waits until my
+        own pushes of two steps ago, which read that buffer, are complete."""
+        ev = self.pushed[(self.step + 1) % 2]
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
 
     def begin(self):
         """Step t starts: x[t % 2] is ready at this point of the main stream."""
@@ -151,6 +178,9 @@ class PeerHalo:
                             self.x_ptrs[b] + (lo - self.cmin) * self.itemsize, (hi - lo) * self.itemsize, cs)
         for q in self.receivers:
             hs.stream_write(cs, self._w(self.peer_flags[q], self.my_slot_at[q]), t)
+        if self.pushed[b] is None:
+            self.pushed[b] = torch.cuda.Event()
+        self.pushed[b].record(self.comm)
         if self.trace is not None:
             e = torch.cuda.Event(enable_timing=True)
             e.record(self.comm)

@@ -17,6 +17,7 @@ struct Options {
   int algo = HSPMV_ALGO_AUTO;
   int k = 0;           // --k 2|3
   bool cache = false;  // --cache: keep / use the binary side file <matrix>.hspmvbin
+  int gpus = 1;        // --gpus N: row-shard the matrix over devices 0..N-1 (hspmv_mg_*, one host thread)
   std::vector<const char *> pos;
 };
 
@@ -27,6 +28,7 @@ inline Options parse(int argc, char **argv) {
     else if (!std::strcmp(argv[i], "--fp64")) o.fp32 = false;
     else if (!std::strcmp(argv[i], "--cache")) o.cache = true;
     else if (!std::strcmp(argv[i], "--base") && i + 1 < argc) o.base = std::atoi(argv[++i]);
+    else if (!std::strcmp(argv[i], "--gpus") && i + 1 < argc) o.gpus = std::atoi(argv[++i]);
     else if (!std::strcmp(argv[i], "--k") && i + 1 < argc) o.k = std::atoi(argv[++i]);
     else if (!std::strcmp(argv[i], "--algo") && i + 1 < argc) {
       const char *a = argv[++i];
@@ -120,4 +122,67 @@ template <typename T> inline int count_wrong(const T *y, const T *yref, const un
     if (d > .01 || d < -.01) ++wrong;
   }
   return wrong;
+}
+
+#define CHECK_MG(call)                                                         \
+  do {                                                                         \
+    if (call) {                                                                \
+      std::printf("Error: %s\n", hspmv_mg_last_error());                       \
+      std::exit(0);                                                            \
+    }                                                                          \
+  } while (0)
+
+// --gpus N: the same protocol on N devices of the box through the multi-GPU entry points of the C ABI.
+// x and y cross hspmv_mg_* in the ORIGINAL numbering, so the self-check needs no permutation.
+// k = 1: plain CSR; k = 2 / 3: Band-k on device 0, shards cut at super-row / super-super-row boundaries.
+template <typename T>
+inline int run_multi_gpu(const Options &o, const HostCsr &H, int N, int warmup, int k, const int *sizes, int index_base) {
+  std::vector<int> dev((size_t)o.gpus);
+  for (int i = 0; i < o.gpus; ++i) dev[(size_t)i] = i;
+  hspmv_mg *M = nullptr;
+  CHECK_MG(hspmv_mg_create_csr(&M, dev.data(), o.gpus, H.m, H.n, H.nnz, H.rp, H.ci, H.val, H.dtype, index_base, k, sizes));
+  int repl = 0;
+  CHECK_MG(hspmv_mg_info(M, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, &repl));
+  std::vector<int64_t> row_lo((size_t)o.gpus + 1), halo((size_t)o.gpus), nz((size_t)o.gpus);
+  CHECK_MG(hspmv_mg_partition_query(M, nullptr, row_lo.data(), nullptr, nullptr, nz.data(), halo.data()));
+  std::printf("Multi-GPU: %d devices, %s\n", o.gpus, repl ? "x replicated, y row-sharded" : "nnz-balanced row blocks + x halo exchange over NVLink");
+  for (int d = 0; d < o.gpus; ++d)
+    std::printf("  device %d: rows [%lld,%lld) nnz %lld halo %lld\n", d, (long long)row_lo[(size_t)d], (long long)row_lo[(size_t)d + 1],
+                (long long)nz[(size_t)d], (long long)halo[(size_t)d]);
+  std::vector<T> x((size_t)(H.n > H.m ? H.n : H.m), (T)1), y((size_t)H.m, (T)0), yser((size_t)H.m, (T)0);
+  CHECK_MG(hspmv_mg_set_x(M, x.data()));
+  for (int i = 0; i < warmup; ++i) CHECK_MG(hspmv_mg_spmv(M));
+  CHECK_MG(hspmv_mg_sync(M));
+  Times host;
+  for (int i = 0; i < N; ++i) {
+    auto tic = std::chrono::steady_clock::now();
+    CHECK_MG(hspmv_mg_spmv(M));
+    CHECK_MG(hspmv_mg_sync(M));
+    std::chrono::duration<float> toc = std::chrono::steady_clock::now() - tic;
+    host.add(toc.count());
+  }
+  host.print();
+  if (N > 0) {
+    std::vector<float> ms((size_t)N);
+    CHECK_MG(hspmv_mg_spmv_timed(M, 0, N, ms.data()));
+    float mn = 1e30f, sum = 0;
+    for (float t : ms) { mn = t < mn ? t : mn; sum += t; }
+    std::printf("DeviceTimeMin: %lg\nDeviceTimeAvg: %lg\n", (double)mn * 1e-3, (double)(sum / N) * 1e-3);
+    std::printf("Kernel: %s\n", hspmv_last_kernel((hspmv_matrix *)hspmv_mg_shard(M, 0)));
+  }
+  HostCsr Z = H; // the self-check product on 0-based arrays
+  std::vector<int32_t> rp0, ci0;
+  if (index_base) {
+    rp0.assign(H.rp, H.rp + H.m + 1);
+    ci0.assign(H.ci, H.ci + H.nnz);
+    for (auto &t : rp0) t -= index_base;
+    for (auto &t : ci0) t -= index_base;
+    Z.rp = rp0.data();
+    Z.ci = ci0.data();
+  }
+  test_spmv<T>(Z, x.data(), yser.data());
+  CHECK_MG(hspmv_mg_get_y(M, y.data()));
+  std::printf("Number Wrong: %d \n", count_wrong<T>(y.data(), yser.data(), nullptr, H.m));
+  hspmv_mg_destroy(M);
+  return 0;
 }

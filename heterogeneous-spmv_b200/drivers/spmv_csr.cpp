@@ -4,6 +4,7 @@
 #include "common.h"
 
 template <typename T> static int run(const Options &o, HostCsr &H, int N) {
+  if (o.gpus > 1) return run_multi_gpu<T>(o, H, N, /*warmup=*/0, 1, nullptr, 0);
   std::vector<T> x((size_t)(H.n > H.m ? H.n : H.m), (T)1), y((size_t)H.m, (T)0), yhat((size_t)H.m, (T)0);
   std::printf("---------BEFORE FIRST FILL---------\n");
   hspmv_matrix *A = nullptr;

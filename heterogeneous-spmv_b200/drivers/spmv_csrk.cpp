@@ -11,6 +11,7 @@
 static bool o_tune = false; // --tune, and the default of spmv-auto-b200 (--no-tune switches it off)
 
 template <typename T> static int run(const Options &o, HostCsr &H, int N, int k, int *sizes, bool print_perm) {
+  if (o.gpus > 1) return run_multi_gpu<T>(o, H, N, /*warmup=*/5, k, sizes, 0); // (read_matrix already removed the 1-base)
   std::vector<T> x((size_t)H.m, (T)1), y((size_t)H.m, (T)0), yser((size_t)H.m, (T)0);
   hspmv_matrix *A = nullptr;
   CHECK(hspmv_create_csr(&A, H.m, H.n, H.nnz, H.rp, H.ci, H.val, H.dtype, 0, 1));

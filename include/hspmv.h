@@ -184,6 +184,12 @@ void *hspmv_y_device(hspmv_matrix *A);
  * (generators.py:vector_x; the non-constant x the parity tests use instead of the reference's
  * x = 1, which is blind to permutation errors -- SURVEY.md section 4). */
 int hspmv_fill_x_synthetic(hspmv_matrix *A, int64_t global_offset);
+/* The same rule times `scale`, on up to 8 index ranges [lo[s], hi[s]) of any device vector, in one
+ * stream-ordered launch: x_i = (1 + ((global_offset + i) mod 97)/128) * scale.  The multi-GPU parity
+ * runs use it to change the boundary slices of x every step, so that every step needs a fresh halo
+ * (a push that never lands, or lands at the wrong offset, then shows in y). */
+int hspmv_fill_x_segments(void *d_x, int dtype, int n_seg, const int64_t *lo, const int64_t *hi,
+                          int64_t global_offset, double scale, void *stream);
 
 /* ---- the hot path ----------------------------------------------------------------- */
 int hspmv_set_option(hspmv_matrix *A, int option, int64_t value);
@@ -234,13 +240,16 @@ const char *hspmv_last_kernel(const hspmv_matrix *A);
 
 /* Source-compatible replacements for spmv-csr/spmv.h:11-12 (double) and the float body in
  * spmv-csr/spmv.c:92-114: host CSR in, host y out.  The matrix is uploaded on first use and
- * cached by (row_start, col_idx, val, nnz) identity, so repeated calls in a timing loop
- * only move x and y. */
+ * cached by (row_start, col_idx, val, m, nnz) identity plus a content fingerprint (all of
+ * row_start, 4096 samples of col_idx / val) that is re-checked on every call, so repeated calls
+ * in a timing loop only move x and y, while arrays that were refilled in place or reallocated at
+ * the same addresses are uploaded again. */
 int hspmv_omp_spmv_f64(int m, int n, int nnz, const int *row_start, const int *col_idx,
                        const double *val, const double *x, double *y);
 int hspmv_omp_spmv_f32(int m, int n, int nnz, const int *row_start, const int *col_idx,
                        const float *val, const float *x, float *y);
 void hspmv_omp_spmv_cache_clear(void);
+int hspmv_omp_spmv_cache_size(void); /* matrices currently resident in that cache (<= 4, LRU) */
 
 /* ---- multi-GPU index work (host; bit-exact vs oracle/partition_oracle.py) ---------- */
 /* nnz-balanced contiguous row blocks: row_lo[p] = first row r with row_ptr[r] >= p*nnz/P
@@ -289,10 +298,58 @@ int hspmv_stream_write(void *stream, int *addr, int value);
 int hspmv_stream_wait_ge(void *stream, const int *addr, int value);
 /* One launch for a whole shard: tiles of the interior rows [interior_lo, interior_hi) first, then
  * the rows below and above, which reference the x halo; a warp reaching its first halo tile spins
- * (bounded; *timed_out is set on failure) until every wait_flags[i] >= wait_step.  With
- * n_wait == 0 it is hspmv_spmv over the three ranges in that order. */
+ * (bounded) until every wait_flags[i] >= wait_step, and the halo tiles gather x through L2
+ * (ld.global.cg), not through the read-only path, because a peer writes that part of x while the
+ * kernel runs.  `timed_out` points to a block of HSPMV_HALO_DIAG_WORDS (10) device ints:
+ * [0] set to 1 when a wait gave up, [1] longest warp spin (1024-cycle units), [2] number of
+ * warp-level waits, [3] their total spin, [4..9] a histogram of the spins.  With n_wait == 0 it
+ * is hspmv_spmv over the three ranges in that order and timed_out may be NULL. */
+#define HSPMV_HALO_DIAG_WORDS 10
 int hspmv_spmv_halo(hspmv_matrix *A, int64_t interior_lo, int64_t interior_hi, const void *d_x, void *d_y,
                     const int *wait_flags, int n_wait, int wait_step, int *timed_out, void *stream);
+
+/* ---- multi-GPU in ONE process (csrc/mg.cu) -----------------------------------------------------
+ * "multi-GPU init (device list) + partition query ... one stream + comm per device".  For C/C++
+ * drivers in the style of cuda-spmv-csrk/cuda/spmv.cu:111-266 (one host thread, default device) that want every
+ * GPU of the box: the matrix is built on devices[0] (uploaded or generated, optionally Band-k-reordered there),
+ * cut into nnz-balanced row blocks (CSR-k: at super-row / super-super-row boundaries) and every device keeps its
+ * block with the x window it references.  Banded matrices exchange the x halo over NVLink every step (peer
+ * copies + flag words, the local kernel waits for the flags itself: hspmv_spmv_halo); matrices whose blocks
+ * reference all of x, or whose exchange plan is not symmetric, run with x replicated.  x and y cross this
+ * boundary in the ORIGINAL numbering (the Band-k permutation is applied inside, like setX / the check at
+ * spmv-csrk/spmv.cpp:203).  One handle per host thread; every call returns after ENQUEUEING unless it says so. */
+typedef struct hspmv_mg hspmv_mg;
+const char *hspmv_mg_last_error(void);
+/* k = 1: plain CSR; k = 2 / 3: hspmv_build_csrk(k, sup_row_sizes) on devices[0] before the cut. */
+int hspmv_mg_create_csr(hspmv_mg **out, const int *devices, int n_dev, int64_t m, int64_t n, int64_t nnz,
+                        const int32_t *row_ptr, const int32_t *col_idx, const void *val, int dtype, int index_base,
+                        int k, const int *sup_row_sizes);
+/* the closed-form stencils of hspmv_create_stencil (kind 27 / 5), generated in HBM on devices[0] */
+int hspmv_mg_create_stencil(hspmv_mg **out, const int *devices, int n_dev, int kind, int64_t g, int dtype, int mode,
+                            int k, const int *sup_row_sizes);
+int hspmv_mg_destroy(hspmv_mg *M);
+int hspmv_mg_info(const hspmv_mg *M, int *n_dev, int64_t *m, int64_t *n, int64_t *nnz, int *dtype, int *k,
+                  int *replicated);
+/* Partition query (any pointer may be NULL): devices[n_dev], row_lo[n_dev+1] (kernel row numbering), the column
+ * window [col_min[d], col_max[d]] of each block, its nonzeros, and the x entries it receives per step. */
+int hspmv_mg_partition_query(const hspmv_mg *M, int *devices, int64_t *row_lo, int64_t *col_min, int64_t *col_max,
+                             int64_t *nnz_per_dev, int64_t *halo_elems);
+int hspmv_mg_get_perm(const hspmv_mg *M, uint32_t *perm); /* CSR-k: new -> old, m entries */
+void *hspmv_mg_shard(hspmv_mg *M, int d);                 /* the hspmv_matrix* of block d (options, last_kernel) */
+/* Upload x (n entries, original numbering): every device receives the slice it OWNS; halo entries only ever
+ * arrive device to device inside hspmv_mg_spmv.  Replicated mode: all of x to every device.  Synchronous. */
+int hspmv_mg_set_x(hspmv_mg *M, const void *x_host);
+/* One step on every device (halo exchange of the current x + local SpMV), enqueued only. */
+int hspmv_mg_spmv(hspmv_mg *M);
+/* Wait for everything enqueued; HSPMV_ECUDA if an in-kernel halo wait gave up. */
+int hspmv_mg_sync(hspmv_mg *M);
+int hspmv_mg_get_y(hspmv_mg *M, void *y_host); /* m entries, original row order; synchronous */
+/* ms_per_step[i] = longest device time of step i (host-synchronised between steps, like the reference drivers'
+ * loop at cuda-spmv-csr/spmv.cu:240-260); _batch: iters steps back to back, one mean. */
+int hspmv_mg_spmv_timed(hspmv_mg *M, int warmup, int iters, float *ms_per_step);
+int hspmv_mg_spmv_timed_batch(hspmv_mg *M, int warmup, int iters, float *ms_per_step);
+/* test hook: NaN into every halo region of both x buffers (only a correct push makes them finite again) */
+int hspmv_mg_poison_halos(hspmv_mg *M);
 
 /* ---- kernel-side index tables, exposed for the bit-exactness tests ------------------ */
 /* CSR_MERGE tile table: tile_row[t] = last row r with row_ptr[r] <= t*tile, t = 0..n_tiles

@@ -82,6 +82,25 @@ def ref(kind, dtype):
     return _REF[key]
 
 
+# --------------------------------------------------------------------------- generators
+def stencil27(g, row_lo=0, row_hi=None, dtype=np.float64, mode="classic"):
+    """rows [row_lo,row_hi) of the 27-point g^3 stencil (same arrays as generators.stencil27, built
+    by the C closed form in parallel): (rp int32 rebased, ci int32 GLOBAL ids, val)."""
+    n = g ** 3
+    row_hi = n if row_hi is None else row_hi
+    L = lib()
+    L.gen_stencil27_before.restype = C.c_long
+    L.gen_stencil27_before.argtypes = [C.c_long, C.c_long]
+    nnz = L.gen_stencil27_before(row_hi, g) - L.gen_stencil27_before(row_lo, g)
+    rp = np.empty(row_hi - row_lo + 1, np.int32)
+    ci = np.empty(nnz, np.int32)
+    val = np.empty(nnz, dtype)
+    fn = getattr(L, "gen_stencil27_" + _sfx(dtype))
+    fn.argtypes = [C.c_long, C.c_long, C.c_long, C.c_int, i32p, i32p, _fp(dtype)]
+    fn(g, row_lo, row_hi, 0 if mode == "classic" else 1, rp, ci, val)
+    return rp, ci, val
+
+
 # --------------------------------------------------------------------------- restatement
 def csr_spmv(rp, ci, v, x, parallel=False):
     """y = A x, one accumulator per row, left to right (spmv-csr/spmv.c:68-90 / :92-114)."""

@@ -623,7 +623,7 @@ def test_fused_halo_launch_single_gpu(hs, oracle, gen):
     scale = oracle.abs_rowsum(rp, ci, v, x)
     A = hs.Matrix.from_csr(rp, ci, v)
     A.set_x(x)
-    flags = hs.peer_alloc(64)
+    flags = hs.peer_alloc(4 * 64)      # ints [0,2): data flags; [8, 8 + HSPMV_HALO_DIAG_WORDS): timeout word + spin diagnostics
     st = torch.cuda.current_stream().cuda_stream
     for a, b in ((g * g + g + 1, n - g * g - g - 1), (0, n), (0, 0), (n, n), (100, 101)):
         for n_wait, step in ((0, 0), (2, 7)):

@@ -18,9 +18,11 @@ import random
 import pytest
 
 
-def simulate(P, T, B, rng, skew):
-    """returns the list of violations (reader rank, step, writer rank, writer step)"""
-    nbrs = {r: [q for q in (r - 1, r + 1) if 0 <= q < P] for r in range(P)}
+def simulate(P, T, B, rng, skew, one_sided=False):
+    """returns the list of violations (reader rank, step, writer rank, writer step).
+    one_sided: rank r only receives from r-1 (a structurally unsymmetric matrix): the writer r-1 never
+    waits for anything from its reader, which is what dist.halo_is_symmetric() refuses."""
+    nbrs = {r: [q for q in ((r - 1,) if one_sided else (r - 1, r + 1)) if 0 <= q < P] for r in range(P)}
     k_end = {(r, 0): 0.0 for r in range(P)}        # K(r,0): nothing
     p_end = {(r, 0): 0.0 for r in range(P)}
     p_start, read_start = {}, {}
@@ -65,3 +67,22 @@ def test_ping_pong_without_acks_is_race_free(P, skew):
 def test_single_buffer_without_acks_races_in_the_model():
     hits = sum(bool(simulate(4, 12, 1, random.Random(seed), 5.0)) for seed in range(40))
     assert hits > 0, "the model cannot see the race it is supposed to rule out"
+
+
+def test_one_sided_senders_race_even_with_two_buffers():
+    """negative control for ADVICE r1: with senders != receivers the ack-less ping-pong is NOT safe (a fast
+    one-sided sender laps its reader); PeerHalo refuses such plans (dist.halo_is_symmetric)."""
+    hits = sum(bool(simulate(4, 12, 2, random.Random(seed), 50.0, one_sided=True)) for seed in range(40))
+    assert hits > 0
+
+
+def test_halo_is_symmetric_accepts_banded_and_rejects_one_sided():
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from heterogeneous_spmv_b200 import dist as hd
+    row_lo = [0, 100, 200, 300]
+    banded = [(0, 109), (90, 209), (190, 299)]
+    assert hd.halo_is_symmetric(row_lo, banded)
+    lower_only = [(0, 99), (90, 199), (190, 299)]          # every rank needs only columns below its block
+    assert not hd.halo_is_symmetric(row_lo, lower_only)
