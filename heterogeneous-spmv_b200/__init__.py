@@ -23,10 +23,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HSPMV_LIB") or os.path.join(HERE, "lib", "libhspmv.so")
 
 F32, F64 = 0, 1
-ALGO_AUTO, ALGO_CSR_VECTOR, ALGO_CSR_STREAM, ALGO_CSR_MERGE, ALGO_CSRK = 0, 1, 2, 3, 4
-ALGO_NAMES = {0: "auto", 1: "csr_vector", 2: "csr_stream", 3: "csr_merge", 4: "csrk"}
+ALGO_AUTO, ALGO_CSR_VECTOR, ALGO_CSR_STREAM, ALGO_CSR_MERGE, ALGO_CSRK, ALGO_CSR_BLOCK = 0, 1, 2, 3, 4, 5
+ALGO_NAMES = {0: "auto", 1: "csr_vector", 2: "csr_stream", 3: "csr_merge", 4: "csrk", 5: "csr_block"}
 (OPT_VEC, OPT_WARPS, OPT_STAGES, OPT_STAGE_NNZ, OPT_CTAS_PER_SM, OPT_ROWS_PER_TILE,
- OPT_L2_PERSIST_X, OPT_MERGE_TILE, OPT_THREADS, OPT_CHUNK, OPT_NO_PIPELINE, OPT_BANDK_HOST, OPT_TAIL) = range(1, 14)
+ OPT_L2_PERSIST_X, OPT_MERGE_TILE, OPT_THREADS, OPT_CHUNK, OPT_NO_PIPELINE, OPT_BANDK_HOST, OPT_TAIL, OPT_BLOCK_NNZ) = range(1, 15)
 ARCH_VOLTA, ARCH_AMPERE, ARCH_MI100, ARCH_B200 = 0, 1, 2, 3
 
 _lib = None
@@ -241,6 +241,15 @@ def bin_rows_host(row_ptr):
     bp = np.zeros(9, np.int64)
     _check(lib().hspmv_bin_rows_host(C.c_int64(m), _p(row_ptr), _p(rows), _p(bp)))
     return rows[:m], bp
+
+
+def block_rows_host(row_ptr, cap, max_rows):
+    row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int32)
+    m = len(row_ptr) - 1
+    out = np.zeros(m + 2, np.int32)
+    nb = C.c_int64()
+    _check(lib().hspmv_block_rows_host(C.c_int64(m), _p(row_ptr), C.c_int64(cap), C.c_int64(max_rows), _p(out), C.byref(nb)))
+    return out[: nb.value + 1].copy() if m > 0 else out[:1].copy()
 
 
 def merge_tile_rows_host(row_ptr, tile):

@@ -35,8 +35,10 @@ int fail(int code, const std::string &msg) {
 #define CU(call)                                                                          \
   do {                                                                                    \
     cudaError_t e_ = (call);                                                              \
-    if (e_ != cudaSuccess)                                                                \
+    if (e_ != cudaSuccess) {                                                              \
+      cudaGetLastError(); /* do not leave it for the next cudaGetLastError() */           \
       return fail(HSPMV_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));       \
+    }                                                                                     \
   } while (0)
 
 constexpr int64_t PAD = 16; // tail padding (elements) of every device array
@@ -90,6 +92,10 @@ struct hspmv_matrix {
   int64_t sr_max_rows = 0, sr_max_nnz = 0; // largest super-row (exact stage capacity)
   int64_t len_p90 = -1;                     // 90th percentile of the row lengths (ragged matrices only; lazily)
 
+  // CSR_BLOCK
+  int64_t block_cap = 0, block_max_rows = 0, n_blocks = 0;
+  int *d_blk_row = nullptr;
+
   // CSR_MERGE
   int64_t merge_tile = 0, merge_tiles = 0;
   int merge_ctas = 0;
@@ -138,7 +144,7 @@ void free_device(hspmv_matrix *A) {
   free_pipe(A);
   void *ptrs[] = {A->d_rp, A->d_ci, A->d_val, A->d_x, A->d_y, A->d_tmp, A->d_sr, A->d_ssr,
                   A->d_sr_e, A->d_perm, A->d_bin_rows, A->d_long_seg, A->d_long_ptr, A->d_long_partial,
-                  A->d_tile_row, A->d_carry_row,
+                  A->d_tile_row, A->d_carry_row, A->d_blk_row,
                   A->d_carry_val, A->d_flush};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -564,6 +570,66 @@ int run_csrk(hspmv_matrix *A, bool stream_mode, const T *x, T *y, cudaStream_t s
   return HSPMV_OK;
 }
 
+// CSR_BLOCK: one CTA per row block of <= cap nonzeros, products staged in shared memory (kernels.cuh)
+template <typename T, int VEC>
+int launch_csr_block(hspmv_matrix *A, int cap, size_t smem, const T *x, T *y, cudaStream_t st) {
+  auto kern = hspmv::csr_block_kernel<T, VEC, 256>;
+  static size_t configured[64] = {0};
+  size_t &have = configured[A->dev.device & 63];
+  if (smem > have) {
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    have = smem;
+  }
+  kern<<<(int)A->n_blocks, 256, smem, st>>>((int)A->n_blocks, cap, A->d_blk_row, A->d_rp, A->d_ci, (const T *)A->d_val, x, y);
+  LAUNCHED();
+  return HSPMV_OK;
+}
+
+template <typename T>
+int run_csr_block(hspmv_matrix *A, const T *x, T *y, cudaStream_t st) {
+  const double mean = A->m ? (double)A->nnz / (double)A->m : 0.0;
+  int64_t cap = A->opt[HSPMV_OPT_BLOCK_NNZ];
+  if (cap <= 0) cap = 2048;
+  cap = (cap + 3) & ~(int64_t)3;
+  int64_t max_rows = cap; // a block never needs more row slots than nonzero slots + empty rows; bounded for shared memory
+  if (max_rows > 2048) max_rows = 2048;
+  if (A->block_cap != cap || A->block_max_rows != max_rows || !A->d_blk_row) {
+    std::vector<int32_t> rp, blk;
+    int rc = ensure_host_rp(A, rp);
+    if (rc) return rc;
+    hspmv::block_rows(A->m, rp.data(), cap, max_rows, blk);
+    if (A->d_blk_row) cudaFree(A->d_blk_row);
+    A->d_blk_row = nullptr;
+    CU(cudaMalloc(&A->d_blk_row, blk.size() * 4 + 16));
+    CU(cudaMemcpy(A->d_blk_row, blk.data(), blk.size() * 4, cudaMemcpyHostToDevice));
+    A->n_blocks = (int64_t)blk.size() - 1;
+    A->block_cap = cap;
+    A->block_max_rows = max_rows;
+  }
+  if (A->n_blocks <= 0) return HSPMV_OK;
+  int vec = (int)A->opt[HSPMV_OPT_VEC];
+  if (vec <= 0) { // lanes per row in the reduction phase: a lane adds <= 8 products of a typical row
+    vec = 1;
+    while (vec < 32 && mean / vec > 8.0) vec <<= 1;
+  }
+  const size_t smem = (size_t)(cap + 8) * sizeof(T) + (size_t)(max_rows + 1) * 4;
+  int rc;
+  switch (vec) {
+  case 1: rc = launch_csr_block<T, 1>(A, (int)cap, smem, x, y, st); break;
+  case 2: rc = launch_csr_block<T, 2>(A, (int)cap, smem, x, y, st); break;
+  case 4: rc = launch_csr_block<T, 4>(A, (int)cap, smem, x, y, st); break;
+  case 8: rc = launch_csr_block<T, 8>(A, (int)cap, smem, x, y, st); break;
+  case 16: rc = launch_csr_block<T, 16>(A, (int)cap, smem, x, y, st); break;
+  default: rc = launch_csr_block<T, 32>(A, (int)cap, smem, x, y, st); vec = 32; break;
+  }
+  if (rc) return rc;
+  char name[128];
+  std::snprintf(name, sizeof(name), "csr_block<%s,vec=%d> cap=%d blocks=%lld threads=256", sizeof(T) == 8 ? "f64" : "f32", vec, (int)cap,
+                (long long)A->n_blocks);
+  A->last_kernel = name;
+  return HSPMV_OK;
+}
+
 template <typename T>
 int run_csr_merge(hspmv_matrix *A, const T *x, T *y, cudaStream_t st) {
   int64_t tile = A->opt[HSPMV_OPT_MERGE_TILE];
@@ -670,6 +736,7 @@ int dispatch(hspmv_matrix *A, int algo, const void *dx, void *dy, cudaStream_t s
   case HSPMV_ALGO_CSR_VECTOR: rc = run_csr_vector<T>(A, x, y, st, row_lo, row_hi); break;
   case HSPMV_ALGO_CSR_STREAM: rc = run_csrk<T>(A, true, x, y, st, row_lo, row_hi); break;
   case HSPMV_ALGO_CSR_MERGE: rc = run_csr_merge<T>(A, x, y, st); break;
+  case HSPMV_ALGO_CSR_BLOCK: rc = run_csr_block<T>(A, x, y, st); break;
   case HSPMV_ALGO_CSRK: rc = run_csrk<T>(A, false, x, y, st); break;
   default: return fail(HSPMV_EINVAL, "unknown algo");
   }
@@ -981,6 +1048,7 @@ int finish_csrk(hspmv_matrix *A, int k, std::vector<u32> &perm, std::vector<u32>
   A->n_ssr = k == 3 ? (int64_t)A->h_ssr.size() - 1 : 0;
   A->bins_ready = false;
   A->merge_tile = 0;
+  A->block_cap = 0;
   free_pipe(A);
   hspmv::row_stats(A->m, A->h_rp.data(), A->stats);
   A->stats_ready = true;
@@ -1227,6 +1295,8 @@ int hspmv_fill_x_segments(void *d_x, int dtype, int n_seg, const int64_t *lo, co
 // ---- hot path ---------------------------------------------------------------------------
 int hspmv_set_option(hspmv_matrix *A, int option, int64_t value) {
   if (!A || option < 1 || option > 15) return fail(HSPMV_EINVAL, "bad option");
+  if (option == HSPMV_OPT_BLOCK_NNZ && value != 0 && (value < 256 || value > 16384))
+    return fail(HSPMV_EINVAL, "HSPMV_OPT_BLOCK_NNZ must be 0 or within [256, 16384]");
   if (option == HSPMV_OPT_VEC && value != 0 && (value < 1 || value > 32 || (value & (value - 1))))
     return fail(HSPMV_EINVAL, "HSPMV_OPT_VEC must be 0 or a power of two <= 32");
   A->opt[option] = value;
@@ -1842,6 +1912,15 @@ int hspmv_merge_tile_rows_device(const hspmv_matrix *A, int64_t *tile, int64_t *
   if (tile) *tile = A->merge_tile;
   if (n_tiles) *n_tiles = A->merge_tiles;
   if (tile_row) CU(cudaMemcpy(tile_row, A->d_tile_row, (size_t)(A->merge_tiles + 1) * 4, cudaMemcpyDeviceToHost));
+  return HSPMV_OK;
+}
+// row blocks of the CSR_BLOCK path, host rule: blk_row has room for m + 2 entries; *n_blocks out
+int hspmv_block_rows_host(int64_t m, const int32_t *row_ptr, int64_t cap, int64_t max_rows, int32_t *blk_row, int64_t *n_blocks) {
+  if (!row_ptr || !blk_row || !n_blocks || cap <= 0 || max_rows <= 0) return fail(HSPMV_EINVAL, "bad arguments");
+  std::vector<int32_t> b;
+  hspmv::block_rows(m, row_ptr, cap, max_rows, b);
+  std::memcpy(blk_row, b.data(), b.size() * 4);
+  *n_blocks = (int64_t)b.size() - 1;
   return HSPMV_OK;
 }
 // row bins of the CSR_VECTOR path, host (for the bit-exactness tests): rows[m], bin_ptr[9]

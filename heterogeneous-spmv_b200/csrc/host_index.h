@@ -70,6 +70,11 @@ void bin_rows(int64_t m, const int32_t *rp, std::vector<int32_t> &rows, int64_t 
 // row that owns nonzero t*tile; tile_row[n_tiles] = m
 void tile_rows(int64_t m, const int32_t *rp, int64_t tile, std::vector<int32_t> &tile_row);
 
+// CSR_BLOCK row blocks: consecutive rows are gathered into a block while the block's nonzeros stay <= cap and its
+// rows <= max_rows; a row that alone exceeds cap is a block of its own.  blk_row[b] = first row of block b,
+// blk_row[n_blocks] = m (oracle/partition_oracle.py: block_rows restates the rule).
+void block_rows(int64_t m, const int32_t *rp, int64_t cap, int64_t max_rows, std::vector<int32_t> &blk_row);
+
 // ---- heuristics.cpp
 int auto_params(int64_t nnz, int64_t n_rows, int arch, int sizes[2], int *veclevel, int *block_dim_y);
 

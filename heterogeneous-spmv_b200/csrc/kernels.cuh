@@ -246,6 +246,93 @@ __global__ void zero_rows_kernel(int64_t n_rows, const int *__restrict__ row_lis
 }
 
 // ------------------------------------------------------------------------------------------
+// CSR_BLOCK: row blocks sized by nonzero count, products staged in shared memory
+// ------------------------------------------------------------------------------------------
+// For matrices that live in L2 (a launch lasts tens of microseconds: the persistent TMA ring's
+// prologue and its one-tile-per-warp latency chain are most of that) and for ragged rows (no
+// padding of every row to a common slot count).  blk_row[b] .. blk_row[b+1] is a block of
+// consecutive rows with at most `cap` nonzeros (host_index.h: block_rows), one CTA each, grid =
+// number of blocks, many CTAs per SM -- latency is hidden by occupancy, not by a pipeline:
+//   phase 1  the block's nonzero range is read with coalesced 128-bit loads, every thread keeps
+//            4 x gathers in flight per step, the products go to shared memory;
+//   phase 2  VEC lanes per row add the row's products from shared memory (stride VEC), warp
+//            shuffle finishes the sum.
+// A row longer than `cap` is a block of its own and never touches shared memory for products:
+// every thread adds its strided share in a register, then one block reduction.
+// The aligned quads that straddle the ends of the block's range multiply entries of the
+// neighbouring rows (or the zero pad) by valid x entries; those products are never added.
+template <typename T, int VEC, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+csr_block_kernel(int n_blocks, int cap, const int *__restrict__ blk_row, const int *__restrict__ rp,
+                 const int *__restrict__ ci, const T *__restrict__ val, const T *__restrict__ x, T *__restrict__ y) {
+  extern __shared__ __align__(16) unsigned char block_smem[];
+  T *prod = reinterpret_cast<T *>(block_smem);                 // cap + 8 products
+  int *s_rp = reinterpret_cast<int *>(prod + cap + 8);         // row pointers of the block
+  __shared__ T warp_part[THREADS / 32];
+  const int b = blockIdx.x;
+  const int r0 = blk_row[b], r1 = blk_row[b + 1];
+  const int rows = r1 - r0;
+  const int64_t e0 = rp[r0], e1 = rp[r1];
+  const int64_t ea = e0 & ~(int64_t)3;
+  if (rows == 1 && e1 - ea > cap) { // one long row: register accumulation + block reduction
+    T acc = 0;
+    for (int64_t j = ea + 4 * (int64_t)threadIdx.x; j < e1; j += 4 * THREADS) {
+      const int4 c = ld_stream(reinterpret_cast<const int4 *>(ci + j));
+      const Quad<T> q = load_quad(val, j);
+      const T x0 = __ldg(x + c.x), x1 = __ldg(x + c.y), x2 = __ldg(x + c.z), x3 = __ldg(x + c.w);
+      if (j >= e0 && j + 3 < e1) {
+        acc += q.v[0] * x0;
+        acc += q.v[1] * x1;
+        acc += q.v[2] * x2;
+        acc += q.v[3] * x3;
+      } else {
+        if (j >= e0 && j < e1) acc += q.v[0] * x0;
+        if (j + 1 >= e0 && j + 1 < e1) acc += q.v[1] * x1;
+        if (j + 2 >= e0 && j + 2 < e1) acc += q.v[2] * x2;
+        if (j + 3 >= e0 && j + 3 < e1) acc += q.v[3] * x3;
+      }
+    }
+    acc = group_sum<T, 32>(acc);
+    if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      T s = 0;
+#pragma unroll
+      for (int w = 0; w < THREADS / 32; ++w) s += warp_part[w];
+      y[r0] = s;
+    }
+    return;
+  }
+  for (int i = threadIdx.x; i <= rows; i += THREADS) s_rp[i] = rp[r0 + i] - (int)ea;
+  // phase 1
+  for (int64_t j = ea + 4 * (int64_t)threadIdx.x; j < e1; j += 4 * THREADS) {
+    const int4 c = ld_stream(reinterpret_cast<const int4 *>(ci + j));
+    const Quad<T> q = load_quad(val, j);
+    const T x0 = __ldg(x + c.x), x1 = __ldg(x + c.y), x2 = __ldg(x + c.z), x3 = __ldg(x + c.w);
+    T *o = prod + (j - ea);
+    o[0] = q.v[0] * x0;
+    o[1] = q.v[1] * x1;
+    o[2] = q.v[2] * x2;
+    o[3] = q.v[3] * x3;
+  }
+  __syncthreads();
+  // phase 2 (warp-uniform trip count: the shuffles name the whole warp)
+  const int sub = threadIdx.x & (VEC - 1);
+  for (int rb = (threadIdx.x & ~31) / VEC; rb < rows; rb += THREADS / VEC) {
+    const int r = rb + (threadIdx.x & 31) / VEC;
+    int rs = 0, re = 0;
+    if (r < rows) {
+      rs = s_rp[r];
+      re = s_rp[r + 1];
+    }
+    T acc = 0;
+    for (int j = rs + sub; j < re; j += VEC) acc += prod[j];
+    acc = group_sum<T, VEC>(acc);
+    if (r < rows && sub == 0) y[r0 + r] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // CSR-k, TMA-staged super-rows
 // ------------------------------------------------------------------------------------------
 template <typename T> struct CsrkParams {
@@ -600,7 +687,8 @@ __global__ void __launch_bounds__(512, 1) csrk_tma_kernel(const CsrkParams<T> p)
       // next tile's copies fly during the x gathers instead of after them), and the gathers and
       // FMAs run from registers.  The rare row that is longer has its excess consumed straight
       // from the stage before the release (one extra round of gathers for that tile only).
-      const bool single = (r1 - r0) <= 32 / VEC;
+      // (halo tiles -- a few per launch -- take the csrk_rows<COH> path below, so that this path keeps one gather flavour)
+      const bool single = (r1 - r0) <= 32 / VEC && !halo_tile;
       int rs = 0, re = 0;
       const int r = r0 + gid;
       const bool active = r < r1;
@@ -627,7 +715,7 @@ __global__ void __launch_bounds__(512, 1) csrk_tma_kernel(const CsrkParams<T> p)
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              const T xg = halo_tile ? ld_x<true>(p.x + cx[u]) : ld_x<false>(p.x + cx[u]);
+              const T xg = __ldg(p.x + cx[u]);
               if (j + u * VEC < re) acc += vx[u] * xg; // predicated: an idle slot must not meet an inf in x
             }
           }
@@ -667,13 +755,8 @@ __global__ void __launch_bounds__(512, 1) csrk_tma_kernel(const CsrkParams<T> p)
         advance(st);
         released = true;
         T xv[NS];
-        if (halo_tile) {
 #pragma unroll
-          for (int u = 0; u < NS; ++u) xv[u] = ld_x<true>(p.x + c[u]);
-        } else {
-#pragma unroll
-          for (int u = 0; u < NS; ++u) xv[u] = ld_x<false>(p.x + c[u]);
-        }
+        for (int u = 0; u < NS; ++u) xv[u] = __ldg(p.x + c[u]);
 #pragma unroll
         for (int u = 0; u < NS; ++u) acc += v[u] * xv[u]; // same order as csrk_rows: a row's sum does not depend on the tiling
         if (re <= rs) acc = (T)0; // empty row: its idle slots multiplied 0 by x[0], which may be inf

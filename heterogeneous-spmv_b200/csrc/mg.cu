@@ -32,6 +32,7 @@ namespace {
 thread_local std::string g_mg_err;
 int mg_fail(int code, const std::string &msg) {
   g_mg_err = msg;
+  cudaGetLastError(); // a failed runtime call must not be found again by the next cudaGetLastError() of the library
   return code;
 }
 #define MGCU(call)                                                                              \
@@ -175,7 +176,7 @@ int build_shards(hspmv_mg *M, hspmv_matrix *full, const int *devices, int n_dev)
       if (a != b || a.size() > 32) M->replicated = true;
     }
   }
-  if (M->replicated)
+  if (M->replicated || n_dev == 1) // the device holds all of x
     for (Shard &sh : M->s) {
       sh.cmin = 0;
       sh.cmax = M->n - 1;

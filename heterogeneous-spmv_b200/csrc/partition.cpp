@@ -84,6 +84,20 @@ void bin_rows(int64_t m, const int32_t *rp, std::vector<int32_t> &rows, int64_t 
   for (int64_t r = 0; r < m; ++r) rows[(size_t)cur[bin_of_len((int64_t)rp[r + 1] - rp[r])]++] = (int32_t)r;
 }
 
+void block_rows(int64_t m, const int32_t *rp, int64_t cap, int64_t max_rows, std::vector<int32_t> &blk_row) {
+  blk_row.clear();
+  blk_row.push_back(0);
+  int64_t start = 0;
+  for (int64_t r = 0; r < m; ++r) {
+    // would row r still fit into the block that starts at `start`?
+    if (r > start && ((int64_t)rp[r + 1] - rp[start] > cap || r - start >= max_rows)) {
+      blk_row.push_back((int32_t)r);
+      start = r;
+    }
+  }
+  if (m > 0) blk_row.push_back((int32_t)m);
+}
+
 void tile_rows(int64_t m, const int32_t *rp, int64_t tile, std::vector<int32_t> &tile_row) {
   const int64_t nnz = rp[m];
   const int64_t n_tiles = (nnz + tile - 1) / tile;

@@ -44,7 +44,9 @@ enum {
   HSPMV_ALGO_CSR_VECTOR = 1, /* row-length binned: sub-warp vector-per-row (2..32 lanes), block-per-row */
   HSPMV_ALGO_CSR_STREAM = 2, /* fixed-row tiles staged by TMA bulk copies (CSR-k engine, virtual super-rows) */
   HSPMV_ALGO_CSR_MERGE = 3,  /* nnz-balanced split with carry fix-up (power-law matrices) */
-  HSPMV_ALGO_CSRK = 4        /* SSR -> CTA, SR -> warp, row -> lane(s), TMA-staged super-rows (needs build_csrk) */
+  HSPMV_ALGO_CSRK = 4,       /* SSR -> CTA, SR -> warp, row -> lane(s), TMA-staged super-rows (needs build_csrk) */
+  HSPMV_ALGO_CSR_BLOCK = 5   /* row blocks of <= HSPMV_OPT_BLOCK_NNZ nonzeros, one CTA each, products staged in shared memory:
+                                matrices that live in L2 (tens of microseconds per launch) and ragged rows */
 };
 
 /* Tunables for hspmv_set_option (all optional; defaults come from the auto-tuner). */
@@ -61,6 +63,7 @@ enum {
   HSPMV_OPT_NO_PIPELINE = 11, /* 1: hspmv_spmv_host copies, computes, copies back strictly in sequence */
   HSPMV_OPT_TAIL = 13,        /* TMA kernels: masked gathers per lane per round (compiled: see csrc/csrk_variants.h); 0 = default */
   HSPMV_OPT_BANDK_HOST = 12,  /* 1: hspmv_build_csrk runs entirely on the host (default: coarse graph + reorderA in HBM) */
+  HSPMV_OPT_BLOCK_NNZ = 14,   /* CSR_BLOCK: nonzeros per row block (256..16384; 0 = 2048) */
   HSPMV_OPT_CHUNK = 10        /* TMA kernels: unmasked x gathers a lane keeps in flight per chunk; 0 = auto, < 0 = masked loop only */
 };
 
@@ -360,6 +363,10 @@ int hspmv_merge_tile_rows_device(const hspmv_matrix *A, int64_t *tile, int64_t *
 /* Smallest L such that at least pct % of the rows have <= L entries (the 90th percentile sizes the
  * masked kernel shape for ragged matrices). */
 int64_t hspmv_row_len_percentile_host(int64_t m, const int32_t *row_ptr, int pct);
+/* CSR_BLOCK row blocks: greedy runs of consecutive rows with <= cap nonzeros and <= max_rows rows (a longer row is
+ * alone); blk_row needs room for m + 2 entries. */
+int hspmv_block_rows_host(int64_t m, const int32_t *row_ptr, int64_t cap, int64_t max_rows, int32_t *blk_row,
+                          int64_t *n_blocks);
 /* CSR_VECTOR bins: rows[m] grouped by bin in ascending row order, bin_ptr[9]. */
 int hspmv_bin_rows_host(int64_t m, const int32_t *row_ptr, int32_t *rows, int64_t *bin_ptr);
 

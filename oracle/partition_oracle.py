@@ -113,3 +113,17 @@ def row_len_percentile(rp, pct):
         return 0
     need = (m * pct + 99) // 100
     return int(lens[need - 1]) if need > 0 else 0
+
+
+def block_rows(rp, cap, max_rows):
+    """CSR_BLOCK row blocks (csrc/partition.cpp:block_rows): greedy consecutive rows with <= cap nonzeros and
+    <= max_rows rows per block; a row longer than cap is alone in its block.  Returns blk_row (first rows + m)."""
+    m = len(rp) - 1
+    out, start = [0], 0
+    for r in range(m):
+        if r > start and (int(rp[r + 1]) - int(rp[start]) > cap or r - start >= max_rows):
+            out.append(r)
+            start = r
+    if m > 0:
+        out.append(m)
+    return np.asarray(out, dtype=np.int32)

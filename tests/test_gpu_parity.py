@@ -37,7 +37,7 @@ def check_csr(hs, oracle, gen, rp, ci, v, algos, x=None, opts=None, what=""):
 
 @pytest.mark.parametrize("dtype", DT, ids=DT_IDS)
 def test_csr_regular_matrices(dtype, hs, oracle, gen):
-    algos = [hs.ALGO_CSR_VECTOR, hs.ALGO_CSR_STREAM, hs.ALGO_CSR_MERGE, hs.ALGO_AUTO]
+    algos = [hs.ALGO_CSR_VECTOR, hs.ALGO_CSR_STREAM, hs.ALGO_CSR_MERGE, hs.ALGO_CSR_BLOCK, hs.ALGO_AUTO]
     for name, (rp, ci, v) in [("lap64rcm", gen.laplace2d_5pt(64, dtype=dtype, rcm=True, mode="varied")),
                               ("lap33", gen.laplace2d_5pt(33, dtype=dtype)),
                               ("st27_16", gen.stencil27(16, dtype=dtype, mode="varied")),
@@ -47,7 +47,7 @@ def test_csr_regular_matrices(dtype, hs, oracle, gen):
 
 @pytest.mark.parametrize("dtype", DT, ids=DT_IDS)
 def test_csr_ragged_empty_and_long_rows(dtype, hs, oracle, gen):
-    algos = [hs.ALGO_CSR_VECTOR, hs.ALGO_CSR_STREAM, hs.ALGO_CSR_MERGE, hs.ALGO_AUTO]
+    algos = [hs.ALGO_CSR_VECTOR, hs.ALGO_CSR_STREAM, hs.ALGO_CSR_MERGE, hs.ALGO_CSR_BLOCK, hs.ALGO_AUTO]
     check_csr(hs, oracle, gen, *gen.random_ragged(3000, max_len=70, dtype=dtype), algos, what="ragged")
     check_csr(hs, oracle, gen, *gen.random_ragged(257, max_len=257, dtype=dtype, empty_frac=0.5), algos, what="ragged-half-empty")
     check_csr(hs, oracle, gen, *gen.rmat(13, 8, dtype=dtype), algos, what="rmat13")
@@ -70,9 +70,13 @@ def test_csr_ragged_empty_and_long_rows(dtype, hs, oracle, gen):
     rp2 = np.concatenate([[0], np.cumsum(lens2)]).astype(np.int32)
     ci2 = np.concatenate([np.sort(rng.choice(n2, size=l, replace=False)) for l in lens2]).astype(np.int32)
     v2 = (rng.integers(1, 64, size=len(ci2)) / 64.0).astype(dtype)
-    check_csr(hs, oracle, gen, rp2, ci2, v2, [hs.ALGO_CSR_VECTOR, hs.ALGO_AUTO, hs.ALGO_CSR_MERGE], what="hub-rows")
+    check_csr(hs, oracle, gen, rp2, ci2, v2, [hs.ALGO_CSR_VECTOR, hs.ALGO_AUTO, hs.ALGO_CSR_MERGE, hs.ALGO_CSR_BLOCK], what="hub-rows")
     for vec in (1, 2, 4, 8, 16, 32):   # forced lane counts incl. mismatched ones
-        check_csr(hs, oracle, gen, rp, ci, v, [hs.ALGO_CSR_VECTOR, hs.ALGO_CSR_STREAM], opts={hs.OPT_VEC: vec}, what="long-rows vec=%d" % vec)
+        check_csr(hs, oracle, gen, rp, ci, v, [hs.ALGO_CSR_VECTOR, hs.ALGO_CSR_STREAM, hs.ALGO_CSR_BLOCK], opts={hs.OPT_VEC: vec}, what="long-rows vec=%d" % vec)
+    for cap in (256, 1024, 16384):     # CSR_BLOCK: block capacities below / above the long rows
+        check_csr(hs, oracle, gen, rp, ci, v, [hs.ALGO_CSR_BLOCK], opts={hs.OPT_BLOCK_NNZ: cap}, what="long-rows block cap=%d" % cap)
+        check_csr(hs, oracle, gen, *gen.random_ragged(3000, max_len=70, dtype=dtype), [hs.ALGO_CSR_BLOCK], opts={hs.OPT_BLOCK_NNZ: cap},
+                  what="ragged block cap=%d" % cap)
     # masked single-round shapes (HSPMV_OPT_TAIL), one row per lane group and several
     for vec, tail, rpt in ((1, 12, 32), (2, 12, 16), (4, 12, 8), (4, 14, 24), (8, 8, 4), (8, 12, 12), (16, 8, 2), (32, 4, 1)):
         check_csr(hs, oracle, gen, rp, ci, v, [hs.ALGO_CSR_STREAM],
@@ -85,7 +89,7 @@ def test_csr_ragged_empty_and_long_rows(dtype, hs, oracle, gen):
 
 @pytest.mark.parametrize("dtype", DT, ids=DT_IDS)
 def test_csr_degenerate_shapes(dtype, hs, oracle, gen):
-    algos = [hs.ALGO_CSR_VECTOR, hs.ALGO_CSR_STREAM, hs.ALGO_CSR_MERGE, hs.ALGO_AUTO]
+    algos = [hs.ALGO_CSR_VECTOR, hs.ALGO_CSR_STREAM, hs.ALGO_CSR_MERGE, hs.ALGO_CSR_BLOCK, hs.ALGO_AUTO]
     # 1x1, single dense row, all-empty matrix, diagonal
     check_csr(hs, oracle, gen, np.array([0, 1], np.int32), np.array([0], np.int32), np.array([2.5], dtype), algos, what="1x1")
     n = 300

@@ -401,3 +401,21 @@ def test_bins_and_tiles_bit_exact(hs, gen):
     for rp in (gen.random_ragged(5000, max_len=70)[0], gen.stencil27(9)[0], rp):
         for tile in (4, 64, 4096):
             assert np.array_equal(hs.merge_tile_rows_host(rp, tile), PO.tile_rows(rp, tile))
+
+
+def test_block_rows_bit_exact(hs, gen):
+    """CSR_BLOCK row blocks: library rule == oracle/partition_oracle.py:block_rows, and the invariants the kernel needs."""
+    lens = np.array([0, 0, 5, 300, 1, 2, 3, 0, 700, 4, 4, 4, 4, 4, 4, 0], dtype=np.int64)
+    rps = [np.concatenate([[0], np.cumsum(lens)]).astype(np.int32), gen.random_ragged(5000, max_len=70)[0], gen.stencil27(9)[0],
+           gen.rmat(10, 8)[0], np.zeros(1, np.int32), np.zeros(8, np.int32)]
+    for rp in rps:
+        m = len(rp) - 1
+        for cap, max_rows in ((256, 256), (2048, 2048), (64, 3), (16384, 2048)):
+            b = hs.block_rows_host(rp, cap, max_rows)
+            assert np.array_equal(b, PO.block_rows(rp, cap, max_rows)), (m, cap, max_rows)
+            if m == 0:
+                continue
+            assert b[0] == 0 and b[-1] == m and np.all(np.diff(b) > 0)
+            nnz = rp[b[1:]].astype(np.int64) - rp[b[:-1]]
+            rows = np.diff(b)
+            assert np.all((nnz <= cap) | (rows == 1)) and np.all(rows <= max_rows)

@@ -22,9 +22,17 @@ ap.add_argument("--opts", default="")
 ap.add_argument("--k", type=int, default=0)
 ap.add_argument("--sizes", default="32,8")
 ap.add_argument("--iters", type=int, default=5)
+ap.add_argument("--matrix", default="stencil", help="stencil (with --g/--kind) | cfg1 | cfg3 | cfg4 (BASELINE configs at full size)")
 a = ap.parse_args()
 dt = np.float64 if a.dtype == "f64" else np.float32
-A = hs.Matrix.stencil(a.kind, a.g, dt, 0)
+OPT.update({"chunk": hs.OPT_CHUNK, "tail": hs.OPT_TAIL})
+if a.matrix == "stencil":
+    A = hs.Matrix.stencil(a.kind, a.g, dt, 0)
+else:
+    from heterogeneous_spmv_b200 import generators as G
+    rp, ci, v = {"cfg1": lambda: G.laplace2d_5pt(1000, rcm=True), "cfg3": lambda: G.shell_blocks(1_500_000),
+                 "cfg4": lambda: G.rmat_torch(24, 16)}[a.matrix]()
+    A = hs.Matrix.from_csr(rp, ci, v.astype(dt), keep_host=a.k >= 2)
 if a.k >= 2:
     A.build_csrk(a.k, [int(t) for t in a.sizes.split(",")])
 A.fill_x_synthetic(0)
