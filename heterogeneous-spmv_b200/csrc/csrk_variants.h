@@ -40,9 +40,21 @@ template <typename T> int launch_csrk_group2(const CsrkParams<T> &p, int grid, i
 template <typename T> int launch_csrk_group4(const CsrkParams<T> &p, int grid, int warps, size_t smem, cudaStream_t st, int device, const CsrkVariant &v);
 template <typename T> int launch_csrk_group8(const CsrkParams<T> &p, int grid, int warps, size_t smem, cudaStream_t st, int device, const CsrkVariant &v);
 
+// the same groups with the halo support compiled in (csrk_inst_halo_*.cu)
+template <typename T> int launch_csrk_halo_group1(const CsrkParams<T> &p, int grid, int warps, size_t smem, cudaStream_t st, int device, const CsrkVariant &v);
+template <typename T> int launch_csrk_halo_group2(const CsrkParams<T> &p, int grid, int warps, size_t smem, cudaStream_t st, int device, const CsrkVariant &v);
+template <typename T> int launch_csrk_halo_group4(const CsrkParams<T> &p, int grid, int warps, size_t smem, cudaStream_t st, int device, const CsrkVariant &v);
+template <typename T> int launch_csrk_halo_group8(const CsrkParams<T> &p, int grid, int warps, size_t smem, cudaStream_t st, int device, const CsrkVariant &v);
+
 template <typename T>
 inline int launch_csrk_variant(const CsrkParams<T> &p, int grid, int warps, size_t smem, cudaStream_t st,
                                int device, const CsrkVariant &v) {
+  if (p.n_ranges > 1 || p.n_wait > 0) { // hspmv_spmv_halo
+    if (v.vec == 1) return launch_csrk_halo_group1<T>(p, grid, warps, smem, st, device, v);
+    if (v.vec == 2) return launch_csrk_halo_group2<T>(p, grid, warps, smem, st, device, v);
+    if (v.vec == 4) return launch_csrk_halo_group4<T>(p, grid, warps, smem, st, device, v);
+    return launch_csrk_halo_group8<T>(p, grid, warps, smem, st, device, v);
+  }
   if (v.vec == 1) return launch_csrk_group1<T>(p, grid, warps, smem, st, device, v);
   if (v.vec == 2) return launch_csrk_group2<T>(p, grid, warps, smem, st, device, v);
   if (v.vec == 4) return launch_csrk_group4<T>(p, grid, warps, smem, st, device, v);
@@ -63,9 +75,9 @@ static const int kNumCsrkProdVariants = (int)(sizeof(kCsrkProdVariants) / sizeof
 // returns 0, a cudaError_t, or -1 (no such variant)
 template <typename T> int launch_csrk_prod(const CsrkParams<T> &p, int grid, int warps, size_t smem, cudaStream_t st, int device, int vec, int u);
 
-template <typename T, int VEC, int MAIN, int TAIL>
+template <typename T, int VEC, int MAIN, int TAIL, bool HALO = false>
 inline int launch_csrk_one(const CsrkParams<T> &p, int grid, int warps, size_t smem, cudaStream_t st, int device) {
-  auto kern = csrk_tma_kernel<T, VEC, MAIN, TAIL>;
+  auto kern = csrk_tma_kernel<T, VEC, MAIN, TAIL, HALO>;
   static size_t configured[64] = {0}; // per device: opt-in shared memory already granted
   size_t &have = configured[device & 63];
   if (smem > have) {

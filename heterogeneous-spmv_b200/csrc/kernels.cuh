@@ -528,7 +528,9 @@ static __device__ __noinline__ void csrk_rows_halo_direct(int r0, int r1, const 
   csrk_rows<T, VEC, MAIN, TAIL, int64_t, true>(r0, r1, rp, 0, ci, val, (int64_t)0, x, y, lane);
 }
 
-template <typename T, int VEC, int MAIN, int TAIL>
+// HALO = false: the kernel every single-GPU launch runs; it contains no trace of the halo support.  HALO = true
+// (hspmv_spmv_halo): up to three row ranges, the in-kernel flag wait and L2 gathers for the halo tiles.
+template <typename T, int VEC, int MAIN, int TAIL, bool HALO>
 __global__ void __launch_bounds__(512, 1) csrk_tma_kernel(const CsrkParams<T> p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
@@ -576,7 +578,7 @@ __global__ void __launch_bounds__(512, 1) csrk_tma_kernel(const CsrkParams<T> p)
     SrMeta mt;
     if (p.k == 1) {
       int64_t r0, hi;
-      if (sr < p.tiles_before[1]) {          // (warp-uniform branches; a single range always takes the first)
+      if (!HALO || sr < p.tiles_before[1]) { // (warp-uniform branches; a single range always takes the first)
         r0 = p.range_lo[0] + sr * p.rows_per_tile;
         hi = p.range_hi[0];
       } else if (sr < p.tiles_before[2]) {
@@ -672,7 +674,7 @@ __global__ void __launch_bounds__(512, 1) csrk_tma_kernel(const CsrkParams<T> p)
   // Tiles come to a warp in increasing index order, interior range first: the halo wait sits in
   // front of the (wait_at)-th tile this warp consumes; -1 = never.
   int consumed = 0, wait_at = -1;
-  if (p.k == 1 && p.n_wait > 0) {
+  if (HALO && p.k == 1 && p.n_wait > 0) {
     const int64_t gw = (int64_t)blockIdx.x * W + w, GW = (int64_t)gridDim.x * W;
     const int64_t n_int = p.tiles_before[1] > gw ? (p.tiles_before[1] - gw + GW - 1) / GW : 0;
     wait_at = (int)n_int;
@@ -686,9 +688,9 @@ __global__ void __launch_bounds__(512, 1) csrk_tma_kernel(const CsrkParams<T> p)
     unsigned char *base = ring + (size_t)st * stage_bytes;
     const int *meta = reinterpret_cast<const int *>(base);
     const int r0 = meta[0], r1 = meta[1], e0 = meta[2], e1m = meta[3];
-    if (consumed == wait_at) halo_spin_wait(p.wait_flags, p.n_wait, p.wait_step, p.timed_out, lane);
-    const bool halo_tile = wait_at >= 0 && consumed >= wait_at; // warp-uniform: this tile gathers from the halo
-    ++consumed;
+    if (HALO && consumed == wait_at) halo_spin_wait(p.wait_flags, p.n_wait, p.wait_step, p.timed_out, lane);
+    const bool halo_tile = HALO && wait_at >= 0 && consumed >= wait_at; // warp-uniform: this tile gathers from the halo
+    if (HALO) ++consumed;
     bool released = false;
     if (e1m >= 0) {
       const int *rp_w = reinterpret_cast<const int *>(base + 16);
@@ -953,18 +955,18 @@ __global__ void __launch_bounds__(512, 1) csrk_prod_kernel(const CsrkParams<T> p
       const int o0 = e0 - (e0 & ~3), o1 = e1m - (e0 & ~3); // the tile's entries sit at stage offsets [o0, o1)
       // row offsets relative to the tile's first entry, next to the product scratch
       for (int i = lane; i <= rows; i += 32) srp[i] = rp_w[i + (r0 - (r0 & ~3))] - e0;
-      // phase 1, chunks of 32 * U entries
-      for (int cb = o0; cb < o1; cb += 32 * U) {
+      // phase 1: chunks of 32 * U entries, then what is left in chunks of 32 * 2 (at most one of them is masked), so
+      // that a tile costs ceil(entries / 64) * 2 slots per lane at most, not a multiple of U
+      const int full_end = o0 + ((o1 - o0) / (32 * U)) * (32 * U);
+      for (int cb = o0; cb < full_end; cb += 32 * U) {
         int c[U];
         T v[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int j = cb + lane + 32 * u;
-          const int jc = j < o1 ? j : o1 - 1; // a slot past the end re-reads the tile's last entry (its product is not stored)
-          c[u] = ci_w[jc];
-          v[u] = va_w[jc];
+          c[u] = ci_w[cb + lane + 32 * u];
+          v[u] = va_w[cb + lane + 32 * u];
         }
-        if (cb + 32 * U >= o1) { // last chunk: every lane has what it needs from the stage
+        if (cb + 32 * U >= o1) { // that was the whole tile: every lane has what it needs from the stage
           __syncwarp();
           advance(st);
         }
@@ -972,9 +974,32 @@ __global__ void __launch_bounds__(512, 1) csrk_prod_kernel(const CsrkParams<T> p
 #pragma unroll
         for (int u = 0; u < U; ++u) xv[u] = __ldg(p.x + c[u]);
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int j = cb + lane + 32 * u;
-          if (j < o1) prod[j - o0] = v[u] * xv[u];
+        for (int u = 0; u < U; ++u) prod[cb - o0 + lane + 32 * u] = v[u] * xv[u];
+      }
+      if (full_end < o1) {
+        constexpr int R = U - 1 > 0 ? U - 1 : 1; // the remainder is < 32 * U entries: at most U - 1 full slots + one masked
+        int c[R + 1];
+        T v[R + 1];
+#pragma unroll
+        for (int u = 0; u <= R; ++u) {
+          const int j = full_end + lane + 32 * u;
+          const int jc = j < o1 ? j : o1 - 1; // a slot past the end re-reads the tile's last entry (its product is not stored)
+          c[u] = 0;
+          v[u] = (T)0;
+          if (full_end + 32 * u < o1) { // warp-uniform: slots that are entirely past the end cost nothing
+            c[u] = ci_w[jc];
+            v[u] = va_w[jc];
+          }
+        }
+        __syncwarp();
+        advance(st);
+#pragma unroll
+        for (int u = 0; u <= R; ++u) {
+          const int j = full_end + lane + 32 * u;
+          if (full_end + 32 * u < o1) {
+            const T xg = __ldg(p.x + c[u]);
+            if (j < o1) prod[j - o0] = v[u] * xg;
+          }
         }
       }
       __syncwarp(); // products and row offsets visible to the whole warp
