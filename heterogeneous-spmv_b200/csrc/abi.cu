@@ -419,27 +419,8 @@ int run_csrk(hspmv_matrix *A, bool stream_mode, const T *x, T *y, cudaStream_t s
   // masked round of `tail` gathers per lane that covers the 90th-percentile row is 40 % faster
   // (profiles/r1_sweep_ragged_cfg3.jsonl), with one row per lane group per tile so that the
   // register-resident single-pass path applies.
-  const bool ragged_rows = (double)max_len > mean * 1.15 + 1.0;
-  // Product-staging flavour (csrk_prod_kernel): nonzeros taken lane-strided whatever the row lengths, row sums from a
-  // per-warp scratch.  HSPMV_OPT_PROD: 1 = always, -1 = never, 0 = for ragged rows (not under a halo wait: that kernel
-  // takes one row range).
-  const int64_t prod_opt = A->opt[HSPMV_OPT_PROD];
-  const bool prod = !halo && (prod_opt > 0 || (prod_opt == 0 && ragged_rows && chunk == 0 && tail == 0));
-  int prod_u = 8;
-  const bool ragged = !prod && vec <= 0 && chunk == 0 && tail == 0 && ragged_rows;
+  const bool ragged = vec <= 0 && chunk == 0 && tail == 0 && (double)max_len > mean * 1.15 + 1.0;
   int ragged_rpt = 0;
-  if (prod) {
-    if (tail > 0) prod_u = (int)tail; // HSPMV_OPT_TAIL selects the chunk depth of this flavour (compiled: 6, 8, 12)
-    if (vec <= 0) { // lanes per row in the reduction phase: a lane adds <= ~10 products of a typical row
-      vec = 1;
-      while (vec < 32 && mean / vec > 10.0) vec <<= 1;
-    }
-    // a tile of about one chunk (32 * U entries), whole passes of the reduction phase
-    const int per_pass = 32 / vec;
-    int passes = (int)(32.0 * prod_u / ((mean > 1 ? mean : 1.0) * per_pass) + 0.5);
-    if (passes < 1) passes = 1;
-    ragged_rpt = passes * per_pass;
-  }
   if (ragged) {
     if (A->len_p90 < 0) {
       std::vector<int32_t> rp;
@@ -468,7 +449,7 @@ int run_csrk(hspmv_matrix *A, bool stream_mode, const T *x, T *y, cudaStream_t s
     chunk = per_lane <= 13 ? per_lane : (per_lane % 9 == 0 ? 9 : 8);
     if (chunk < 3) chunk = -1;
   }
-  const hspmv::CsrkVariant variant = prod ? hspmv::CsrkVariant{vec, 0, prod_u} : pick_variant(vec, chunk, tail);
+  const hspmv::CsrkVariant variant = pick_variant(vec, chunk, tail);
   int warps = (int)A->opt[HSPMV_OPT_WARPS];
   if (warps <= 0) warps = 16; // r1 sweep: occupancy matters more than stage size (profiles/)
   if (warps > 16) warps = 16;
@@ -557,7 +538,7 @@ int run_csrk(hspmv_matrix *A, bool stream_mode, const T *x, T *y, cudaStream_t s
   const size_t budget = A->dev.max_smem_optin - 1024;
   auto total = [&](int w, int cn, int cr) {
     return (((size_t)w * stages * 8 + 127) & ~(size_t)127) +
-           (size_t)w * (stages * hspmv::csrk_stage_bytes(cn, cr, sizeof(T)) + (prod ? hspmv::csrk_prod_scratch_bytes(cn, cr, sizeof(T)) : 0));
+           (size_t)w * stages * hspmv::csrk_stage_bytes(cn, cr, sizeof(T));
   };
   while (warps > 4 && total(warps, cap_nnz, cap_rows) > budget) --warps;
   while (total(warps, cap_nnz, cap_rows) > budget && cap_nnz > 64) cap_nnz = (cap_nnz * 3 / 4) & ~3;
@@ -580,17 +561,6 @@ int run_csrk(hspmv_matrix *A, bool stream_mode, const T *x, T *y, cudaStream_t s
   if (grid < 1) grid = 1;
 
   char name[192];
-  if (prod) {
-    const int rc = hspmv::launch_csrk_prod<T>(p, (int)grid, warps, smem, st, A->dev.device, vec, prod_u);
-    if (rc == -1) return fail(HSPMV_EINVAL, "no compiled csrk_prod variant for this (vec, chunk depth)");
-    if (rc) return fail(HSPMV_ECUDA, std::string("csrk_prod launch: ") + cudaGetErrorString((cudaError_t)rc));
-    LAUNCHED();
-    std::snprintf(name, sizeof(name), "csrk_prod<%s,vec=%d,u=%d> k=%d grid=%d warps=%d stages=%d cap_nnz=%d cap_rows=%d rpt=%d%s",
-                  sizeof(T) == 8 ? "f64" : "f32", vec, prod_u, p.k, (int)grid, warps, stages, cap_nnz, cap_rows, p.rows_per_tile,
-                  stream_mode ? " (CSR stream tiles)" : "");
-    A->last_kernel = name;
-    return HSPMV_OK;
-  }
   int rc = launch_csrk<T>(A, p, (int)grid, warps, smem, st, variant);
   if (rc) return rc;
   std::snprintf(name, sizeof(name), "csrk_tma<%s,vec=%d,main=%d,tail=%d> k=%d grid=%d warps=%d stages=%d cap_nnz=%d cap_rows=%d%s",
@@ -638,9 +608,9 @@ int run_csr_block(hspmv_matrix *A, const T *x, T *y, cudaStream_t st) {
   }
   if (A->n_blocks <= 0) return HSPMV_OK;
   int vec = (int)A->opt[HSPMV_OPT_VEC];
-  if (vec <= 0) { // lanes per row in the reduction phase: a lane adds <= 8 products of a typical row
+  if (vec <= 0) { // lanes per row in the reduction phase: a lane adds <= 24 products of a typical row (r2 sweep: fewer lanes win)
     vec = 1;
-    while (vec < 32 && mean / vec > 8.0) vec <<= 1;
+    while (vec < 32 && mean / vec > 24.0) vec <<= 1;
   }
   const size_t smem = (size_t)(cap + 8) * sizeof(T) + (size_t)(max_rows + 1) * 4;
   int rc;
@@ -760,6 +730,12 @@ int dispatch(hspmv_matrix *A, int algo, const void *dx, void *dy, cudaStream_t s
       // kernel (profiles/r1_configs_1to4_fullsize.jsonl); the random x gather (32 B sector per 8 B
       // used) caps that matrix near 0.4 of the roofline whatever the row split.
       algo = (A->stats[8] <= 8 * (mean + 1) + 64) ? HSPMV_ALGO_CSR_STREAM : HSPMV_ALGO_CSR_VECTOR;
+      // fp32, short or ragged rows: the streamed bytes halve but the TMA tile engine's per-tile instruction cost does
+      // not, and the row-block kernel (products staged in shared memory, occupancy instead of a pipeline) is 8-25 %
+      // faster (profiles/r2_sweep_block_cfg1to4.jsonl: cfg1 15.3 vs 17.3 us, cfg3 95 vs 120 us; fp64 and the 27-point
+      // stencil stay with the tile engine)
+      if (algo == HSPMV_ALGO_CSR_STREAM && !ranged && sizeof(T) == 4 && (mean < 8.0 || (double)A->stats[8] > mean * 1.15 + 1.0))
+        algo = HSPMV_ALGO_CSR_BLOCK;
     }
   }
   switch (algo) {

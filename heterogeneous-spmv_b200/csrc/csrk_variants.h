@@ -61,20 +61,6 @@ inline int launch_csrk_variant(const CsrkParams<T> &p, int grid, int warps, size
   return launch_csrk_group8<T>(p, grid, warps, smem, st, device, v);
 }
 
-// product-staging flavour (csrk_prod_kernel): X(lanes per row in the reduction phase, entries per lane per chunk)
-#define HSPMV_CSRK_PROD_VARIANTS(X) X(1, 8) X(2, 8) X(4, 8) X(8, 8) X(16, 8) X(32, 8) X(2, 12) X(4, 12) X(8, 12) X(4, 6) X(8, 6)
-struct CsrkProdVariant {
-  int vec, u;
-};
-static const CsrkProdVariant kCsrkProdVariants[] = {
-#define X(v, u) {v, u},
-    HSPMV_CSRK_PROD_VARIANTS(X)
-#undef X
-};
-static const int kNumCsrkProdVariants = (int)(sizeof(kCsrkProdVariants) / sizeof(kCsrkProdVariants[0]));
-// returns 0, a cudaError_t, or -1 (no such variant)
-template <typename T> int launch_csrk_prod(const CsrkParams<T> &p, int grid, int warps, size_t smem, cudaStream_t st, int device, int vec, int u);
-
 template <typename T, int VEC, int MAIN, int TAIL, bool HALO = false>
 inline int launch_csrk_one(const CsrkParams<T> &p, int grid, int warps, size_t smem, cudaStream_t st, int device) {
   auto kern = csrk_tma_kernel<T, VEC, MAIN, TAIL, HALO>;

@@ -799,237 +799,6 @@ __global__ void __launch_bounds__(512, 1) csrk_tma_kernel(const CsrkParams<T> p)
 }
 
 // ------------------------------------------------------------------------------------------
-// CSR-k / CSR tiles, product-staging flavour of the TMA engine (ragged rows)
-// ------------------------------------------------------------------------------------------
-// Same tiles, same per-warp TMA rings and metadata queue as csrk_tma_kernel; what differs is how a warp consumes a
-// staged tile.  csrk_tma_kernel gives every row a group of VEC lanes and every lane a fixed number of slots, which is
-// ideal when all rows have the same length (the stencils: every slot is used) and wasteful when they do not: on the
-// 35 +- 10 entries per row of config 3 the masked shape spends 48 slots per row and ~480 warp instructions per 8-row
-// tile (ncu: profiles/r2_ncu_cfg3_stream_before.*), i.e. it is bound by instruction issue, not by HBM.  Here
-//   phase 1  the tile's nonzeros are taken lane-strided, IGNORING the row structure: entry j belongs to lane j % 32.
-//            A lane reads U (column, value) pairs from the stage into registers, the warp hands the stage back to TMA
-//            (early release, as in the single-pass path), the U gathers fly together, the products go to a per-warp
-//            scratch in shared memory (written and read through the generic proxy only: no proxy fence);
-//   phase 2  VEC lanes per row add the row's products from the scratch (stride VEC) and finish with shuffles; the row
-//            offsets were copied next to the scratch before the stage was released.
-// No slot is wasted whatever the row lengths are (only the last chunk of a tile is masked).  Summation order: stride-VEC
-// partial sums, then the shuffle tree.  Oversized tiles take csrk_rows' direct path, as in csrk_tma_kernel.
-__host__ __device__ inline size_t csrk_prod_scratch_bytes(int cap_nnz, int cap_rows, size_t vsize) {
-  return (size_t)(cap_nnz + 8) * vsize + (size_t)(cap_rows + 8) * 4; // products | row offsets; multiples of 16 B
-}
-
-template <typename T, int VEC, int U>
-__global__ void __launch_bounds__(512, 1) csrk_prod_kernel(const CsrkParams<T> p) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31;
-  const int w = threadIdx.x >> 5;
-  const int W = blockDim.x >> 5;
-  const int S = p.stages;
-  const size_t stage_bytes = csrk_stage_bytes(p.cap_nnz, p.cap_rows, sizeof(T));
-  const size_t scratch_bytes = csrk_prod_scratch_bytes(p.cap_nnz, p.cap_rows, sizeof(T));
-  const size_t per_warp = (size_t)S * stage_bytes + scratch_bytes;
-  // layout: [W*S mbarriers][warp 0: S stages | scratch][warp 1: ...]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw) + (size_t)w * S;
-  unsigned char *ring = smem_raw + (((size_t)W * S * 8 + 127) & ~(size_t)127) + (size_t)w * per_warp;
-  T *prod = reinterpret_cast<T *>(ring + (size_t)S * stage_bytes);
-  int *srp = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(prod) + (size_t)(p.cap_nnz + 8) * sizeof(T));
-
-  if (lane == 0) {
-    for (int s = 0; s < S; ++s) mbar_init(smem_u32(bars + s), 1);
-    fence_barrier_init();
-    fence_proxy_async();
-  }
-  __syncwarp();
-
-  SrCursor cur;
-  cur.three = (p.k == 3);
-  cur.w = w;
-  cur.W = W;
-  cur.ssr_ptr = p.ssr_ptr;
-  cur.n_ssr = p.n_ssr;
-  if (cur.three) {
-    cur.s = (int64_t)blockIdx.x - gridDim.x;
-    cur.s_step = gridDim.x;
-    cur.cur = 0;
-    cur.end = 0;
-    cur.step = 0;
-    cur.pre_lo = cur.pre_hi = 0;
-    cur.carry = 0;
-    cur.prefetch_range(blockIdx.x);
-  } else {
-    cur.cur = (int64_t)blockIdx.x * W + w;
-    cur.step = (int64_t)gridDim.x * W;
-    cur.end = p.n_sr;
-    cur.s = cur.s_step = 0;
-    cur.carry = 0;
-  }
-  const uint64_t policy = l2_policy_evict_first();
-
-  auto load_meta = [&](int64_t sr) -> SrMeta {
-    SrMeta mt;
-    if (p.k == 1) { // one row range (this kernel takes no halo ranges)
-      const int64_t r0 = p.range_lo[0] + sr * p.rows_per_tile;
-      const int64_t r1 = (r0 + p.rows_per_tile < p.range_hi[0]) ? r0 + p.rows_per_tile : p.range_hi[0];
-      mt.r0 = (int)r0;
-      mt.r1 = (int)r1;
-      mt.e0 = ld_meta(p.rp + r0);
-      mt.e1 = ld_meta(p.rp + r1);
-    } else {
-      mt.r0 = (int)ld_meta(p.sr_ptr + sr);
-      mt.r1 = (int)ld_meta(p.sr_ptr + sr + 1);
-      mt.e0 = (int)ld_meta(p.sr_e + sr);
-      mt.e1 = (int)ld_meta(p.sr_e + sr + 1);
-    }
-    return mt;
-  };
-  auto issue = [&](const SrMeta &mt, int st) {
-    if (lane == 0) {
-      unsigned char *base = ring + (size_t)st * stage_bytes;
-      const int rows = mt.r1 - mt.r0, cnt = mt.e1 - mt.e0;
-      const bool staged = rows <= p.cap_rows && cnt <= p.cap_nnz && cnt > 0;
-      int *meta = reinterpret_cast<int *>(base);
-      meta[0] = mt.r0;
-      meta[1] = mt.r1;
-      meta[2] = mt.e0;
-      meta[3] = staged ? mt.e1 : -mt.e1 - 1;
-      const uint32_t bar = smem_u32(bars + st);
-      if (staged) {
-        const int rb = mt.r0 & ~3, rt = (mt.r1 + 1 + 3) & ~3;
-        const int64_t eb = mt.e0 & ~3, et = ((int64_t)mt.e1 + 3) & ~(int64_t)3;
-        const uint32_t rp_bytes = (uint32_t)(rt - rb) * 4u;
-        const uint32_t ci_bytes = (uint32_t)(et - eb) * 4u;
-        const uint32_t va_bytes = (uint32_t)(et - eb) * (uint32_t)sizeof(T);
-        unsigned char *rp_w = base + 16;
-        unsigned char *ci_w = rp_w + (size_t)(p.cap_rows + 8) * 4;
-        unsigned char *va_w = ci_w + (size_t)(p.cap_nnz + 8) * 4;
-        mbar_arrive_expect_tx(bar, rp_bytes + ci_bytes + va_bytes); // (stage only ever READ by the warp: no proxy fence, see csrk_tma_kernel)
-        bulk_g2s(smem_u32(rp_w), p.rp + rb, rp_bytes, bar, policy);
-        bulk_g2s(smem_u32(ci_w), p.ci + eb, ci_bytes, bar, policy);
-        bulk_g2s(smem_u32(va_w), p.val + eb, va_bytes, bar, policy);
-      } else {
-        mbar_arrive(bar);
-      }
-    }
-  };
-
-  int64_t sr;
-  int filled = 0;
-  for (; filled < S; ++filled) {
-    if (!cur.next(sr)) break;
-    issue(load_meta(sr), filled);
-  }
-  SrMeta mq0, mq1;
-  mq0.r0 = mq0.r1 = mq0.e0 = mq0.e1 = 0;
-  mq1 = mq0;
-  bool have0 = cur.next(sr);
-  if (have0) mq0 = load_meta(sr);
-  bool have1 = have0 && cur.next(sr);
-  if (have1) mq1 = load_meta(sr);
-  int live = filled;
-  auto advance = [&](int stg) {
-    --live;
-    if (have0) {
-      issue(mq0, stg);
-      ++live;
-      mq0 = mq1;
-      have0 = have1;
-      have1 = have1 && cur.next(sr);
-      if (have1) mq1 = load_meta(sr);
-    }
-  };
-
-  int st = 0;
-  uint32_t parity = 0;
-  const int sub = lane & (VEC - 1);
-  const int gid = lane / VEC;
-  while (live > 0) {
-    mbar_wait(smem_u32(bars + st), parity);
-    unsigned char *base = ring + (size_t)st * stage_bytes;
-    const int *meta = reinterpret_cast<const int *>(base);
-    const int r0 = meta[0], r1 = meta[1], e0 = meta[2], e1m = meta[3];
-    if (e1m >= 0) {
-      const int *rp_w = reinterpret_cast<const int *>(base + 16);
-      const int *ci_w = rp_w + (p.cap_rows + 8);
-      const T *va_w = reinterpret_cast<const T *>(reinterpret_cast<const unsigned char *>(ci_w) + (size_t)(p.cap_nnz + 8) * 4);
-      const int rows = r1 - r0;
-      const int o0 = e0 - (e0 & ~3), o1 = e1m - (e0 & ~3); // the tile's entries sit at stage offsets [o0, o1)
-      // row offsets relative to the tile's first entry, next to the product scratch
-      for (int i = lane; i <= rows; i += 32) srp[i] = rp_w[i + (r0 - (r0 & ~3))] - e0;
-      // phase 1: chunks of 32 * U entries, then what is left in chunks of 32 * 2 (at most one of them is masked), so
-      // that a tile costs ceil(entries / 64) * 2 slots per lane at most, not a multiple of U
-      const int full_end = o0 + ((o1 - o0) / (32 * U)) * (32 * U);
-      for (int cb = o0; cb < full_end; cb += 32 * U) {
-        int c[U];
-        T v[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          c[u] = ci_w[cb + lane + 32 * u];
-          v[u] = va_w[cb + lane + 32 * u];
-        }
-        if (cb + 32 * U >= o1) { // that was the whole tile: every lane has what it needs from the stage
-          __syncwarp();
-          advance(st);
-        }
-        T xv[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) xv[u] = __ldg(p.x + c[u]);
-#pragma unroll
-        for (int u = 0; u < U; ++u) prod[cb - o0 + lane + 32 * u] = v[u] * xv[u];
-      }
-      if (full_end < o1) {
-        constexpr int R = U - 1 > 0 ? U - 1 : 1; // the remainder is < 32 * U entries: at most U - 1 full slots + one masked
-        int c[R + 1];
-        T v[R + 1];
-#pragma unroll
-        for (int u = 0; u <= R; ++u) {
-          const int j = full_end + lane + 32 * u;
-          const int jc = j < o1 ? j : o1 - 1; // a slot past the end re-reads the tile's last entry (its product is not stored)
-          c[u] = 0;
-          v[u] = (T)0;
-          if (full_end + 32 * u < o1) { // warp-uniform: slots that are entirely past the end cost nothing
-            c[u] = ci_w[jc];
-            v[u] = va_w[jc];
-          }
-        }
-        __syncwarp();
-        advance(st);
-#pragma unroll
-        for (int u = 0; u <= R; ++u) {
-          const int j = full_end + lane + 32 * u;
-          if (full_end + 32 * u < o1) {
-            const T xg = __ldg(p.x + c[u]);
-            if (j < o1) prod[j - o0] = v[u] * xg;
-          }
-        }
-      }
-      __syncwarp(); // products and row offsets visible to the whole warp
-      // phase 2 (warp-uniform trip count)
-      for (int rb = 0; rb < rows; rb += 32 / VEC) {
-        const int r = rb + gid;
-        int rs = 0, re = 0;
-        if (r < rows) {
-          rs = srp[r];
-          re = srp[r + 1];
-        }
-        T acc = 0;
-        for (int j = rs + sub; j < re; j += VEC) acc += prod[j];
-        acc = group_sum<T, VEC>(acc);
-        if (r < rows && sub == 0) p.y[r0 + r] = acc;
-      }
-      __syncwarp(); // the scratch is free for the next tile
-    } else {
-      csrk_rows<T, VEC, 0, 4, int64_t>(r0, r1, p.rp, 0, p.ci, p.val, (int64_t)0, p.x, p.y, lane);
-      __syncwarp();
-      advance(st);
-    }
-    if (++st == S) {
-      st = 0;
-      parity ^= 1;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
 // vector helpers
 // ------------------------------------------------------------------------------------------
 template <typename T>

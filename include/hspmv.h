@@ -63,9 +63,6 @@ enum {
   HSPMV_OPT_NO_PIPELINE = 11, /* 1: hspmv_spmv_host copies, computes, copies back strictly in sequence */
   HSPMV_OPT_TAIL = 13,        /* TMA kernels: masked gathers per lane per round (compiled: see csrc/csrk_variants.h); 0 = default */
   HSPMV_OPT_BANDK_HOST = 12,  /* 1: hspmv_build_csrk runs entirely on the host (default: coarse graph + reorderA in HBM) */
-  HSPMV_OPT_PROD = 15,        /* TMA kernels: 1 = product-staging flavour (lane-strided nonzeros + row sums from a per-warp scratch),
-                                 -1 = slot flavour only, 0 = auto (product staging for ragged rows); HSPMV_OPT_TAIL then selects
-                                 its chunk depth (6, 8 or 12 entries per lane) */
   HSPMV_OPT_BLOCK_NNZ = 14,   /* CSR_BLOCK: nonzeros per row block (256..16384; 0 = 2048) */
   HSPMV_OPT_CHUNK = 10        /* TMA kernels: unmasked x gathers a lane keeps in flight per chunk; 0 = auto, < 0 = masked loop only */
 };

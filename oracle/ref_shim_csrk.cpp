@@ -66,5 +66,52 @@ double ref_csrk_spmv_timed(void *h, float *y, int warmup, int iters) {
 
 void ref_csrk_destroy(void *h) { delete (CSRk_Graph *)h; }
 
+// ---- STS (csrk.cpp:79-89 lowerSTS k == 2, :1522-1672 preprocessingForSTS with LS ordering, :708-809) ----
+// ctor("STS", "LS", "HAND", k = 2) + putInCSRkFormat (find_levels, levels sorted by size, reorderA)
+// + incomplete_choloskey (L / U structure) + compute_b (b = L * 1, x = 0).
+void *ref_sts_create(long n, long nnz, unsigned int *r, unsigned int *c, float *v) {
+  int sizes[1] = {0};
+  CSRk_Graph *g = new CSRk_Graph(n, n, nnz, r, c, v, "STS", "LS", "HAND", false, 2, sizes);
+  g->putInCSRkFormat();
+  g->incomplete_choloskey();
+  g->compute_b();
+  return g;
+}
+int ref_sts_num_packs(void *h) { return ((CSRk_Graph *)h)->numPacks; }
+long ref_sts_nnz_l(void *h) { return ((CSRk_Graph *)h)->num_edges_L[((CSRk_Graph *)h)->N]; }
+void ref_sts_get(void *h, unsigned int *perm, int *pack_ptr, unsigned int *l_rp, unsigned int *l_ci, float *l_val, float *b) {
+  CSRk_Graph *g = (CSRk_Graph *)h;
+  if (perm) for (long i = 0; i < g->N; i++) perm[i] = g->permBigG[i];
+  if (pack_ptr) for (int i = 0; i <= g->numPacks; i++) pack_ptr[i] = g->packsPointer[i];
+  if (l_rp) for (long i = 0; i <= g->N; i++) l_rp[i] = g->num_edges_L[i];
+  const long nl = g->num_edges_L[g->N];
+  if (l_ci) for (long i = 0; i < nl; i++) l_ci[i] = g->adj_L[i];
+  if (l_val) for (long i = 0; i < nl; i++) l_val[i] = g->val_L[i];
+  if (b) for (long i = 0; i < g->N; i++) b[i] = g->b[i];
+}
+void ref_sts_set_b(void *h, float *b) {
+  CSRk_Graph *g = (CSRk_Graph *)h;
+  for (long i = 0; i < g->N; i++) g->b[i] = b[i];
+}
+// lowerSTS(); x comes back in the REORDERED numbering (the numbering the reference solves in)
+void ref_sts_solve(void *h, float *x) {
+  CSRk_Graph *g = (CSRk_Graph *)h;
+  for (long i = 0; i < g->N; i++) g->x[i] = 0;
+  g->lowerSTS();
+  for (long i = 0; i < g->N; i++) x[i] = g->x[i];
+}
+double ref_sts_solve_timed(void *h, int warmup, int iters) {
+  CSRk_Graph *g = (CSRk_Graph *)h;
+  for (int i = 0; i < warmup; i++) g->lowerSTS();
+  double best = 1e30;
+  for (int i = 0; i < iters; i++) {
+    double t0 = omp_get_wtime();
+    g->lowerSTS();
+    double t = omp_get_wtime() - t0;
+    if (t < best) best = t;
+  }
+  return best;
+}
+
 int ref_csrk_sizeof_real(void) { return (int)sizeof(float); }
 }

@@ -82,18 +82,6 @@ def test_csr_ragged_empty_and_long_rows(dtype, hs, oracle, gen):
         check_csr(hs, oracle, gen, rp, ci, v, [hs.ALGO_CSR_STREAM],
                   opts={hs.OPT_VEC: vec, hs.OPT_CHUNK: -1, hs.OPT_TAIL: tail, hs.OPT_ROWS_PER_TILE: rpt},
                   what="long-rows masked vec=%d tail=%d rpt=%d" % (vec, tail, rpt))
-    # product-staging flavour of the TMA engine (csrk_prod_kernel): forced, every compiled (lanes, chunk depth), tiles of one
-    # and of several chunks, rows longer than a stage (direct path), empty rows
-    for vec, u, rpt in ((1, 8, 32), (2, 8, 16), (4, 8, 8), (4, 12, 24), (8, 8, 4), (8, 6, 64), (16, 8, 2), (32, 8, 1), (4, 6, 200)):
-        check_csr(hs, oracle, gen, rp, ci, v, [hs.ALGO_CSR_STREAM],
-                  opts={hs.OPT_PROD: 1, hs.OPT_VEC: vec, hs.OPT_TAIL: u, hs.OPT_ROWS_PER_TILE: rpt},
-                  what="long-rows prod vec=%d u=%d rpt=%d" % (vec, u, rpt))
-        check_csr(hs, oracle, gen, *gen.random_ragged(3000, max_len=70, dtype=dtype), [hs.ALGO_CSR_STREAM],
-                  opts={hs.OPT_PROD: 1, hs.OPT_VEC: vec, hs.OPT_TAIL: u, hs.OPT_ROWS_PER_TILE: rpt}, what="ragged prod vec=%d u=%d rpt=%d" % (vec, u, rpt))
-    check_csr(hs, oracle, gen, *gen.shell_blocks(20000, dtype=dtype), [hs.ALGO_AUTO, hs.ALGO_CSR_STREAM], what="shell auto (prod)")
-    check_csr(hs, oracle, gen, *gen.stencil27(12, dtype=dtype, mode="varied"), [hs.ALGO_CSR_STREAM], opts={hs.OPT_PROD: 1}, what="stencil prod")
-    check_csr(hs, oracle, gen, *gen.stencil27(12, dtype=dtype, mode="varied"), [hs.ALGO_CSR_STREAM], opts={hs.OPT_PROD: 1, hs.OPT_STAGE_NNZ: 64},
-              what="stencil prod tiny stage")
     # tiny capacity: every tile takes the direct (non-staged) path; tiny merge tile: rows span many tiles
     check_csr(hs, oracle, gen, rp, ci, v, [hs.ALGO_CSR_STREAM, hs.ALGO_CSR_MERGE],
               opts={hs.OPT_STAGE_NNZ: 64, hs.OPT_MERGE_TILE: 64, hs.OPT_ROWS_PER_TILE: 7}, what="long-rows tiny tiles")
@@ -196,18 +184,6 @@ def test_csrk_matches_oracle(case, dtype, hs, oracle, gen):
             A.A.set_option(hs.OPT_STAGES, stages)
             A.SpMV(y)
             assert_within_bound(y, y_ref_perm, scale[o["perm"]], dtype, "knobs [%s]" % A.A.last_kernel())
-    # product-staging flavour on super-rows (k = 2: super-row -> warp; k = 3: super-super-row -> CTA)
-    for vec, u in ((1, 8), (4, 8), (4, 12), (8, 6), (32, 8)):
-        for warps, stages in ((4, 2), (16, 3)):
-            for k_, val in ((hs.OPT_PROD, 1), (hs.OPT_VEC, vec), (hs.OPT_TAIL, u), (hs.OPT_WARPS, warps), (hs.OPT_STAGES, stages)):
-                A.A.set_option(k_, val)
-            y[:] = np.nan
-            A.setY(y)
-            A.SpMV(y)
-            assert "csrk_prod" in A.A.last_kernel()
-            assert_within_bound(y, y_ref_perm, scale[o["perm"]], dtype, "prod knobs [%s]" % A.A.last_kernel())
-    for k_ in (hs.OPT_PROD, hs.OPT_TAIL, hs.OPT_WARPS, hs.OPT_STAGES):
-        A.A.set_option(k_, 0)
     A.A.set_option(hs.OPT_VEC, 0)
     for algo in (hs.ALGO_CSR_VECTOR, hs.ALGO_CSR_STREAM, hs.ALGO_CSR_MERGE):
         A.A.spmv(algo)
