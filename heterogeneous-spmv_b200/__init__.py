@@ -252,6 +252,18 @@ def block_rows_host(row_ptr, cap, max_rows):
     return out[: nb.value + 1].copy() if m > 0 else out[:1].copy()
 
 
+def sts_levels_host(row_ptr, col_idx):
+    """Level sets of the triangular solve (kernel "STS", order "LS", k = 2) without a device: dict(perm new->old, pack_ptr)."""
+    row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int32)
+    col_idx = np.ascontiguousarray(col_idx, dtype=np.int32)
+    n = len(row_ptr) - 1
+    perm = np.zeros(n, np.uint32)
+    pack = np.zeros(n + 2, np.int32)
+    npk = C.c_int64()
+    _check(lib().hspmv_sts_levels_host(C.c_int64(n), C.c_int64(len(col_idx)), _p(row_ptr), _p(col_idx), _p(perm), _p(pack), C.byref(npk)))
+    return {"perm": perm, "pack_ptr": pack[: npk.value + 1].copy()}
+
+
 def merge_tile_rows_host(row_ptr, tile):
     row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int32)
     m = len(row_ptr) - 1
@@ -415,6 +427,44 @@ class Matrix:
         if i["k"] == 3:
             out["ssr_ptr"] = ssr
         return out
+
+    # -- STS (triangular solve on the level-set-ordered matrix)
+    def build_sts(self):
+        _check(lib().hspmv_build_sts(self.h))
+
+    def sts(self):
+        npk = C.c_int64()
+        _check(lib().hspmv_sts_get(self.h, None, None, C.byref(npk)))
+        perm = np.zeros(self.info()["m"], np.uint32)
+        pack = np.zeros(npk.value + 1, np.int32)
+        _check(lib().hspmv_sts_get(self.h, _p(perm), _p(pack), C.byref(npk)))
+        return {"perm": perm, "pack_ptr": pack}
+
+    def sts_compute_b(self):
+        _check(lib().hspmv_sts_compute_b(self.h))
+
+    def sts_set_b(self, b, original_order=False):
+        b = np.ascontiguousarray(b, dtype=self.dtype)
+        assert len(b) == self.info()["m"]
+        _check(lib().hspmv_sts_set_b(self.h, _p(b), int(original_order)))
+
+    def sts_get_b(self, original_order=False):
+        b = np.zeros(self.info()["m"], self.dtype)
+        _check(lib().hspmv_sts_get_b(self.h, _p(b), int(original_order)))
+        return b
+
+    def sts_solve(self, stream=None):
+        _check(lib().hspmv_sts_solve(self.h, C.c_void_p(stream)))
+
+    def sts_get_x(self, original_order=False):
+        x = np.zeros(self.info()["m"], self.dtype)
+        _check(lib().hspmv_sts_get_x(self.h, _p(x), int(original_order)))
+        return x
+
+    def sts_solve_timed(self, warmup=3, iters=10):
+        ms = np.zeros(iters, np.float32)
+        _check(lib().hspmv_sts_solve_timed(self.h, int(warmup), int(iters), _p(ms)))
+        return ms
 
     # -- vectors / hot path
     def set_option(self, opt, value):
@@ -644,8 +694,12 @@ class CSRk_Graph:
 
     def __init__(self, nRows, nCols, nnz, rVec, cVec, value, kernelCalled="SpMV", inOrderType="",
                  inCoarsenType="HAND", isTuned=False, inK=2, inSupRowSizes=(8,)):
-        if kernelCalled != "SpMV":
-            raise HspmvError("only the SpMV kernel is in scope (STS is the reference's other kernel)")
+        if kernelCalled not in ("SpMV", "STS"):
+            raise HspmvError("kernel must be SpMV or STS")
+        if kernelCalled == "STS" and (int(inK) != 2 or inOrderType != "LS"):
+            raise HspmvError("STS is built for k = 2 with LS (level-set) ordering; COLOR needs Boost's colouring and k >= 3 "
+                             "the coarsened level search, both out of scope")
+        self.kernel = kernelCalled
         if inCoarsenType != "HAND":
             raise HspmvError("only HAND coarsening is supported: every reference driver hard-codes it (spmv-csrk/spmv.cpp:125)")
         assert len(rVec) == nRows + 1 and len(cVec) == nnz
@@ -656,10 +710,28 @@ class CSRk_Graph:
         self._algo = ALGO_AUTO
 
     def putInCSRkFormat(self):
-        if self.k >= 2:
+        if self.kernel == "STS":
+            self.A.build_sts()
+        elif self.k >= 2:
             self.A.build_csrk(self.k, self.sizes)
 
+    # STS flavour (spmv-csrk/csrk.h:340-344): the L / U split needs no separate step here (L = A' up to the diagonal)
+    def incomplete_choloskey(self):
+        self.A.sts()
+
+    def compute_b(self):
+        self.A.sts_compute_b()
+
+    def lowerSTS(self):
+        self.A.sts_solve()
+
+    def checkError(self):
+        """Total Error of csrk.cpp:833-836: sum of (x_i - 1) after compute_b + lowerSTS"""
+        return float(np.sum(self.A.sts_get_x().astype(np.float64) - 1.0))
+
     def getPermutation(self):
+        if self.kernel == "STS":
+            return self.A.sts()["perm"]
         return self.A.csrk()["perm"] if self.k >= 2 else np.arange(self.A.info()["m"], dtype=np.uint32)
 
     def getNumCoarsestRows(self):

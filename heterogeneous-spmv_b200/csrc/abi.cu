@@ -7,6 +7,7 @@
 #include "merge.cuh"
 #include "csrk_variants.h"
 #include "bandk_gpu.h"
+#include "sts.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -92,6 +93,13 @@ struct hspmv_matrix {
   int64_t sr_max_rows = 0, sr_max_nnz = 0; // largest super-row (exact stage capacity)
   int64_t len_p90 = -1;                     // 90th percentile of the row lengths (ragged matrices only; lazily)
 
+  // STS (hspmv_build_sts): level-set packs of the reordered matrix, diagonal positions, right-hand side, solution
+  bool sts_ready = false;
+  int64_t n_packs = 0, solo_packs = 0;
+  int *d_diag = nullptr, *d_pack = nullptr;
+  void *d_sts_b = nullptr, *d_sts_x = nullptr;
+  std::vector<int32_t> h_pack;
+
   // CSR_BLOCK
   int64_t block_cap = 0, block_max_rows = 0, n_blocks = 0;
   int *d_blk_row = nullptr;
@@ -144,7 +152,7 @@ void free_device(hspmv_matrix *A) {
   free_pipe(A);
   void *ptrs[] = {A->d_rp, A->d_ci, A->d_val, A->d_x, A->d_y, A->d_tmp, A->d_sr, A->d_ssr,
                   A->d_sr_e, A->d_perm, A->d_bin_rows, A->d_long_seg, A->d_long_ptr, A->d_long_partial,
-                  A->d_tile_row, A->d_carry_row, A->d_blk_row,
+                  A->d_tile_row, A->d_carry_row, A->d_blk_row, A->d_diag, A->d_pack, A->d_sts_b, A->d_sts_x,
                   A->d_carry_val, A->d_flush};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -1937,6 +1945,268 @@ int hspmv_bin_rows_host(int64_t m, const int32_t *row_ptr, int32_t *rows, int64_
   hspmv::bin_rows(m, row_ptr, r, bp);
   if (m) std::memcpy(rows, r.data(), (size_t)m * 4);
   std::memcpy(bin_ptr, bp, sizeof(bp));
+  return HSPMV_OK;
+}
+
+} // extern "C"
+
+// ---- STS: sparse triangular solve on the level-set-ordered matrix ------------------------------
+namespace {
+
+template <typename T>
+int launch_sts_solve(hspmv_matrix *A, cudaStream_t st) {
+  const double mean_lower = A->m ? 0.5 * (double)A->nnz / (double)A->m : 1.0;
+  int vec = 1;
+  while (vec < 32 && mean_lower / vec > 6.0) vec <<= 1;
+  void (*kern)(int, int, const int *, const int *, const int *, const int *, const T *, const T *, T *) = nullptr;
+  switch (vec) {
+  case 1: kern = hspmv::sts_solve_kernel<T, 1>; break;
+  case 2: kern = hspmv::sts_solve_kernel<T, 2>; break;
+  case 4: kern = hspmv::sts_solve_kernel<T, 4>; break;
+  case 8: kern = hspmv::sts_solve_kernel<T, 8>; break;
+  case 16: kern = hspmv::sts_solve_kernel<T, 16>; break;
+  default: kern = hspmv::sts_solve_kernel<T, 32>; vec = 32; break;
+  }
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
+  if (per_sm < 1) return fail(HSPMV_ECUDA, "sts_solve_kernel does not fit on an SM");
+  if (per_sm > 4) per_sm = 4; // a grid barrier costs more with more CTAs; 4 x 256 threads per SM hide the gather latency
+  int grid = A->dev.sms * per_sm;
+  int n_packs = (int)A->n_packs, solo = (int)A->solo_packs;
+  const int *pack = A->d_pack, *rp = A->d_rp, *diag = A->d_diag, *ci = A->d_ci;
+  const T *val = (const T *)A->d_val, *b = (const T *)A->d_sts_b;
+  T *x = (T *)A->d_sts_x;
+  void *args[] = {&n_packs, &solo, &pack, &rp, &diag, &ci, &val, &b, &x};
+  CU(cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)grid), dim3(256), args, 0, st));
+  LAUNCHED();
+  char name[128];
+  std::snprintf(name, sizeof(name), "sts_solve<%s,vec=%d> packs=%d (first %d on one CTA) grid=%d threads=256 cooperative", sizeof(T) == 8 ? "f64" : "f32",
+                vec, n_packs, solo, grid);
+  A->last_kernel = name;
+  return HSPMV_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int hspmv_sts_levels_host(int64_t n, int64_t nnz, const int32_t *row_ptr, const int32_t *col_idx, uint32_t *perm, int32_t *pack_ptr,
+                          int64_t *n_packs) {
+  (void)nnz;
+  if (!row_ptr || !col_idx || !perm || !pack_ptr || !n_packs) return fail(HSPMV_EINVAL, "null");
+  std::vector<u32> p;
+  std::vector<int32_t> pk;
+  int rc = hspmv::sts_levels(n, row_ptr, col_idx, p, pk);
+  if (rc) return fail(rc, rc == HSPMV_EUNSUPPORTED ? "STS: a row has no stored diagonal, or the level search stalled (unsymmetric structure)" : "STS: bad arguments");
+  std::memcpy(perm, p.data(), p.size() * 4);
+  std::memcpy(pack_ptr, pk.data(), pk.size() * 4);
+  *n_packs = (int64_t)pk.size() - 1;
+  return HSPMV_OK;
+}
+
+int hspmv_build_sts(hspmv_matrix *A) {
+  if (!A) return fail(HSPMV_EINVAL, "null handle");
+  if (A->m != A->n || A->m <= 0) return fail(HSPMV_EINVAL, "STS needs a square matrix");
+  if (A->k != 1 || A->sts_ready || A->d_perm) return fail(HSPMV_ESTATE, "matrix is already reordered (CSR-k or STS)");
+  const size_t vs = A->vsize();
+  if (A->h_rp.empty()) {
+    A->h_rp.resize((size_t)A->m + 1);
+    CU(cudaMemcpy(A->h_rp.data(), A->d_rp, (size_t)(A->m + 1) * 4, cudaMemcpyDeviceToHost));
+  }
+  if (A->h_ci.size() != (size_t)A->nnz) {
+    A->h_ci.resize((size_t)A->nnz);
+    if (A->nnz) CU(cudaMemcpy(A->h_ci.data(), A->d_ci, (size_t)A->nnz * 4, cudaMemcpyDeviceToHost));
+  }
+  std::vector<u32> perm;
+  std::vector<int32_t> pack;
+  int rc = hspmv::sts_levels(A->m, A->h_rp.data(), A->h_ci.data(), perm, pack);
+  if (rc) return fail(rc, rc == HSPMV_EUNSUPPORTED ? "STS: a row has no stored diagonal, or the level search stalled (unsymmetric structure)" : "STS: bad arguments");
+  // A' = P A P^T (reorderA): in HBM when the rows fit the warp sorter, else on the host
+  int rc0 = ensure_stats(A);
+  if (rc0) return rc0;
+  bool done = false;
+  if (A->stats[8] <= hspmv::BANDK_MAX_ROW) {
+    int *rp2 = nullptr, *ci2 = nullptr;
+    void *val2 = nullptr;
+    u32 *d_perm = nullptr;
+    if (cudaMalloc(&rp2, (size_t)(A->m + 1 + PAD) * 4) == cudaSuccess && cudaMalloc(&ci2, (size_t)(A->nnz + PAD) * 4) == cudaSuccess &&
+        cudaMalloc(&val2, (size_t)(A->nnz + PAD) * vs) == cudaSuccess && cudaMalloc(&d_perm, (size_t)(A->m + PAD) * 4) == cudaSuccess) {
+      cudaMemsetAsync((char *)rp2 + (size_t)(A->m + 1) * 4, 0, PAD * 4, A->stream);
+      cudaMemsetAsync((char *)ci2 + (size_t)A->nnz * 4, 0, PAD * 4, A->stream);
+      cudaMemsetAsync((char *)val2 + (size_t)A->nnz * vs, 0, PAD * vs, A->stream);
+      cudaMemcpyAsync(d_perm, perm.data(), (size_t)A->m * 4, cudaMemcpyHostToDevice, A->stream);
+      int64_t launches = 0;
+      rc = hspmv::reorder_device(A->dtype, A->m, A->nnz, d_perm, (const u32 *)A->d_rp, (const u32 *)A->d_ci, A->d_val, (u32 *)rp2, (u32 *)ci2, val2,
+                                 A->dev.sms, A->stream, &launches);
+      g_launches.fetch_add(launches, std::memory_order_relaxed);
+      if (!rc) {
+        cudaFree(A->d_rp);
+        cudaFree(A->d_ci);
+        cudaFree(A->d_val);
+        A->d_rp = rp2;
+        A->d_ci = ci2;
+        A->d_val = val2;
+        A->d_perm = d_perm;
+        CU(cudaMemcpy(A->h_rp.data(), A->d_rp, (size_t)(A->m + 1) * 4, cudaMemcpyDeviceToHost));
+        std::vector<int32_t>().swap(A->h_ci);
+        std::vector<unsigned char>().swap(A->h_val);
+        done = true;
+      }
+    }
+    if (!done) {
+      cudaFree(rp2);
+      cudaFree(ci2);
+      cudaFree(val2);
+      cudaFree(d_perm);
+      cudaGetLastError();
+    }
+  }
+  if (!done) {
+    if (A->h_val.size() != (size_t)A->nnz * vs) {
+      A->h_val.resize((size_t)A->nnz * vs);
+      if (A->nnz) CU(cudaMemcpy(A->h_val.data(), A->d_val, (size_t)A->nnz * vs, cudaMemcpyDeviceToHost));
+    }
+    std::vector<int32_t> rp2((size_t)A->m + 1), ci2((size_t)A->nnz);
+    std::vector<unsigned char> val2((size_t)A->nnz * vs);
+    if (A->dtype == HSPMV_F64)
+      hspmv::reorder_f64(A->m, perm.data(), (const u32 *)A->h_rp.data(), (const u32 *)A->h_ci.data(), (const double *)A->h_val.data(),
+                         (u32 *)rp2.data(), (u32 *)ci2.data(), (double *)val2.data());
+    else
+      hspmv::reorder_f32(A->m, perm.data(), (const u32 *)A->h_rp.data(), (const u32 *)A->h_ci.data(), (const float *)A->h_val.data(),
+                         (u32 *)rp2.data(), (u32 *)ci2.data(), (float *)val2.data());
+    A->h_rp.swap(rp2);
+    std::vector<int32_t>().swap(A->h_ci);
+    std::vector<unsigned char>().swap(A->h_val);
+    CU(cudaMemcpy(A->d_rp, A->h_rp.data(), (size_t)(A->m + 1) * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(A->d_ci, ci2.data(), (size_t)A->nnz * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(A->d_val, val2.data(), (size_t)A->nnz * vs, cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&A->d_perm, (size_t)(A->m + PAD) * 4));
+    CU(cudaMemcpy(A->d_perm, perm.data(), (size_t)A->m * 4, cudaMemcpyHostToDevice));
+  }
+  A->h_perm.swap(perm);
+  A->h_pack.swap(pack);
+  A->n_packs = (int64_t)A->h_pack.size() - 1;
+  A->solo_packs = 0; // leading packs of <= 256 rows run on one CTA
+  while (A->solo_packs < A->n_packs && A->h_pack[(size_t)A->solo_packs + 1] - A->h_pack[(size_t)A->solo_packs] <= 256) ++A->solo_packs;
+  A->bins_ready = false;
+  A->merge_tile = 0;
+  A->block_cap = 0;
+  free_pipe(A);
+  hspmv::row_stats(A->m, A->h_rp.data(), A->stats);
+  A->stats_ready = true;
+  CU(cudaMalloc(&A->d_diag, (size_t)(A->m + PAD) * 4));
+  CU(cudaMalloc(&A->d_pack, (size_t)(A->n_packs + 1 + PAD) * 4));
+  CU(cudaMalloc(&A->d_sts_b, (size_t)(A->m + PAD) * vs));
+  CU(cudaMalloc(&A->d_sts_x, (size_t)(A->m + PAD) * vs));
+  CU(cudaMemset(A->d_sts_b, 0, (size_t)(A->m + PAD) * vs));
+  CU(cudaMemset(A->d_sts_x, 0, (size_t)(A->m + PAD) * vs));
+  CU(cudaMemcpy(A->d_pack, A->h_pack.data(), (size_t)(A->n_packs + 1) * 4, cudaMemcpyHostToDevice));
+  int *d_bad = nullptr;
+  CU(cudaMalloc(&d_bad, 4));
+  CU(cudaMemset(d_bad, 0, 4));
+  hspmv::sts_diag_kernel<<<grid_for(A->m, 256, A->dev.sms * 16), 256, 0, A->stream>>>(A->m, A->d_rp, A->d_ci, A->d_diag, d_bad);
+  LAUNCHED();
+  int bad = 0;
+  CU(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, A->stream));
+  CU(cudaStreamSynchronize(A->stream));
+  cudaFree(d_bad);
+  if (bad) return fail(HSPMV_EUNSUPPORTED, "STS: a row of the reordered matrix has no diagonal entry");
+  A->sts_ready = true;
+  return HSPMV_OK;
+}
+
+int hspmv_sts_get(const hspmv_matrix *A, uint32_t *perm, int32_t *pack_ptr, int64_t *n_packs) {
+  if (!A) return fail(HSPMV_EINVAL, "null handle");
+  if (!A->sts_ready) return fail(HSPMV_ESTATE, "hspmv_build_sts first");
+  if (perm) std::memcpy(perm, A->h_perm.data(), A->h_perm.size() * 4);
+  if (pack_ptr) std::memcpy(pack_ptr, A->h_pack.data(), A->h_pack.size() * 4);
+  if (n_packs) *n_packs = A->n_packs;
+  return HSPMV_OK;
+}
+
+int hspmv_sts_compute_b(hspmv_matrix *A) {
+  if (!A) return fail(HSPMV_EINVAL, "null handle");
+  if (!A->sts_ready) return fail(HSPMV_ESTATE, "hspmv_build_sts first");
+  const int grid = grid_for(A->m, 256, A->dev.sms * 16);
+  if (A->dtype == HSPMV_F64)
+    hspmv::sts_b_kernel<double><<<grid, 256, 0, A->stream>>>(A->m, A->d_rp, A->d_diag, (const double *)A->d_val, (double *)A->d_sts_b);
+  else
+    hspmv::sts_b_kernel<float><<<grid, 256, 0, A->stream>>>(A->m, A->d_rp, A->d_diag, (const float *)A->d_val, (float *)A->d_sts_b);
+  LAUNCHED();
+  CU(cudaStreamSynchronize(A->stream));
+  return HSPMV_OK;
+}
+
+// b / x cross the boundary in the solver's (reordered) numbering (original_order == 0, what the reference's arrays
+// hold) or in the matrix's original numbering (the permutation is applied inside)
+static int sts_vector_io(hspmv_matrix *A, void *dev, void *host, int original_order, bool upload) {
+  const size_t vs = A->vsize();
+  const int grid = grid_for(A->m, 256, A->dev.sms * 16);
+  if (upload) {
+    if (original_order) { // dev[i] = host[perm[i]]
+      CU(cudaMemcpyAsync(A->d_tmp, host, (size_t)A->m * vs, cudaMemcpyHostToDevice, A->stream));
+      if (A->dtype == HSPMV_F64) hspmv::gather_kernel<double><<<grid, 256, 0, A->stream>>>(A->m, A->d_perm, (const double *)A->d_tmp, (double *)dev);
+      else hspmv::gather_kernel<float><<<grid, 256, 0, A->stream>>>(A->m, A->d_perm, (const float *)A->d_tmp, (float *)dev);
+      LAUNCHED();
+    } else {
+      CU(cudaMemcpyAsync(dev, host, (size_t)A->m * vs, cudaMemcpyHostToDevice, A->stream));
+    }
+  } else {
+    if (A->last_stream_valid && A->last_stream != A->stream) CU(cudaStreamSynchronize(A->last_stream));
+    if (original_order) { // host[perm[i]] = dev[i]
+      if (A->dtype == HSPMV_F64) hspmv::scatter_kernel<double><<<grid, 256, 0, A->stream>>>(A->m, A->d_perm, (const double *)dev, (double *)A->d_tmp);
+      else hspmv::scatter_kernel<float><<<grid, 256, 0, A->stream>>>(A->m, A->d_perm, (const float *)dev, (float *)A->d_tmp);
+      LAUNCHED();
+      CU(cudaMemcpyAsync(host, A->d_tmp, (size_t)A->m * vs, cudaMemcpyDeviceToHost, A->stream));
+    } else {
+      CU(cudaMemcpyAsync(host, dev, (size_t)A->m * vs, cudaMemcpyDeviceToHost, A->stream));
+    }
+  }
+  CU(cudaStreamSynchronize(A->stream));
+  return HSPMV_OK;
+}
+int hspmv_sts_set_b(hspmv_matrix *A, const void *b_host, int original_order) {
+  if (!A || !b_host) return fail(HSPMV_EINVAL, "null");
+  if (!A->sts_ready) return fail(HSPMV_ESTATE, "hspmv_build_sts first");
+  return sts_vector_io(A, A->d_sts_b, const_cast<void *>(b_host), original_order, true);
+}
+int hspmv_sts_get_b(hspmv_matrix *A, void *b_host, int original_order) {
+  if (!A || !b_host) return fail(HSPMV_EINVAL, "null");
+  if (!A->sts_ready) return fail(HSPMV_ESTATE, "hspmv_build_sts first");
+  return sts_vector_io(A, A->d_sts_b, b_host, original_order, false);
+}
+int hspmv_sts_get_x(hspmv_matrix *A, void *x_host, int original_order) {
+  if (!A || !x_host) return fail(HSPMV_EINVAL, "null");
+  if (!A->sts_ready) return fail(HSPMV_ESTATE, "hspmv_build_sts first");
+  return sts_vector_io(A, A->d_sts_x, x_host, original_order, false);
+}
+
+int hspmv_sts_solve(hspmv_matrix *A, void *stream) {
+  if (!A) return fail(HSPMV_EINVAL, "null handle");
+  if (!A->sts_ready) return fail(HSPMV_ESTATE, "hspmv_build_sts first");
+  cudaStream_t st = stream ? (cudaStream_t)stream : A->stream;
+  A->last_stream = st;
+  A->last_stream_valid = true;
+  return A->dtype == HSPMV_F64 ? launch_sts_solve<double>(A, st) : launch_sts_solve<float>(A, st);
+}
+
+int hspmv_sts_solve_timed(hspmv_matrix *A, int warmup, int iters, float *ms_out) {
+  if (!A || iters < 1 || !ms_out) return fail(HSPMV_EINVAL, "bad arguments");
+  for (int i = 0; i < warmup; ++i) {
+    int rc = hspmv_sts_solve(A, A->stream);
+    if (rc) return rc;
+  }
+  std::vector<cudaEvent_t> ev((size_t)iters * 2);
+  for (auto &e : ev) CU(cudaEventCreate(&e));
+  for (int i = 0; i < iters; ++i) {
+    CU(cudaEventRecord(ev[(size_t)2 * i], A->stream));
+    int rc = hspmv_sts_solve(A, A->stream);
+    if (rc) return rc;
+    CU(cudaEventRecord(ev[(size_t)2 * i + 1], A->stream));
+  }
+  CU(cudaStreamSynchronize(A->stream));
+  for (int i = 0; i < iters; ++i) CU(cudaEventElapsedTime(&ms_out[i], ev[(size_t)2 * i], ev[(size_t)2 * i + 1]));
+  for (auto &e : ev) cudaEventDestroy(e);
   return HSPMV_OK;
 }
 

@@ -75,6 +75,9 @@ void tile_rows(int64_t m, const int32_t *rp, int64_t tile, std::vector<int32_t> 
 // blk_row[n_blocks] = m (oracle/partition_oracle.py: block_rows restates the rule).
 void block_rows(int64_t m, const int32_t *rp, int64_t cap, int64_t max_rows, std::vector<int32_t> &blk_row);
 
+// ---- sts.cpp: level sets of the triangular solve (kernel "STS", order "LS", k = 2), bit-exact vs oracle/sts_oracle.cpp
+int sts_levels(int64_t n, const int32_t *rp, const int32_t *ci, std::vector<u32> &perm, std::vector<int32_t> &pack_ptr);
+
 // ---- heuristics.cpp
 int auto_params(int64_t nnz, int64_t n_rows, int arch, int sizes[2], int *veclevel, int *block_dim_y);
 

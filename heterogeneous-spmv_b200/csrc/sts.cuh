@@ -1,0 +1,90 @@
+// Sparse triangular solve L x = b on the level-set-ordered matrix (replaces CSRk_Graph::lowerSTS,
+// k == 2, spmv-csrk/csrk.cpp:79-89, with incomplete_choloskey :708-789 and compute_b :791-809).
+//
+// L is not materialised: after hspmv_build_sts the handle holds A' = P A P^T with sorted rows, and diag[r] is the
+// position of row r's diagonal entry, so L's row r is the entries [rp[r], diag[r]] of A' -- the diagonal last, as in
+// the reference's val_L / adj_L.  Rows of one pack (one level) do not depend on each other; packs run in order:
+//   * the leading packs are small (levels are sorted by size): CTA 0 runs them alone with __syncthreads between
+//     them, the other CTAs wait at one grid barrier;
+//   * the remaining packs are spread over the whole grid, VEC lanes per row, one cooperative grid barrier per pack.
+// x entries written in earlier packs are read with ld.global.cg (L2): another SM wrote them during this launch.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "kernels.cuh"
+
+namespace hspmv {
+
+// diag[r] = position of the entry (r, r); *bad = 1 when a row has none ("Self edge not found", csrk.cpp:731-733)
+static __global__ void sts_diag_kernel(int64_t n, const int *__restrict__ rp, const int *__restrict__ ci, int *__restrict__ diag,
+                                       int *__restrict__ bad) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    int lo = rp[r], hi = rp[r + 1];
+    while (lo < hi) { // first position with column >= r
+      const int mid = (lo + hi) >> 1;
+      if (ci[mid] < (int)r) lo = mid + 1; else hi = mid;
+    }
+    if (lo < rp[r + 1] && ci[lo] == (int)r) diag[r] = lo;
+    else {
+      diag[r] = rp[r];
+      *bad = 1;
+    }
+  }
+}
+
+// b = L * 1, one accumulator per row, left to right (compute_b): bit-identical to the reference's loop
+template <typename T>
+__global__ void sts_b_kernel(int64_t n, const int *__restrict__ rp, const int *__restrict__ diag, const T *__restrict__ val,
+                             T *__restrict__ b) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    T t = 0;
+    for (int j = rp[r]; j <= diag[r]; ++j) t += val[j] * (T)1.0;
+    b[r] = t;
+  }
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ void sts_rows(int row_lo, int row_hi, int group, int n_groups, int sub, const int *__restrict__ rp,
+                                         const int *__restrict__ diag, const int *__restrict__ ci, const T *__restrict__ val,
+                                         const T *__restrict__ b, T *x) {
+  // warp-uniform trip count (full-mask shuffles): groups of one warp advance together
+  const int per_warp = 32 / VEC;
+  for (int base = row_lo + (group / per_warp) * per_warp; base < row_hi; base += n_groups) {
+    const int r = base + group % per_warp;
+    const bool active = r < row_hi;
+    T acc = 0;
+    int d = 0;
+    if (active) {
+      d = diag[r];
+      for (int j = rp[r] + sub; j < d; j += VEC) acc += val[j] * __ldcg(x + ci[j]);
+    }
+    acc = group_sum<T, VEC>(acc);
+    if (active && sub == 0) x[r] = (b[r] - acc) / val[d];
+  }
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) sts_solve_kernel(int n_packs, int solo_packs, const int *__restrict__ pack_ptr,
+                                                        const int *__restrict__ rp, const int *__restrict__ diag,
+                                                        const int *__restrict__ ci, const T *__restrict__ val,
+                                                        const T *__restrict__ b, T *x) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  const int sub = threadIdx.x & (VEC - 1);
+  if (blockIdx.x == 0) { // the small leading packs: one CTA, block barriers
+    const int group = threadIdx.x / VEC, n_groups = blockDim.x / VEC;
+    for (int p = 0; p < solo_packs; ++p) {
+      sts_rows<T, VEC>(pack_ptr[p], pack_ptr[p + 1], group, n_groups, sub, rp, diag, ci, val, b, x);
+      __threadfence();
+      __syncthreads();
+    }
+  }
+  if (solo_packs > 0 && solo_packs < n_packs) grid.sync();
+  const int group = (blockIdx.x * blockDim.x + threadIdx.x) / VEC, n_groups = gridDim.x * blockDim.x / VEC;
+  for (int p = solo_packs; p < n_packs; ++p) {
+    sts_rows<T, VEC>(pack_ptr[p], pack_ptr[p + 1], group, n_groups, sub, rp, diag, ci, val, b, x);
+    if (p + 1 < n_packs) grid.sync();
+  }
+}
+
+} // namespace hspmv

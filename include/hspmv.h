@@ -354,6 +354,25 @@ int hspmv_mg_spmv_timed_batch(hspmv_mg *M, int warmup, int iters, float *ms_per_
 /* test hook: NaN into every halo region of both x buffers (only a correct push makes them finite again) */
 int hspmv_mg_poison_halos(hspmv_mg *M);
 
+/* ---- STS: sparse triangular solve on CSR-k, k = 2, level-set ordering --------------------
+ * Replaces, for kernel "STS" / order "LS" / k = 2: BAND_k::preprocessingForSTS (spmv-csrk/csrk.cpp:1522-1672,
+ * find_levels :2704-2816, levels sorted by size), CSRk_Graph::reorderA, incomplete_choloskey (:708-789), compute_b
+ * (:791-809) and lowerSTS (:79-89).  COLOR ordering (Boost sequential_vertex_coloring) and k >= 3 are out of scope.
+ * hspmv_build_sts: level sets on the host (bit-exact permutation and pack bounds), A' = P A P^T in HBM; L is the part
+ * of A' up to and including the diagonal of every row (not materialised).  Afterwards the handle is a plain-CSR
+ * handle of A' (k stays 1; set_x / get_y apply the permutation), and the STS entry points below work on it. */
+int hspmv_sts_levels_host(int64_t n, int64_t nnz, const int32_t *row_ptr, const int32_t *col_idx, uint32_t *perm,
+                          int32_t *pack_ptr, int64_t *n_packs); /* the index work alone; pack_ptr: room for n + 1 */
+int hspmv_build_sts(hspmv_matrix *A);
+int hspmv_sts_get(const hspmv_matrix *A, uint32_t *perm, int32_t *pack_ptr, int64_t *n_packs);
+int hspmv_sts_compute_b(hspmv_matrix *A); /* b = L * 1 (compute_b), left to right per row */
+/* original_order = 0: the solver's (reordered) numbering, as the reference's b / x arrays; 1: the input matrix' */
+int hspmv_sts_set_b(hspmv_matrix *A, const void *b_host, int original_order);
+int hspmv_sts_get_b(hspmv_matrix *A, void *b_host, int original_order);
+int hspmv_sts_solve(hspmv_matrix *A, void *stream); /* lowerSTS: packs in order, one cooperative launch */
+int hspmv_sts_get_x(hspmv_matrix *A, void *x_host, int original_order);
+int hspmv_sts_solve_timed(hspmv_matrix *A, int warmup, int iters, float *ms_out);
+
 /* ---- kernel-side index tables, exposed for the bit-exactness tests ------------------ */
 /* CSR_MERGE tile table: tile_row[t] = last row r with row_ptr[r] <= t*tile, t = 0..n_tiles
  * (n_tiles = ceil(nnz/tile)); tile_row[n_tiles] = m.  Host rule and the device copy. */

@@ -231,7 +231,114 @@ def bandk_reorder(perm, rp, ci, v):
     return r2, c2, v2
 
 
+# --------------------------------------------------------------------------- STS restatement (sts_oracle.cpp)
+def sts_levels(rp, ci):
+    """find_levels + levels sorted by size (csrk.cpp:2704-2816, 1612-1666): dict(perm new->old, pack_ptr)."""
+    rp = np.ascontiguousarray(rp, dtype=np.int32)
+    ci = np.ascontiguousarray(ci, dtype=np.int32)
+    n = len(rp) - 1
+    perm = np.zeros(n, np.uint32)
+    pack = np.zeros(n + 2, np.int32)
+    npk = C.c_int(0)
+    fn = lib().sts_oracle_levels
+    fn.argtypes = [C.c_long, C.c_long, i32p, i32p, u32p, i32p, C.POINTER(C.c_int)]
+    rc = fn(n, len(ci), rp, ci, perm, pack, C.byref(npk))
+    if rc:
+        raise RuntimeError("sts_oracle_levels: the level search stalled (no stored diagonal, or unsymmetric structure)")
+    return {"perm": perm, "pack_ptr": pack[: npk.value + 1].copy()}
+
+
+def sts_lower(rp, ci, v):
+    """L (column <= row) of an already reordered matrix (csrk.cpp:708-789): (l_rp, l_ci, l_val)."""
+    v = np.ascontiguousarray(v)
+    rp = np.ascontiguousarray(rp, dtype=np.uint32)
+    ci = np.ascontiguousarray(ci, dtype=np.uint32)
+    n = len(rp) - 1
+    l_rp = np.zeros(n + 1, np.uint32)
+    l_ci = np.zeros(len(ci), np.uint32)
+    pos = np.zeros(len(ci), np.int64)
+    fn = lib().sts_oracle_lower
+    fn.restype = C.c_long
+    fn.argtypes = [C.c_long, u32p, u32p, u32p, u32p, np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")]
+    cnt = fn(n, rp, ci, l_rp, l_ci, pos)
+    if cnt < 0:
+        raise RuntimeError("sts_oracle_lower: a row has no diagonal entry")
+    return l_rp, l_ci[:cnt].copy(), v[pos[:cnt]].copy()
+
+
+def sts_b(l_rp, l_ci, l_val):
+    """compute_b (csrk.cpp:791-809): b = L * 1."""
+    l_val = np.ascontiguousarray(l_val)
+    b = np.zeros(len(l_rp) - 1, l_val.dtype)
+    fn = getattr(lib(), "sts_oracle_b_" + _sfx(l_val.dtype))
+    fn.argtypes = [C.c_long, u32p, u32p, _fp(l_val.dtype), _fp(l_val.dtype)]
+    fn(len(l_rp) - 1, np.ascontiguousarray(l_rp, np.uint32), np.ascontiguousarray(l_ci, np.uint32), l_val, b)
+    return b
+
+
+def sts_solve(pack_ptr, l_rp, l_ci, l_val, b):
+    """lowerSTS, k == 2 (csrk.cpp:79-89): x with L x = b, packs in order."""
+    l_val = np.ascontiguousarray(l_val)
+    b = np.ascontiguousarray(b, dtype=l_val.dtype)
+    x = np.zeros(len(l_rp) - 1, l_val.dtype)
+    pack_ptr = np.ascontiguousarray(pack_ptr, dtype=np.int32)
+    fn = getattr(lib(), "sts_oracle_solve_" + _sfx(l_val.dtype))
+    fp = _fp(l_val.dtype)
+    fn.argtypes = [C.c_long, C.c_int, i32p, u32p, u32p, fp, fp, fp]
+    fn(len(l_rp) - 1, len(pack_ptr) - 1, pack_ptr, np.ascontiguousarray(l_rp, np.uint32), np.ascontiguousarray(l_ci, np.uint32), l_val, b, x)
+    return x
+
+
 # --------------------------------------------------------------------------- real reference
+class RefSTS:
+    """The reference's STS-2 path with LS ordering (ctor "STS"/"LS"/k=2, putInCSRkFormat, incomplete_choloskey,
+    compute_b), via oracle/_ref."""
+
+    def __init__(self, rp, ci, v):
+        v = np.ascontiguousarray(v)
+        self.dtype = v.dtype
+        self.L = ref("csrk", v.dtype)
+        self.n = len(rp) - 1
+        rp = np.ascontiguousarray(rp, dtype=np.uint32)
+        ci = np.ascontiguousarray(ci, dtype=np.uint32)
+        self.L.ref_sts_create.restype = C.c_void_p
+        self.L.ref_sts_create.argtypes = [C.c_long, C.c_long, u32p, u32p, _fp(v.dtype)]
+        self.h = C.c_void_p(self.L.ref_sts_create(self.n, len(ci), rp, ci, v))
+        self.L.ref_sts_nnz_l.restype = C.c_long
+        self.L.ref_sts_nnz_l.argtypes = [C.c_void_p]
+        self.L.ref_sts_num_packs.argtypes = [C.c_void_p]
+        self.L.ref_sts_solve_timed.restype = C.c_double
+
+    def arrays(self):
+        npk = self.L.ref_sts_num_packs(self.h)
+        nl = self.L.ref_sts_nnz_l(self.h)
+        perm = np.zeros(self.n, np.uint32)
+        pack = np.zeros(npk + 1, np.int32)
+        l_rp = np.zeros(self.n + 1, np.uint32)
+        l_ci = np.zeros(nl, np.uint32)
+        l_val = np.zeros(nl, self.dtype)
+        b = np.zeros(self.n, self.dtype)
+        fp = _fp(self.dtype)
+        self.L.ref_sts_get.argtypes = [C.c_void_p, u32p, i32p, u32p, u32p, fp, fp]
+        self.L.ref_sts_get(self.h, perm, pack, l_rp, l_ci, l_val, b)
+        return {"perm": perm, "pack_ptr": pack, "l_rp": l_rp, "l_ci": l_ci, "l_val": l_val, "b": b}
+
+    def set_b(self, b):
+        b = np.ascontiguousarray(b, dtype=self.dtype)
+        self.L.ref_sts_set_b.argtypes = [C.c_void_p, _fp(self.dtype)]
+        self.L.ref_sts_set_b(self.h, b)
+
+    def solve(self):
+        x = np.zeros(self.n, self.dtype)
+        self.L.ref_sts_solve.argtypes = [C.c_void_p, _fp(self.dtype)]
+        self.L.ref_sts_solve(self.h, x)
+        return x
+
+    def solve_timed(self, warmup=3, iters=10):
+        self.L.ref_sts_solve_timed.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        return float(self.L.ref_sts_solve_timed(self.h, warmup, iters))
+
+
 class RefCSRk:
     """The reference's CSRk_Graph (ctor + putInCSRkFormat), via oracle/_ref."""
 

@@ -21,6 +21,11 @@
 //                                   REORDERED matrix (the diagonal is the last entry of a row)
 //   sts_oracle_b_*      :791-809    compute_b: b = L * 1, one accumulator per row, left to right
 //   sts_oracle_solve_*  :79-89      lowerSTS, k == 2: packs in order, rows of a pack in parallel
+//
+// Built with the SAME floating-point flags as the reference library in oracle/_ref (-O3 -march=x86-64-v3, GNU's
+// default -ffp-contract=fast: `t += v * x` is one fused multiply-add), unlike spmv_oracle.c: the solve divides, so its
+// x is not exactly representable and a fused and an unfused accumulation differ in the last bits.  With equal flags
+// the restated loop and the reference's loop give bit-identical x, which is what tests/test_sts.py asserts.
 // ============================================================================
 #include <algorithm>
 #include <cstdint>
