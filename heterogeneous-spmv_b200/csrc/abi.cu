@@ -1956,8 +1956,8 @@ namespace {
 template <typename T>
 int launch_sts_solve(hspmv_matrix *A, cudaStream_t st) {
   const double mean_lower = A->m ? 0.5 * (double)A->nnz / (double)A->m : 1.0;
-  int vec = 1;
-  while (vec < 32 && mean_lower / vec > 6.0) vec <<= 1;
+  int vec = 1; // one round of four entries per lane should cover the lower part of a typical row
+  while (vec < 32 && mean_lower / vec > 4.0) vec <<= 1;
   void (*kern)(int, int, const int *, const int *, const int *, const int *, const T *, const T *, T *) = nullptr;
   switch (vec) {
   case 1: kern = hspmv::sts_solve_kernel<T, 1>; break;
@@ -1967,20 +1967,20 @@ int launch_sts_solve(hspmv_matrix *A, cudaStream_t st) {
   case 16: kern = hspmv::sts_solve_kernel<T, 16>; break;
   default: kern = hspmv::sts_solve_kernel<T, 32>; vec = 32; break;
   }
+  const int threads = 1024;
   int per_sm = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0));
   if (per_sm < 1) return fail(HSPMV_ECUDA, "sts_solve_kernel does not fit on an SM");
-  if (per_sm > 4) per_sm = 4; // a grid barrier costs more with more CTAs; 4 x 256 threads per SM hide the gather latency
-  int grid = A->dev.sms * per_sm;
+  int grid = A->dev.sms; // one CTA of 1024 threads per SM: a grid barrier costs less with fewer CTAs
   int n_packs = (int)A->n_packs, solo = (int)A->solo_packs;
   const int *pack = A->d_pack, *rp = A->d_rp, *diag = A->d_diag, *ci = A->d_ci;
   const T *val = (const T *)A->d_val, *b = (const T *)A->d_sts_b;
   T *x = (T *)A->d_sts_x;
   void *args[] = {&n_packs, &solo, &pack, &rp, &diag, &ci, &val, &b, &x};
-  CU(cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)grid), dim3(256), args, 0, st));
+  CU(cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)grid), dim3((unsigned)threads), args, 0, st));
   LAUNCHED();
   char name[128];
-  std::snprintf(name, sizeof(name), "sts_solve<%s,vec=%d> packs=%d (first %d on one CTA) grid=%d threads=256 cooperative", sizeof(T) == 8 ? "f64" : "f32",
+  std::snprintf(name, sizeof(name), "sts_solve<%s,vec=%d> packs=%d (first %d on one CTA) grid=%d threads=1024 cooperative", sizeof(T) == 8 ? "f64" : "f32",
                 vec, n_packs, solo, grid);
   A->last_kernel = name;
   return HSPMV_OK;
@@ -2086,7 +2086,7 @@ int hspmv_build_sts(hspmv_matrix *A) {
   A->h_perm.swap(perm);
   A->h_pack.swap(pack);
   A->n_packs = (int64_t)A->h_pack.size() - 1;
-  A->solo_packs = 0; // leading packs of <= 256 rows run on one CTA
+  A->solo_packs = 0; // leading packs that one CTA of 1024 threads finishes in one pass (>= 4 lanes per row: 256 rows) run on CTA 0
   while (A->solo_packs < A->n_packs && A->h_pack[(size_t)A->solo_packs + 1] - A->h_pack[(size_t)A->solo_packs] <= 256) ++A->solo_packs;
   A->bins_ready = false;
   A->merge_tile = 0;

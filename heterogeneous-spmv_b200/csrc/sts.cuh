@@ -4,10 +4,11 @@
 // L is not materialised: after hspmv_build_sts the handle holds A' = P A P^T with sorted rows, and diag[r] is the
 // position of row r's diagonal entry, so L's row r is the entries [rp[r], diag[r]] of A' -- the diagonal last, as in
 // the reference's val_L / adj_L.  Rows of one pack (one level) do not depend on each other; packs run in order:
-//   * the leading packs are small (levels are sorted by size): CTA 0 runs them alone with __syncthreads between
-//     them, the other CTAs wait at one grid barrier;
-//   * the remaining packs are spread over the whole grid, VEC lanes per row, one cooperative grid barrier per pack.
-// x entries written in earlier packs are read with ld.global.cg (L2): another SM wrote them during this launch.
+//   * the leading packs are small (levels are sorted by size): CTA 0 (1024 threads) runs them alone with
+//     __syncthreads between them and plain loads of x (its own SM wrote them); the other CTAs wait at one grid barrier;
+//   * the remaining packs are spread over the whole grid (one CTA per SM: a grid barrier costs less with fewer CTAs),
+//     VEC lanes per row, one cooperative grid barrier per pack; x entries written in earlier packs are read with
+//     ld.global.cg (L2): another SM wrote them during this launch.
 #pragma once
 #include <cooperative_groups.h>
 
@@ -43,7 +44,7 @@ __global__ void sts_b_kernel(int64_t n, const int *__restrict__ rp, const int *_
   }
 }
 
-template <typename T, int VEC>
+template <typename T, int VEC, bool LOCAL>
 __device__ __forceinline__ void sts_rows(int row_lo, int row_hi, int group, int n_groups, int sub, const int *__restrict__ rp,
                                          const int *__restrict__ diag, const int *__restrict__ ci, const T *__restrict__ val,
                                          const T *__restrict__ b, T *x) {
@@ -52,19 +53,42 @@ __device__ __forceinline__ void sts_rows(int row_lo, int row_hi, int group, int 
   for (int base = row_lo + (group / per_warp) * per_warp; base < row_hi; base += n_groups) {
     const int r = base + group % per_warp;
     const bool active = r < row_hi;
-    T acc = 0;
-    int d = 0;
+    T acc = 0, rhs = 0, dia = 1;
+    int rs = 0, d = 0;
     if (active) {
+      rs = rp[r];
       d = diag[r];
-      for (int j = rp[r] + sub; j < d; j += VEC) acc += val[j] * __ldcg(x + ci[j]);
+      rhs = b[r];   // both independent of x: in flight while the dependencies are gathered
+      dia = val[d];
+    }
+    // four entries per lane per round, all column / value loads of a round issued before its x gathers: a row costs
+    // ceil(lower entries / (4 * VEC)) rounds of latency, not one per entry (warp-uniform trip count)
+    for (int j0 = rs + sub; __any_sync(0xffffffffu, j0 < d); j0 += 4 * VEC) {
+      int c[4];
+      T v[4], xv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool ok = j0 + u * VEC < d;
+        c[u] = ok ? ci[j0 + u * VEC] : 0;
+        v[u] = ok ? val[j0 + u * VEC] : (T)0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        // LOCAL: every x entry read here was written by THIS CTA (its own SM's L1 is coherent with its own stores);
+        // otherwise another SM wrote it during this launch: read it from L2
+        const bool ok = j0 + u * VEC < d;
+        xv[u] = ok ? (LOCAL ? x[c[u]] : __ldcg(x + c[u])) : (T)0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc += v[u] * xv[u];
     }
     acc = group_sum<T, VEC>(acc);
-    if (active && sub == 0) x[r] = (b[r] - acc) / val[d];
+    if (active && sub == 0) x[r] = (rhs - acc) / dia;
   }
 }
 
 template <typename T, int VEC>
-__global__ void __launch_bounds__(256) sts_solve_kernel(int n_packs, int solo_packs, const int *__restrict__ pack_ptr,
+__global__ void __launch_bounds__(1024) sts_solve_kernel(int n_packs, int solo_packs, const int *__restrict__ pack_ptr,
                                                         const int *__restrict__ rp, const int *__restrict__ diag,
                                                         const int *__restrict__ ci, const T *__restrict__ val,
                                                         const T *__restrict__ b, T *x) {
@@ -74,15 +98,15 @@ __global__ void __launch_bounds__(256) sts_solve_kernel(int n_packs, int solo_pa
   if (blockIdx.x == 0) { // the small leading packs: one CTA, block barriers
     const int group = threadIdx.x / VEC, n_groups = blockDim.x / VEC;
     for (int p = 0; p < solo_packs; ++p) {
-      sts_rows<T, VEC>(pack_ptr[p], pack_ptr[p + 1], group, n_groups, sub, rp, diag, ci, val, b, x);
-      __threadfence();
+      sts_rows<T, VEC, true>(pack_ptr[p], pack_ptr[p + 1], group, n_groups, sub, rp, diag, ci, val, b, x);
       __syncthreads();
     }
   }
+  if (blockIdx.x == 0) __threadfence();
   if (solo_packs > 0 && solo_packs < n_packs) grid.sync();
   const int group = (blockIdx.x * blockDim.x + threadIdx.x) / VEC, n_groups = gridDim.x * blockDim.x / VEC;
   for (int p = solo_packs; p < n_packs; ++p) {
-    sts_rows<T, VEC>(pack_ptr[p], pack_ptr[p + 1], group, n_groups, sub, rp, diag, ci, val, b, x);
+    sts_rows<T, VEC, false>(pack_ptr[p], pack_ptr[p + 1], group, n_groups, sub, rp, diag, ci, val, b, x);
     if (p + 1 < n_packs) grid.sync();
   }
 }
