@@ -223,6 +223,14 @@ int build_shards(hspmv_mg *M, hspmv_matrix *full, const int *devices, int n_dev)
       sh.slot_at.push_back((int)(std::find(theirs.begin(), theirs.end(), d) - theirs.begin()));
     }
   }
+  // One untimed launch of the kernel every step will use, without a flag wait (x is all zeros): the module is loaded
+  // and its shared-memory attribute set before any step has work pending on the device.
+  for (Shard &sh : M->s) {
+    MGCU(cudaSetDevice(sh.dev));
+    if (k == 1) MGRC(hspmv_spmv_halo(sh.A, sh.int_a, sh.int_b, sh.x[0], nullptr, sh.flags, 0, 0, sh.flags + 32, sh.main));
+    else MGRC(hspmv_spmv(sh.A, HSPMV_ALGO_CSRK, sh.x[0], nullptr, sh.main));
+    MGCU(cudaStreamSynchronize(sh.main));
+  }
   return HSPMV_OK;
 }
 
@@ -414,19 +422,20 @@ int hspmv_mg_spmv(hspmv_mg *M) {
   const int b = t & 1;
   const size_t vs = M->vs();
   const bool exchange = !M->replicated && M->n_dev > 1;
+  if (!exchange) {
+    for (Shard &sh : M->s) {
+      MGCU(cudaSetDevice(sh.dev));
+      MGRC(hspmv_spmv(sh.A, HSPMV_ALGO_AUTO, sh.x[b], nullptr, sh.main));
+    }
+    return HSPMV_OK;
+  }
+  // 1. every device's pushes are enqueued BEFORE any kernel: one host thread feeds all devices, and a launch may block
+  //    the host (the first launch of a kernel loads its module, which waits for the device's pending work -- e.g. a
+  //    cuStreamWaitValue32 that only the next device's push can satisfy); with the pushes already in their queues
+  //    nothing a device waits for depends on the host any more
   for (Shard &sh : M->s) {
     MGCU(cudaSetDevice(sh.dev));
-    if (!exchange) {
-      MGRC(hspmv_spmv(sh.A, HSPMV_ALGO_AUTO, sh.x[b], nullptr, sh.main));
-      continue;
-    }
     MGCU(cudaEventRecord(sh.ready[b], sh.main)); // x of step t is complete at this point of the main stream
-    if (M->k == 1) {
-      MGRC(hspmv_spmv_halo(sh.A, sh.int_a, sh.int_b, sh.x[b], nullptr, sh.flags, (int)sh.senders.size(), t, sh.flags + 32, sh.main));
-    } else {
-      for (size_t i = 0; i < sh.senders.size(); ++i) MGRC(hspmv_stream_wait_ge(sh.main, sh.flags + i, t));
-      MGRC(hspmv_spmv(sh.A, HSPMV_ALGO_CSRK, sh.x[b], nullptr, sh.main));
-    }
     // comm stream: my boundary slices into the neighbours' x[b], then their flag words
     MGCU(cudaStreamWaitEvent(sh.comm, sh.ready[b], 0));
     for (const Seg &g : sh.send) {
@@ -439,6 +448,16 @@ int hspmv_mg_spmv(hspmv_mg *M) {
       MGRC(hspmv_stream_write(sh.comm, M->s[(size_t)sh.receivers[i]].flags + sh.slot_at[i], t));
     MGCU(cudaEventRecord(sh.pushed[b], sh.comm));
     sh.pushed_valid[b] = true;
+  }
+  // 2. the local products
+  for (Shard &sh : M->s) {
+    MGCU(cudaSetDevice(sh.dev));
+    if (M->k == 1) { // one launch: interior tiles, in-kernel wait for the neighbours' flags, boundary tiles
+      MGRC(hspmv_spmv_halo(sh.A, sh.int_a, sh.int_b, sh.x[b], nullptr, sh.flags, (int)sh.senders.size(), t, sh.flags + 32, sh.main));
+    } else {         // CSR-k walks whole super-rows: front-end wait for the flags, then one launch
+      for (size_t i = 0; i < sh.senders.size(); ++i) MGRC(hspmv_stream_wait_ge(sh.main, sh.flags + i, t));
+      MGRC(hspmv_spmv(sh.A, HSPMV_ALGO_CSRK, sh.x[b], nullptr, sh.main));
+    }
   }
   return HSPMV_OK;
 }

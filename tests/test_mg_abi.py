@@ -112,12 +112,12 @@ def test_c_program_and_drivers_on_all_visible_gpus(tmp_path, hs, gen):
     gen.write_csr_text(f1, rp, ci, v, base=1)
     for nd in _device_counts(hs):
         for k in (1, 2, 3):
-            r = subprocess.run([exe, "28", str(nd), str(k)], capture_output=True, text=True)
+            r = subprocess.run([exe, "28", str(nd), str(k)], capture_output=True, text=True, timeout=120)
             assert r.returncode == 0 and "Number Wrong: 0" in r.stdout, r.stdout + r.stderr
         if nd == 1:
             continue
-        r = subprocess.run([os.path.join(BIN, "cuda-spmv-csr", "spmv.exe"), f0, "5", "--gpus", str(nd)], capture_output=True, text=True)
+        r = subprocess.run([os.path.join(BIN, "cuda-spmv-csr", "spmv.exe"), f0, "5", "--gpus", str(nd)], capture_output=True, text=True, timeout=120)
         assert r.returncode == 0 and "Number Wrong: 0" in r.stdout and "TimeMin:" in r.stdout and "Multi-GPU: %d devices" % nd in r.stdout, r.stdout + r.stderr
         for args in (["16"], ["16", "8"]):
-            r = subprocess.run([os.path.join(BIN, "cuda-spmv-csrk", "cuda", "spmv"), f1, "5"] + args + ["--gpus", str(nd)], capture_output=True, text=True)
+            r = subprocess.run([os.path.join(BIN, "cuda-spmv-csrk", "cuda", "spmv"), f1, "5"] + args + ["--gpus", str(nd)], capture_output=True, text=True, timeout=120)
             assert r.returncode == 0 and "Number Wrong: 0" in r.stdout and "TimeAvg:" in r.stdout, r.stdout + r.stderr

@@ -26,6 +26,6 @@ def test_halo_exchange_data_path_on_gpus(ranks):
         pytest.skip("needs %d GPUs, %d visible" % (ranks, _gpus()))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(ranks),
            "--master-addr", "127.0.0.1", "--master-port", str(29600 + ranks), os.path.join(ROOT, "tests", "mp_halo_worker.py")]
-    p = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    p = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=420)
     assert p.returncode == 0, p.stdout[-3000:] + "\n" + p.stderr[-3000:]
     assert "MP_HALO_OK ranks=%d" % ranks in p.stdout, p.stdout[-2000:]
