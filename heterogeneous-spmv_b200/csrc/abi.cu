@@ -1953,11 +1953,17 @@ int hspmv_bin_rows_host(int64_t m, const int32_t *row_ptr, int32_t *rows, int64_
 // ---- STS: sparse triangular solve on the level-set-ordered matrix ------------------------------
 namespace {
 
+// lanes per row of the solve: one round of four entries per lane should cover the lower part of a typical row
+int sts_vec(const hspmv_matrix *A) {
+  const double mean_lower = A->m ? 0.5 * (double)A->nnz / (double)A->m : 1.0;
+  int vec = 1;
+  while (vec < 32 && mean_lower / vec > 4.0) vec <<= 1;
+  return vec;
+}
+
 template <typename T>
 int launch_sts_solve(hspmv_matrix *A, cudaStream_t st) {
-  const double mean_lower = A->m ? 0.5 * (double)A->nnz / (double)A->m : 1.0;
-  int vec = 1; // one round of four entries per lane should cover the lower part of a typical row
-  while (vec < 32 && mean_lower / vec > 4.0) vec <<= 1;
+  int vec = sts_vec(A);
   void (*kern)(int, int, const int *, const int *, const int *, const int *, const T *, const T *, T *) = nullptr;
   switch (vec) {
   case 1: kern = hspmv::sts_solve_kernel<T, 1>; break;
@@ -2086,8 +2092,11 @@ int hspmv_build_sts(hspmv_matrix *A) {
   A->h_perm.swap(perm);
   A->h_pack.swap(pack);
   A->n_packs = (int64_t)A->h_pack.size() - 1;
-  A->solo_packs = 0; // leading packs that one CTA of 1024 threads finishes in one pass (>= 4 lanes per row: 256 rows) run on CTA 0
-  while (A->solo_packs < A->n_packs && A->h_pack[(size_t)A->solo_packs + 1] - A->h_pack[(size_t)A->solo_packs] <= 256) ++A->solo_packs;
+  // leading packs that one CTA of 1024 threads finishes in ONE pass run on CTA 0 alone (a block barrier per pack, ~2 us);
+  // larger packs are worth a grid barrier (~3.5 us).  (r2 measurements, profiles/r2_sts_vs_reference_*.jsonl)
+  const int64_t solo_rows = 1024 / sts_vec(A);
+  A->solo_packs = 0;
+  while (A->solo_packs < A->n_packs && A->h_pack[(size_t)A->solo_packs + 1] - A->h_pack[(size_t)A->solo_packs] <= solo_rows) ++A->solo_packs;
   A->bins_ready = false;
   A->merge_tile = 0;
   A->block_cap = 0;
