@@ -468,6 +468,12 @@ def rmat_section(args, hs, hd, np, torch, dist, rank, world, peak, steps, warmup
     gen_s = time.time() - t0
     A = hs.Matrix.from_csr(rp_l, ci_l, v_l, n_cols=n, keep_host=False)
     x = G.vector_x(n)
+    if not args.no_hub:
+        # columns renumbered by popularity in HBM (one-time set-up like Band-k): hot x entries become neighbours.  With
+        # N > 1 every rank relabels by the counts of ITS row block, so the ranks' x numberings differ; x is set per rank.
+        t_hub = time.time()
+        perm_cols = A.relabel_hub_columns()
+        t_hub = time.time() - t_hub
     par = parity_vs_numpy(A, hs, rp_l, ci_l, v_l, x, hs.ALGO_AUTO)
     m_loc, nnz_loc = hi - lo, e1 - e0
     stream = torch.cuda.current_stream().cuda_stream
@@ -511,19 +517,27 @@ def rmat_section(args, hs, hd, np, torch, dist, rank, world, peak, steps, warmup
     out = {"workload": "rmat%d_csr" % args.rmat_scale, "n": n, "nnz": nnz, "n_gpus": world,
            "x": "replicated" if world > 1 else "single GPU", "ms_per_step": ms,
            "gflops": 2.0 * nnz / (ms * 1e-3) / 1e9, "kernel": kernel, "parity": par,
-           "generate_s": gen_s, "launches_per_step_per_rank": launches / max(steps, 1)}
+           "generate_s": gen_s, "launches_per_step_per_rank": launches / max(steps, 1),
+           "hub_column_relabel": (not args.no_hub), "hub_relabel_s": (t_hub if not args.no_hub else None)}
     b = alg_bytes(m_loc, n, nnz_loc)
     out["roofline"] = {"algorithmic_bytes_per_rank": b, "achieved_gbs_per_rank": b / (ms * 1e-3) / 1e9,
                        "frac_measured": b / (ms * 1e-3) / 1e9 / peak, "frac_nominal": b / (ms * 1e-3) / 1e9 / NOMINAL_GBS}
     if world > 1:
+        perm_t = None if args.no_hub else torch.from_numpy(perm_cols.astype(np.int64)).cuda()
+        y_all = torch.empty(n, dtype=torch.float64, device="cuda") if perm_t is not None else None
+
         def step_gather():
             rep.step()
-            rep.all_gather_y(y_local, x_full)
+            if perm_t is None:
+                rep.all_gather_y(y_local, x_full)
+            else:   # y blocks arrive in the original numbering; this rank's kernel wants x_kernel[i] = x[perm[i]]
+                rep.all_gather_y(y_local, y_all)
+                torch.index_select(y_all, 0, perm_t, out=x_full)
         x_keep = x_full.clone()
         for _ in range(2):
             step_gather()
             x_full.copy_(x_keep)
-        ms_g = timed(lambda: (rep.step(), rep.all_gather_y(y_local, x_full)), max(3, steps // 2))
+        ms_g = timed(step_gather, max(3, steps // 2))
         x_full.copy_(x_keep)
         out["all_gather_mode"] = {"ms_per_step": ms_g, "gflops": 2.0 * nnz / (ms_g * 1e-3) / 1e9,
                                   "what": "local SpMV + all_gather of the y blocks into every rank's x (y feeds the next x)"}
@@ -1055,6 +1069,7 @@ def main():
     ap.add_argument("--no-csrk", action="store_true", help="skip the CSR-2 / CSR-3 timings of the same matrix (N = 1 only)")
     ap.add_argument("--no-configs", action="store_true", help="skip the cfg1-cfg3 section (N = 1 only)")
     ap.add_argument("--no-rmat", action="store_true", help="skip the R-MAT (cfg4) section")
+    ap.add_argument("--no-hub", action="store_true", help="R-MAT: skip the hub-column relabel (hspmv_relabel_hub_columns)")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity record (diagnosis only)")
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "peer-unfused", "nccl"],

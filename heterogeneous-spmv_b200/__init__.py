@@ -428,6 +428,12 @@ class Matrix:
             out["ssr_ptr"] = ssr
         return out
 
+    def relabel_hub_columns(self):
+        """power-law matrices: columns renumbered by popularity in HBM; returns perm (new column -> old column)"""
+        perm = np.zeros(self.info()["n"], np.uint32)
+        _check(lib().hspmv_relabel_hub_columns(self.h, _p(perm)))
+        return perm
+
     # -- STS (triangular solve on the level-set-ordered matrix)
     def build_sts(self):
         _check(lib().hspmv_build_sts(self.h))

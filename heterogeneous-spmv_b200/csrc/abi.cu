@@ -100,6 +100,12 @@ struct hspmv_matrix {
   void *d_sts_b = nullptr, *d_sts_x = nullptr;
   std::vector<int32_t> h_pack;
 
+  // hspmv_relabel_hub_columns: d_perm permutes x only (columns were renumbered, rows were not)
+  bool cols_only_perm = false;
+  // CSR_VECTOR bins run concurrently on auxiliary streams (independent rows): fork / join events
+  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+
   // CSR_BLOCK
   int64_t block_cap = 0, block_max_rows = 0, n_blocks = 0;
   int *d_blk_row = nullptr;
@@ -156,6 +162,11 @@ void free_device(hspmv_matrix *A) {
                   A->d_carry_val, A->d_flush};
   for (void *p : ptrs)
     if (p) cudaFree(p);
+  for (int i = 0; i < 3; ++i) {
+    if (A->aux[i]) cudaStreamDestroy(A->aux[i]);
+    if (A->ev_join[i]) cudaEventDestroy(A->ev_join[i]);
+  }
+  if (A->ev_fork) cudaEventDestroy(A->ev_fork);
 }
 
 int alloc_vectors(hspmv_matrix *A) {
@@ -336,28 +347,55 @@ int run_csr_vector(hspmv_matrix *A, const T *x, T *y, cudaStream_t st, int64_t r
   rc = ensure_bins(A);
   if (rc) return rc;
   static const int bin_vec[hspmv::NUM_BINS] = {1, 1, 2, 4, 8, 16, 32, 32};
-  int launches = 0;
-  for (int b = 0; b < hspmv::NUM_BINS; ++b) {
+  // The bins cover disjoint rows, so their launches are independent: they go round-robin to the caller's stream and
+  // three auxiliary streams (fork / join with events), and the tail of one bin's grid overlaps the next bin's start
+  // instead of idling the GPU eight times per product.
+  if (!A->ev_fork) {
+    CU(cudaEventCreateWithFlags(&A->ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < 3; ++i) {
+      CU(cudaStreamCreateWithFlags(&A->aux[i], cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&A->ev_join[i], cudaEventDisableTiming));
+    }
+  }
+  CU(cudaEventRecord(A->ev_fork, st));
+  for (int i = 0; i < 3; ++i) CU(cudaStreamWaitEvent(A->aux[i], A->ev_fork, 0));
+  int launches = 0, lane = 0;
+  // largest bins first (they take longest), the long-row pair stays on one stream
+  int order[hspmv::NUM_BINS];
+  for (int b = 0; b < hspmv::NUM_BINS; ++b) order[b] = b;
+  std::sort(order, order + hspmv::NUM_BINS, [&](int a, int b) {
+    const int64_t wa = (A->bin_ptr[a + 1] - A->bin_ptr[a]) * (int64_t)bin_vec[a] * (a == hspmv::NUM_BINS - 1 ? 64 : 1);
+    const int64_t wb = (A->bin_ptr[b + 1] - A->bin_ptr[b]) * (int64_t)bin_vec[b] * (b == hspmv::NUM_BINS - 1 ? 64 : 1);
+    return wa > wb;
+  });
+  for (int oi = 0; oi < hspmv::NUM_BINS; ++oi) {
+    const int b = order[oi];
     const int64_t cnt = A->bin_ptr[b + 1] - A->bin_ptr[b];
     if (!cnt) continue;
+    cudaStream_t s_ = lane == 0 ? st : A->aux[lane - 1];
+    lane = (lane + 1) & 3;
     const int *rows = A->d_bin_rows + A->bin_ptr[b];
     if (b == 0) {
-      hspmv::zero_rows_kernel<T><<<grid_for(cnt, 256, A->dev.sms * 8), 256, 0, st>>>(cnt, rows, y);
+      hspmv::zero_rows_kernel<T><<<grid_for(cnt, 256, A->dev.sms * 8), 256, 0, s_>>>(cnt, rows, y);
       LAUNCHED();
     } else if (b == hspmv::NUM_BINS - 1) {
       const int64_t ns = A->n_long_seg;
-      hspmv::csr_longrow_kernel<T><<<(int)(ns < A->dev.sms * 8 ? ns : A->dev.sms * 8), 256, 0, st>>>(
+      hspmv::csr_longrow_kernel<T><<<(int)(ns < A->dev.sms * 8 ? ns : A->dev.sms * 8), 256, 0, s_>>>(
           ns, A->d_long_seg, A->d_ci, (const T *)A->d_val, x, (T *)A->d_long_partial);
       LAUNCHED();
-      hspmv::longrow_reduce_kernel<T><<<grid_for(cnt, 256, A->dev.sms * 8), 256, 0, st>>>(cnt, rows, A->d_long_ptr,
+      hspmv::longrow_reduce_kernel<T><<<grid_for(cnt, 256, A->dev.sms * 8), 256, 0, s_>>>(cnt, rows, A->d_long_ptr,
                                                                                          (const T *)A->d_long_partial, y);
       LAUNCHED();
     } else {
-      launch_vector_vec<T>(A, bin_vec[b], true, rows, cnt, 0, x, y, st);
+      launch_vector_vec<T>(A, bin_vec[b], true, rows, cnt, 0, x, y, s_);
     }
     ++launches;
   }
-  std::snprintf(name, sizeof(name), "csr_vector<%s> binned (%d launches)", sizeof(T) == 8 ? "f64" : "f32", launches);
+  for (int i = 0; i < 3; ++i) {
+    CU(cudaEventRecord(A->ev_join[i], A->aux[i]));
+    CU(cudaStreamWaitEvent(st, A->ev_join[i], 0));
+  }
+  std::snprintf(name, sizeof(name), "csr_vector<%s> binned (%d launches on 4 streams)", sizeof(T) == 8 ? "f64" : "f32", launches);
   A->last_kernel = name;
   return HSPMV_OK;
 }
@@ -1197,6 +1235,49 @@ int hspmv_build_csrk(hspmv_matrix *A, int k, const int *sup_row_sizes) {
   return finish_csrk(A, k, perm, sr, ssr);
 }
 
+// Power-law matrices: renumber the COLUMNS by how often they are referenced, most popular first.  The x entries that
+// the gathers hit most become neighbours in memory (four of them per 32-byte sector, all hot), so the gathers hit L1 /
+// L2 instead of pulling a sector per entry from all over a 134 MB vector.  Rows are not moved: y keeps its numbering;
+// hspmv_set_x / hspmv_spmv_host permute x on the way in (x_kernel[i] = x[perm[i]]).
+int hspmv_relabel_hub_columns(hspmv_matrix *A, uint32_t *perm_out) {
+  if (!A) return fail(HSPMV_EINVAL, "null handle");
+  if (A->k != 1 || A->d_perm || A->sts_ready) return fail(HSPMV_ESTATE, "matrix is already reordered (CSR-k, STS or hub columns)");
+  if (A->n <= 0) return HSPMV_OK;
+  unsigned int *d_cnt = nullptr;
+  CU(cudaMalloc(&d_cnt, (size_t)A->n * 4));
+  CU(cudaMemsetAsync(d_cnt, 0, (size_t)A->n * 4, A->stream));
+  if (A->nnz) {
+    hspmv::col_count_kernel<<<grid_for(A->nnz, 256, A->dev.sms * 16), 256, 0, A->stream>>>(A->nnz, A->d_ci, d_cnt);
+    LAUNCHED();
+  }
+  std::vector<u32> cnt((size_t)A->n), perm((size_t)A->n), inv((size_t)A->n);
+  CU(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)A->n * 4, cudaMemcpyDeviceToHost, A->stream));
+  CU(cudaStreamSynchronize(A->stream));
+  // counting sort by descending count, ascending column id inside a count (deterministic, O(n + max count))
+  u32 mx = 0;
+  for (u32 c : cnt) mx = std::max(mx, c);
+  std::vector<int64_t> start((size_t)mx + 2, 0);
+  for (u32 c : cnt) ++start[(size_t)(mx - c) + 1];
+  for (size_t i = 1; i < start.size(); ++i) start[i] += start[i - 1];
+  for (int64_t c = 0; c < A->n; ++c) perm[(size_t)start[(size_t)(mx - cnt[(size_t)c])]++] = (u32)c;
+  for (int64_t i = 0; i < A->n; ++i) inv[perm[(size_t)i]] = (u32)i;
+  CU(cudaMemcpyAsync(d_cnt, inv.data(), (size_t)A->n * 4, cudaMemcpyHostToDevice, A->stream)); // reuse as new_id[]
+  if (A->nnz) {
+    hspmv::col_relabel_kernel<<<grid_for(A->nnz, 256, A->dev.sms * 16), 256, 0, A->stream>>>(A->nnz, d_cnt, A->d_ci);
+    LAUNCHED();
+  }
+  CU(cudaStreamSynchronize(A->stream));
+  cudaFree(d_cnt);
+  CU(cudaMalloc(&A->d_perm, (size_t)(A->n + PAD) * 4));
+  CU(cudaMemcpy(A->d_perm, perm.data(), (size_t)A->n * 4, cudaMemcpyHostToDevice));
+  A->cols_only_perm = true;
+  std::vector<int32_t>().swap(A->h_ci); // host copy (if any) is stale
+  free_pipe(A);
+  if (perm_out) std::memcpy(perm_out, perm.data(), perm.size() * 4);
+  A->h_perm.swap(perm);
+  return HSPMV_OK;
+}
+
 int hspmv_csrk_get(const hspmv_matrix *A, uint32_t *perm, uint32_t *sr_ptr, uint32_t *ssr_ptr) {
   if (!A) return fail(HSPMV_EINVAL, "null handle");
   if (A->k < 2) return fail(HSPMV_ESTATE, "not in CSR-k form");
@@ -1238,7 +1319,7 @@ int hspmv_get_y(hspmv_matrix *A, void *y_host, int original_order) {
   const size_t vs = A->vsize();
   // the last SpMV may have been enqueued on the caller's stream: order the read-back after it
   if (A->last_stream_valid && A->last_stream != A->stream) CU(cudaStreamSynchronize(A->last_stream));
-  if (original_order && A->d_perm) {
+  if (original_order && A->d_perm && !A->cols_only_perm) {
     const int grid = grid_for(A->m, 256, A->dev.sms * 16);
     if (A->dtype == HSPMV_F64)
       hspmv::scatter_kernel<double><<<grid, 256, 0, A->stream>>>(A->m, A->d_perm, (const double *)A->d_y, (double *)A->d_tmp);

@@ -815,6 +815,16 @@ __global__ void scatter_kernel(int64_t n, const uint32_t *__restrict__ perm,
        i += (int64_t)gridDim.x * blockDim.x)
     dst[perm[i]] = src[i];
 }
+// hspmv_relabel_hub_columns: how often every column is referenced; then ci[j] = new_id[ci[j]]
+static __global__ void col_count_kernel(int64_t nnz, const int *__restrict__ ci, unsigned int *__restrict__ count) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd(count + ci[i], 1u);
+}
+static __global__ void col_relabel_kernel(int64_t nnz, const uint32_t *__restrict__ new_id, int *__restrict__ ci) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x)
+    ci[i] = (int)new_id[ci[i]];
+}
+
 // sr_e[s] = rp[sr_ptr[s]]
 static __global__ void sr_offsets_kernel(int64_t n_sr, const uint32_t *__restrict__ sr_ptr,
                                   const int *__restrict__ rp, uint32_t *__restrict__ sr_e) {

@@ -76,6 +76,7 @@ struct hspmv_mg {
   std::vector<Shard> s;
   std::vector<int64_t> row_lo;
   std::vector<uint32_t> perm; // CSR-k: new -> old (x and y cross the boundary in the ORIGINAL numbering)
+  std::vector<uint32_t> xperm; // replicated power-law matrices: hub-column relabel, x only (new column -> old column)
   std::vector<unsigned char> stage; // host staging for permuted vectors
   size_t vs() const { return dtype == HSPMV_F64 ? 8 : 4; }
 };
@@ -175,6 +176,11 @@ int build_shards(hspmv_mg *M, hspmv_matrix *full, const int *devices, int n_dev)
       for (const Seg &g : send) b.insert(g.peer);
       if (a != b || a.size() > 32) M->replicated = true;
     }
+  }
+  if (M->replicated && k == 1 && M->m == M->n) { // power law: columns renumbered by popularity before the cut (x only)
+    M->xperm.resize((size_t)M->n);
+    MGCU(cudaSetDevice(devices[0]));
+    MGRC(hspmv_relabel_hub_columns(full, M->xperm.data()));
   }
   if (M->replicated || n_dev == 1) // the device holds all of x
     for (Shard &sh : M->s) {
@@ -366,18 +372,19 @@ int hspmv_mg_set_x(hspmv_mg *M, const void *x_host) {
   if (!M || !x_host) return mg_fail(HSPMV_EINVAL, "null");
   const size_t vs = M->vs();
   const char *src = (const char *)x_host;
-  if (!M->perm.empty()) { // setX: x_k[i] = x[perm[i]] (spmv-csrk/csrk.h:327-335)
+  const std::vector<uint32_t> &xp = !M->perm.empty() ? M->perm : M->xperm;
+  if (!xp.empty()) { // setX: x_k[i] = x[perm[i]] (spmv-csrk/csrk.h:327-335); hub relabel: the same, for x only
     M->stage.resize((size_t)M->n * vs);
     if (vs == 8) {
       const double *x = (const double *)x_host;
       double *o = (double *)M->stage.data();
 #pragma omp parallel for schedule(static)
-      for (int64_t i = 0; i < M->n; ++i) o[i] = x[M->perm[(size_t)i]];
+      for (int64_t i = 0; i < M->n; ++i) o[i] = x[xp[(size_t)i]];
     } else {
       const float *x = (const float *)x_host;
       float *o = (float *)M->stage.data();
 #pragma omp parallel for schedule(static)
-      for (int64_t i = 0; i < M->n; ++i) o[i] = x[M->perm[(size_t)i]];
+      for (int64_t i = 0; i < M->n; ++i) o[i] = x[xp[(size_t)i]];
     }
     src = (const char *)M->stage.data();
   }

@@ -354,6 +354,15 @@ int hspmv_mg_spmv_timed_batch(hspmv_mg *M, int warmup, int iters, float *ms_per_
 /* test hook: NaN into every halo region of both x buffers (only a correct push makes them finite again) */
 int hspmv_mg_poison_halos(hspmv_mg *M);
 
+/* ---- power-law matrices: hub-column relabel ---------------------------------------------------------
+ * Renumbers the COLUMNS of a plain-CSR handle by how often they are referenced (most popular first; ties by column
+ * id), in HBM.  The x entries the gathers hit most become neighbours in memory, so the gathers of an R-MAT-like matrix
+ * are served by L1 / L2 instead of pulling one 32-byte sector per 8-byte entry from all over x.  Rows are not moved
+ * (y keeps its numbering, the column order inside a row is no longer sorted); hspmv_set_x and hspmv_spmv_host apply
+ * the permutation to x on the way in, a caller that passes its own device x must supply x_kernel[i] = x[perm[i]].
+ * perm_out (optional): n entries, new column -> old column.  One-time set-up, like hspmv_build_csrk. */
+int hspmv_relabel_hub_columns(hspmv_matrix *A, uint32_t *perm_out);
+
 /* ---- STS: sparse triangular solve on CSR-k, k = 2, level-set ordering --------------------
  * Replaces, for kernel "STS" / order "LS" / k = 2: BAND_k::preprocessingForSTS (spmv-csrk/csrk.cpp:1522-1672,
  * find_levels :2704-2816, levels sorted by size), CSRk_Graph::reorderA, incomplete_choloskey (:708-789), compute_b

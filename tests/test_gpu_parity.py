@@ -643,3 +643,33 @@ def test_fused_halo_launch_single_gpu(hs, oracle, gen):
     hs.stream_wait_ge(st, flags, 7)                                               # already satisfied: returns
     torch.cuda.synchronize()
     hs.peer_free(flags)
+
+
+def test_hub_column_relabel_keeps_the_product(hs, oracle, gen):
+    """hspmv_relabel_hub_columns: columns renumbered by popularity (x permuted on the way in, y untouched)."""
+    for dtype in (np.float64, np.float32):
+        rp, ci, v = gen.rmat(14, 8, dtype=dtype)
+        n = len(rp) - 1
+        x = gen.vector_x(n, dtype)
+        y_ref = oracle.csr_spmv(rp, ci, v, x)
+        scale = oracle.abs_rowsum(rp, ci, v, x)
+        A = hs.Matrix.from_csr(rp, ci, v)
+        perm = A.relabel_hub_columns()
+        cnt = np.bincount(ci, minlength=n)
+        assert np.array_equal(np.sort(perm), np.arange(n, dtype=np.uint32))
+        assert np.all(np.diff(cnt[perm].astype(np.int64)) <= 0)                          # most referenced first
+        same = np.diff(cnt[perm].astype(np.int64)) == 0
+        assert np.all(np.diff(perm.astype(np.int64))[same] > 0)                          # ties by column id
+        d_rp, d_ci, d_v = A.download()
+        inv = np.empty(n, np.int64)
+        inv[perm] = np.arange(n)
+        assert np.array_equal(d_rp, rp) and np.array_equal(d_ci, inv[ci]) and np.array_equal(d_v, v)
+        A.set_x(x)
+        for algo in (hs.ALGO_AUTO, hs.ALGO_CSR_VECTOR, hs.ALGO_CSR_STREAM, hs.ALGO_CSR_MERGE, hs.ALGO_CSR_BLOCK):
+            A.set_y(np.full(n, np.nan, dtype))
+            A.spmv(algo)
+            assert_within_bound(A.get_y(), y_ref, scale, dtype, "hub relabel %s [%s]" % (hs.ALGO_NAMES[algo], A.last_kernel()))
+        assert_within_bound(A.spmv_host(x), y_ref, scale, dtype, "hub relabel, host call")
+        with pytest.raises(hs.HspmvError):
+            A.relabel_hub_columns()
+        A.close()
