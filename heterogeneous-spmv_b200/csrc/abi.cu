@@ -1706,7 +1706,9 @@ int hspmv_autotune(hspmv_matrix *A, int algo, int effort, float *best_ms) {
 int hspmv_spmv_host(hspmv_matrix *A, int algo, const void *x_host, void *y_host) {
   if (!A || !x_host || !y_host) return fail(HSPMV_EINVAL, "null");
   const int resolved = resolve_algo(A, algo);
-  if ((resolved == HSPMV_ALGO_CSR_STREAM || resolved == HSPMV_ALGO_CSR_VECTOR) && !A->opt[HSPMV_OPT_NO_PIPELINE]) {
+  // (the pipelined form launches row CHUNKS; only the tile engine takes them at full speed -- a binned matrix would run its
+  // chunks through the contiguous vector kernel, which is what the bins exist to avoid)
+  if (resolved == HSPMV_ALGO_CSR_STREAM && !A->opt[HSPMV_OPT_NO_PIPELINE]) {
     if (!A->pipe.tried) {
       int rc0 = build_pipe(A);
       if (rc0) return rc0;

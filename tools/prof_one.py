@@ -22,10 +22,11 @@ ap.add_argument("--opts", default="")
 ap.add_argument("--k", type=int, default=0)
 ap.add_argument("--sizes", default="32,8")
 ap.add_argument("--iters", type=int, default=5)
+ap.add_argument("--hub", action="store_true", help="hspmv_relabel_hub_columns before timing (power-law matrices)")
 ap.add_argument("--matrix", default="stencil", help="stencil (with --g/--kind) | cfg1 | cfg3 | cfg4 (BASELINE configs at full size)")
 a = ap.parse_args()
 dt = np.float64 if a.dtype == "f64" else np.float32
-OPT.update({"chunk": hs.OPT_CHUNK, "tail": hs.OPT_TAIL})
+OPT.update({"chunk": hs.OPT_CHUNK, "tail": hs.OPT_TAIL, "block": hs.OPT_BLOCK_NNZ})
 if a.matrix == "stencil":
     A = hs.Matrix.stencil(a.kind, a.g, dt, 0)
 else:
@@ -35,6 +36,8 @@ else:
     A = hs.Matrix.from_csr(rp, ci, v.astype(dt), keep_host=a.k >= 2)
 if a.k >= 2:
     A.build_csrk(a.k, [int(t) for t in a.sizes.split(",")])
+if a.hub:
+    A.relabel_hub_columns()
 A.fill_x_synthetic(0)
 for kv in filter(None, a.opts.split(",")):
     k, v = kv.split("=")
