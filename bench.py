@@ -354,7 +354,11 @@ def timed_formats(A, hs, algo, n, nnz, vs, extra=0, peak=6550.7, iters=20):
     t = float(np.median(ms))
     b2b = A.spmv_timed_batch(algo, warmup=5, iters=iters)
     b = alg_bytes(n, n, nnz, vs, extra)
-    return {"ms_flushed": t, "ms_back_to_back": b2b, "gflops_flushed": 2.0 * nnz / (t * 1e-3) / 1e9,
+    try:
+        graph = A.spmv_graph_timed(algo, iters=iters, reps=5)     # the same products as one CUDA-graph replay per `iters`
+    except Exception:      # noqa: BLE001
+        graph = None
+    return {"ms_flushed": t, "ms_back_to_back": b2b, "ms_graph_replay": graph, "gflops_flushed": 2.0 * nnz / (t * 1e-3) / 1e9,
             "gflops_back_to_back": 2.0 * nnz / (b2b * 1e-3) / 1e9,
             "roofline": {"algorithmic_bytes": b, "frac_measured_flushed": b / (t * 1e-3) / 1e9 / peak,
                          "frac_measured_back_to_back": b / (b2b * 1e-3) / 1e9 / peak,
@@ -442,6 +446,26 @@ def config_section(hs, np, peak, no_cpu):
                     cpu["csr%d" % k] = {"gflops": 2.0 * nnz / best[0] / 1e9, "ms": best[0] * 1e3,
                                         "sizes": [best[1]] if k == 2 else [best[1], 8]}
                 rec["cpu_reference"] = cpu
+            if key in ("cfg1", "cfg2"):
+                # triangular solve L x = b on the level-set-ordered matrix (k = 2, LS ordering), b = L * 1,
+                # beside the compiled reference's lowerSTS on the host cores
+                S = hs.Matrix.from_csr(rp, ci, v)
+                tb = time.time()
+                S.build_sts()
+                tb = time.time() - tb
+                S.sts_compute_b()
+                ms = S.sts_solve_timed(3, 10)
+                xs = S.sts_get_x()
+                nnz_l = (nnz + n) // 2
+                sts = {"packs": int(len(S.sts()["pack_ptr"]) - 1), "nnz_L": nnz_l, "build_s": tb, "ms": float(np.median(ms)),
+                       "gflops": 2.0 * nnz_l / float(np.median(ms)) / 1e6, "max_abs_x_minus_1": float(np.max(np.abs(xs - 1.0))),
+                       "algorithmic_gbs": (nnz_l * 12 + n * 28) / float(np.median(ms)) / 1e6, "kernel": S.last_kernel()}
+                S.close()
+                if O is not None and O.have_ref():
+                    R = O.RefSTS(rp, ci, v)
+                    sts["cpu_reference_ms"] = R.solve_timed(3, 10) * 1e3
+                    sts["cpu_reference_x_is_one"] = bool(np.all(R.solve() == 1.0))
+                rec["sts"] = sts
             rec["seconds"] = time.time() - t0
             out[key] = rec
         except Exception as e:      # noqa: BLE001  (an extra, never the reason for a missing bench line)

@@ -531,6 +531,15 @@ class Matrix:
         _check(lib().hspmv_spmv_timed_batch(self.h, int(algo), int(warmup), int(iters), C.byref(ms)))
         return ms.value
 
+    def spmv_graph(self, algo=ALGO_AUTO, iters=10, stream=None):
+        """`iters` products as one CUDA-graph replay (captured on first use)"""
+        _check(lib().hspmv_spmv_graph(self.h, int(algo), int(iters), C.c_void_p(stream)))
+
+    def spmv_graph_timed(self, algo=ALGO_AUTO, iters=20, reps=5):
+        ms = C.c_float()
+        _check(lib().hspmv_spmv_graph_timed(self.h, int(algo), int(iters), int(reps), C.byref(ms)))
+        return ms.value
+
     def autotune(self, algo=ALGO_AUTO, effort=1):
         """times the kernel shapes around the heuristic choice, keeps the fastest; returns its ms per launch"""
         ms = C.c_float()

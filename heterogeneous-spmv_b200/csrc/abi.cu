@@ -106,6 +106,11 @@ struct hspmv_matrix {
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
 
+  // hspmv_spmv_graph: `iters` products captured once as a CUDA graph
+  cudaGraphExec_t graph_exec = nullptr;
+  int graph_algo = -1, graph_iters = 0;
+  int64_t graph_launches = 0;
+
   // CSR_BLOCK
   int64_t block_cap = 0, block_max_rows = 0, n_blocks = 0;
   int *d_blk_row = nullptr;
@@ -167,6 +172,8 @@ void free_device(hspmv_matrix *A) {
     if (A->ev_join[i]) cudaEventDestroy(A->ev_join[i]);
   }
   if (A->ev_fork) cudaEventDestroy(A->ev_fork);
+  if (A->graph_exec) cudaGraphExecDestroy(A->graph_exec);
+  A->graph_exec = nullptr;
 }
 
 int alloc_vectors(hspmv_matrix *A) {
@@ -1395,6 +1402,7 @@ int hspmv_set_option(hspmv_matrix *A, int option, int64_t value) {
   if (option == HSPMV_OPT_VEC && value != 0 && (value < 1 || value > 32 || (value & (value - 1))))
     return fail(HSPMV_EINVAL, "HSPMV_OPT_VEC must be 0 or a power of two <= 32");
   A->opt[option] = value;
+  A->graph_iters = 0; // a captured graph froze the old option
   return HSPMV_OK;
 }
 
@@ -1521,6 +1529,64 @@ int hspmv_spmv_timed(hspmv_matrix *A, int algo, int warmup, int iters, int flush
   CU(cudaStreamSynchronize(A->stream));
   for (int i = 0; i < iters; ++i) CU(cudaEventElapsedTime(&ms_out[i], ev[(size_t)2 * i], ev[(size_t)2 * i + 1]));
   for (auto &e : ev) cudaEventDestroy(e);
+  return HSPMV_OK;
+}
+
+// Solver-style loops on matrices whose product takes tens of microseconds: `iters` products on the handle's own x / y,
+// captured ONCE as a CUDA graph (per handle, algo and iters; kernel options are frozen at capture) and replayed with one
+// host call, so neither the per-launch host cost nor the stream's launch-to-launch gap is paid `iters` times.
+int hspmv_spmv_graph(hspmv_matrix *A, int algo, int iters, void *stream) {
+  if (!A || iters < 1) return fail(HSPMV_EINVAL, "bad arguments");
+  cudaStream_t st = stream ? (cudaStream_t)stream : A->stream;
+  if (!A->graph_exec || A->graph_algo != algo || A->graph_iters != iters) {
+    if (A->graph_exec) cudaGraphExecDestroy(A->graph_exec);
+    A->graph_exec = nullptr;
+    int rc = do_spmv(A, algo, nullptr, nullptr, A->stream); // uncaptured first: lazy tables, attributes, module load
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(A->stream));
+    const int64_t before = g_launches.load();
+    cudaGraph_t graph = nullptr;
+    CU(cudaStreamBeginCapture(A->stream, cudaStreamCaptureModeThreadLocal));
+    for (int i = 0; i < iters && !rc; ++i) rc = do_spmv(A, algo, nullptr, nullptr, A->stream);
+    cudaError_t e = cudaStreamEndCapture(A->stream, &graph);
+    A->graph_launches = g_launches.load() - before;
+    g_launches.fetch_sub(A->graph_launches, std::memory_order_relaxed); // captured, not launched
+    if (rc) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (e != cudaSuccess) return fail(HSPMV_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&A->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(HSPMV_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    A->graph_algo = algo;
+    A->graph_iters = iters;
+  }
+  CU(cudaGraphLaunch(A->graph_exec, st));
+  g_launches.fetch_add(A->graph_launches, std::memory_order_relaxed);
+  A->last_stream = st;
+  A->last_stream_valid = true;
+  return HSPMV_OK;
+}
+
+// ms per product of `reps` replays of the `iters`-product graph
+int hspmv_spmv_graph_timed(hspmv_matrix *A, int algo, int iters, int reps, float *ms_per_product) {
+  if (!A || iters < 1 || reps < 1 || !ms_per_product) return fail(HSPMV_EINVAL, "bad arguments");
+  int rc = hspmv_spmv_graph(A, algo, iters, A->stream); // capture + one warm replay
+  if (rc) return rc;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, A->stream));
+  for (int r = 0; r < reps; ++r)
+    if ((rc = hspmv_spmv_graph(A, algo, iters, A->stream))) return rc;
+  CU(cudaEventRecord(e1, A->stream));
+  CU(cudaStreamSynchronize(A->stream));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_per_product = ms / (float)(iters * reps);
   return HSPMV_OK;
 }
 

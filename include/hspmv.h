@@ -238,6 +238,12 @@ int hspmv_spmv_host(hspmv_matrix *A, int algo, const void *x_host, void *y_host)
  * *ms_total covers every H2D copy of x, permutation, kernel and D2H copy of y. */
 int hspmv_spmv_host_timed(hspmv_matrix *A, int algo, const void *x_host, void *y_host, int iters,
                           float *ms_total);
+/* Solver-style loops on small matrices (a product of tens of microseconds): `iters` products on the handle's own
+ * x / y captured ONCE as a CUDA graph and replayed with one host call per `iters` products.  Replaces the reference
+ * drivers' launch + cudaDeviceSynchronize per product (cuda-spmv-csr/spmv.cu:240-260).  Options are frozen at capture;
+ * hspmv_set_option drops the graph. */
+int hspmv_spmv_graph(hspmv_matrix *A, int algo, int iters, void *stream);
+int hspmv_spmv_graph_timed(hspmv_matrix *A, int algo, int iters, int reps, float *ms_per_product);
 /* Name of the kernel variant the last hspmv_spmv on this handle launched (for reports). */
 const char *hspmv_last_kernel(const hspmv_matrix *A);
 

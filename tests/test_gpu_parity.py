@@ -673,3 +673,30 @@ def test_hub_column_relabel_keeps_the_product(hs, oracle, gen):
         with pytest.raises(hs.HspmvError):
             A.relabel_hub_columns()
         A.close()
+
+
+def test_graph_replay_equals_plain_launches(hs, oracle, gen):
+    """hspmv_spmv_graph: N products as one CUDA-graph replay -- same y, launch counter counts the captured kernels, options drop the graph."""
+    for maker, algo in ((lambda: gen.laplace2d_5pt(64, rcm=True, mode="varied"), hs.ALGO_AUTO), (lambda: gen.rmat(13, 8), hs.ALGO_AUTO),
+                        (lambda: gen.stencil27(14, mode="varied"), hs.ALGO_CSR_BLOCK)):
+        rp, ci, v = maker()
+        n = len(rp) - 1
+        x = gen.vector_x(n)
+        A = hs.Matrix.from_csr(rp, ci, v)
+        A.set_x(x)
+        A.spmv(algo)
+        y_plain = A.get_y()
+        A.set_y(np.full(n, np.nan))
+        before = hs.launch_count()
+        A.spmv_graph(algo, iters=4)
+        captured_per_replay = hs.launch_count() - before
+        assert np.array_equal(A.get_y(), y_plain)
+        assert captured_per_replay >= 4
+        A.set_y(np.full(n, np.nan))
+        A.spmv_graph(algo, iters=4)                         # replay of the cached graph
+        assert np.array_equal(A.get_y(), y_plain) and hs.launch_count() - before == 2 * captured_per_replay
+        assert A.spmv_graph_timed(algo, iters=8, reps=2) > 0
+        A.set_option(hs.OPT_VEC, 4)                         # drops the graph; the next call captures again
+        A.spmv_graph(algo, iters=2)
+        assert_within_bound(A.get_y(), oracle.csr_spmv(rp, ci, v, x), oracle.abs_rowsum(rp, ci, v, x), np.float64, "graph after option")
+        A.close()
