@@ -1630,7 +1630,9 @@ int build_pipe(hspmv_matrix *A) {
   P.tried = true;
   const size_t vs = A->vsize();
   if (A->d_perm || A->k != 1 || (size_t)A->m * vs < ((size_t)32 << 20)) return HSPMV_OK; // small or permuted: plain path
-  int C = (int)(A->m / (2 << 20));
+  // pieces of ~4 MB of y (and of x): fine enough that the three legs of the pipeline overlap on a shard of a few million
+  // rows (r2, N = 8: with four 16 MB pieces a call took twice the PCIe floor), coarse enough to amortise a copy's set-up
+  int C = (int)((size_t)A->m * vs / ((size_t)4 << 20));
   if (C < 4) C = 4;
   if (C > 32) C = 32;
   P.chunks = C;
