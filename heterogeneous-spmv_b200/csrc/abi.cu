@@ -504,8 +504,10 @@ int run_csrk(hspmv_matrix *A, bool stream_mode, const T *x, T *y, cudaStream_t s
   }
   const hspmv::CsrkVariant variant = pick_variant(vec, chunk, tail);
   int warps = (int)A->opt[HSPMV_OPT_WARPS];
-  if (warps <= 0) warps = 16; // r1 sweep: occupancy matters more than stage size (profiles/)
-  if (warps > 16) warps = 16;
+  // r1 sweep: occupancy matters more than stage size; r2: the shapes that fit 96 registers run 18 warps (640-thread build)
+  const bool wide_ok = hspmv::csrk_has_wide(variant);
+  if (warps <= 0) warps = wide_ok ? hspmv::CSRK_WIDE_WARPS : 16;
+  if (warps > (wide_ok ? 20 : 16)) warps = wide_ok ? 20 : 16;
   int stages = (int)A->opt[HSPMV_OPT_STAGES];
   if (stages <= 0) stages = 2;
 
@@ -593,6 +595,9 @@ int run_csrk(hspmv_matrix *A, bool stream_mode, const T *x, T *y, cudaStream_t s
     return (((size_t)w * stages * 8 + 127) & ~(size_t)127) +
            (size_t)w * stages * hspmv::csrk_stage_bytes(cn, cr, sizeof(T));
   };
+  // 18 warps only while their stages leave the x gathers ~30 KB of L1: with 19 warps (205 KB of stages) or with CSR-2's
+  // larger stages at 18 (202 KB) the kernel is 6-20 % SLOWER than with 16 (profiles/r2_ab_warps_per_sm.txt)
+  if (warps > 16 && !A->opt[HSPMV_OPT_WARPS] && total(warps, cap_nnz, cap_rows) > (size_t)198000) warps = 16;
   while (warps > 4 && total(warps, cap_nnz, cap_rows) > budget) --warps;
   while (total(warps, cap_nnz, cap_rows) > budget && cap_nnz > 64) cap_nnz = (cap_nnz * 3 / 4) & ~3;
   while (total(warps, cap_nnz, cap_rows) > budget && cap_rows > 8) cap_rows = (cap_rows / 2) & ~3;

@@ -40,6 +40,18 @@ template <typename T> int launch_csrk_group2(const CsrkParams<T> &p, int grid, i
 template <typename T> int launch_csrk_group4(const CsrkParams<T> &p, int grid, int warps, size_t smem, cudaStream_t st, int device, const CsrkVariant &v);
 template <typename T> int launch_csrk_group8(const CsrkParams<T> &p, int grid, int warps, size_t smem, cudaStream_t st, int device, const CsrkVariant &v);
 
+// shapes that also exist compiled for 640 threads per CTA (csrk_inst_wide.cu): X(vec, main, tail)
+#define HSPMV_CSRK_WIDE_VARIANTS(X) X(2, 13, 1) X(2, 12, 1)
+enum { CSRK_WIDE_WARPS = 18 };
+inline bool csrk_has_wide(const CsrkVariant &v) {
+#define X(vv, mm, tt) \
+  if (v.vec == vv && v.main == mm && v.tail == tt) return true;
+  HSPMV_CSRK_WIDE_VARIANTS(X)
+#undef X
+  return false;
+}
+template <typename T> int launch_csrk_wide(const CsrkParams<T> &p, int grid, int warps, size_t smem, cudaStream_t st, int device, const CsrkVariant &v);
+
 // the same groups with the halo support compiled in (csrk_inst_halo_*.cu)
 template <typename T> int launch_csrk_halo_group1(const CsrkParams<T> &p, int grid, int warps, size_t smem, cudaStream_t st, int device, const CsrkVariant &v);
 template <typename T> int launch_csrk_halo_group2(const CsrkParams<T> &p, int grid, int warps, size_t smem, cudaStream_t st, int device, const CsrkVariant &v);
@@ -49,6 +61,7 @@ template <typename T> int launch_csrk_halo_group8(const CsrkParams<T> &p, int gr
 template <typename T>
 inline int launch_csrk_variant(const CsrkParams<T> &p, int grid, int warps, size_t smem, cudaStream_t st,
                                int device, const CsrkVariant &v) {
+  if (warps > 16) return launch_csrk_wide<T>(p, grid, warps, smem, st, device, v); // only the caller's wide shapes get here
   if (p.n_ranges > 1 || p.n_wait > 0) { // hspmv_spmv_halo
     if (v.vec == 1) return launch_csrk_halo_group1<T>(p, grid, warps, smem, st, device, v);
     if (v.vec == 2) return launch_csrk_halo_group2<T>(p, grid, warps, smem, st, device, v);
@@ -61,9 +74,9 @@ inline int launch_csrk_variant(const CsrkParams<T> &p, int grid, int warps, size
   return launch_csrk_group8<T>(p, grid, warps, smem, st, device, v);
 }
 
-template <typename T, int VEC, int MAIN, int TAIL, bool HALO = false>
+template <typename T, int VEC, int MAIN, int TAIL, bool HALO = false, bool WIDE = false>
 inline int launch_csrk_one(const CsrkParams<T> &p, int grid, int warps, size_t smem, cudaStream_t st, int device) {
-  auto kern = csrk_tma_kernel<T, VEC, MAIN, TAIL, HALO>;
+  auto kern = csrk_tma_kernel<T, VEC, MAIN, TAIL, HALO, WIDE>;
   static size_t configured[64] = {0}; // per device: opt-in shared memory already granted
   size_t &have = configured[device & 63];
   if (smem > have) {

@@ -530,8 +530,12 @@ static __device__ __noinline__ void csrk_rows_halo_direct(int r0, int r1, const 
 
 // HALO = false: the kernel every single-GPU launch runs; it contains no trace of the halo support.  HALO = true
 // (hspmv_spmv_halo): up to three row ranges, the in-kernel flag wait and L2 gathers for the halo tiles.
-template <typename T, int VEC, int MAIN, int TAIL, bool HALO>
-__global__ void __launch_bounds__(512, 1) csrk_tma_kernel(const CsrkParams<T> p) {
+// WIDE = true: compiled for 640 threads per CTA (96 registers per thread instead of 128), launched with 18 warps.  Only
+// instantiated for the shapes that fit 96 registers without spilling and were measured faster that way (the 27-point
+// stencil shapes: 3.136 -> 3.082 ms on config 5; 20 warps are slower again -- their stages leave 20 KB of L1 for the x
+// gathers -- and the masked shapes spill; profiles/r2_ab_warps_per_sm.txt).
+template <typename T, int VEC, int MAIN, int TAIL, bool HALO, bool WIDE = false>
+__global__ void __launch_bounds__(WIDE ? 640 : 512, 1) csrk_tma_kernel(const CsrkParams<T> p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int w = threadIdx.x >> 5;
