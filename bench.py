@@ -352,15 +352,20 @@ def timed_formats(A, hs, algo, n, nnz, vs, extra=0, peak=6550.7, iters=20):
     import numpy as np
     ms = A.spmv_timed(algo, warmup=3, iters=iters, flush_l2=True)
     t = float(np.median(ms))
+    # the same with L2 left CLEAN (a read pass over a second buffer after the written one): a launch timed right after
+    # the memset also pays for the write-back of the memset's dirty lines, which is not part of the product
+    t_clean = float(np.median(A.spmv_timed(algo, warmup=1, iters=iters, flush_l2=2)))
     b2b = A.spmv_timed_batch(algo, warmup=5, iters=iters)
     b = alg_bytes(n, n, nnz, vs, extra)
     try:
         graph = A.spmv_graph_timed(algo, iters=iters, reps=5)     # the same products as one CUDA-graph replay per `iters`
     except Exception:      # noqa: BLE001
         graph = None
-    return {"ms_flushed": t, "ms_back_to_back": b2b, "ms_graph_replay": graph, "gflops_flushed": 2.0 * nnz / (t * 1e-3) / 1e9,
+    return {"ms_flushed": t, "ms_flushed_clean_l2": t_clean, "ms_back_to_back": b2b, "ms_graph_replay": graph,
+            "gflops_flushed": 2.0 * nnz / (t * 1e-3) / 1e9,
             "gflops_back_to_back": 2.0 * nnz / (b2b * 1e-3) / 1e9,
             "roofline": {"algorithmic_bytes": b, "frac_measured_flushed": b / (t * 1e-3) / 1e9 / peak,
+                         "frac_measured_flushed_clean_l2": b / (t_clean * 1e-3) / 1e9 / peak,
                          "frac_measured_back_to_back": b / (b2b * 1e-3) / 1e9 / peak,
                          "frac_nominal_flushed": b / (t * 1e-3) / 1e9 / NOMINAL_GBS,
                          "frac_nominal_back_to_back": b / (b2b * 1e-3) / 1e9 / NOMINAL_GBS},

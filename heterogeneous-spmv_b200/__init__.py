@@ -522,6 +522,7 @@ class Matrix:
 
     def spmv_timed(self, algo=ALGO_AUTO, warmup=3, iters=20, flush_l2=False):
         ms = np.zeros(iters, np.float32)
+        # flush_l2: False / True, or 2 = write + read flush (L2 left full of clean foreign lines)
         _check(lib().hspmv_spmv_timed(self.h, int(algo), int(warmup), int(iters), int(flush_l2), _p(ms)))
         return ms
 

@@ -141,7 +141,7 @@ struct hspmv_matrix {
   cudaStream_t stream = nullptr; // handle's own stream (timed runs, set_x/get_y)
   cudaStream_t last_stream = nullptr; // stream of the most recent hspmv_spmv (may be the caller's)
   bool last_stream_valid = false;
-  void *d_flush = nullptr;
+  void *d_flush = nullptr, *d_flush_rd = nullptr;
   size_t flush_bytes = 0;
   bool l2_window_set = false;
   std::string last_kernel;
@@ -164,7 +164,7 @@ void free_device(hspmv_matrix *A) {
   void *ptrs[] = {A->d_rp, A->d_ci, A->d_val, A->d_x, A->d_y, A->d_tmp, A->d_sr, A->d_ssr,
                   A->d_sr_e, A->d_perm, A->d_bin_rows, A->d_long_seg, A->d_long_ptr, A->d_long_partial,
                   A->d_tile_row, A->d_carry_row, A->d_blk_row, A->d_diag, A->d_pack, A->d_sts_b, A->d_sts_x,
-                  A->d_carry_val, A->d_flush};
+                  A->d_carry_val, A->d_flush, A->d_flush_rd};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   for (int i = 0; i < 3; ++i) {
@@ -1113,6 +1113,7 @@ int finish_csrk(hspmv_matrix *A, int k, std::vector<u32> &perm, std::vector<u32>
   A->bins_ready = false;
   A->merge_tile = 0;
   A->block_cap = 0;
+  A->graph_iters = 0; // a captured graph points at the old arrays
   free_pipe(A);
   hspmv::row_stats(A->m, A->h_rp.data(), A->stats);
   A->stats_ready = true;
@@ -1283,6 +1284,7 @@ int hspmv_relabel_hub_columns(hspmv_matrix *A, uint32_t *perm_out) {
   CU(cudaMalloc(&A->d_perm, (size_t)(A->n + PAD) * 4));
   CU(cudaMemcpy(A->d_perm, perm.data(), (size_t)A->n * 4, cudaMemcpyHostToDevice));
   A->cols_only_perm = true;
+  A->graph_iters = 0; // (the arrays stay where they are, but a replay must not be mistaken for the un-relabelled product)
   std::vector<int32_t>().swap(A->h_ci); // host copy (if any) is stale
   free_pipe(A);
   if (perm_out) std::memcpy(perm_out, perm.data(), perm.size() * 4);
@@ -1518,6 +1520,10 @@ int hspmv_spmv_timed(hspmv_matrix *A, int algo, int warmup, int iters, int flush
     A->flush_bytes = (size_t)A->dev.l2 * 2;
     CU(cudaMalloc(&A->d_flush, A->flush_bytes));
   }
+  if (flush_l2 == 2 && !A->d_flush_rd) { // second buffer, only read: evicts the first one's dirty lines
+    CU(cudaMalloc(&A->d_flush_rd, A->flush_bytes + 64));
+    CU(cudaMemset(A->d_flush_rd, 0, A->flush_bytes + 64));
+  }
   for (int i = 0; i < warmup; ++i) {
     int rc = do_spmv(A, algo, nullptr, nullptr, A->stream);
     if (rc) return rc;
@@ -1526,6 +1532,11 @@ int hspmv_spmv_timed(hspmv_matrix *A, int algo, int warmup, int iters, int flush
   for (auto &e : ev) CU(cudaEventCreate(&e));
   for (int i = 0; i < iters; ++i) {
     if (flush_l2) CU(cudaMemsetAsync(A->d_flush, i & 0xff, A->flush_bytes, A->stream));
+    if (flush_l2 == 2) {
+      hspmv::flush_read_kernel<<<A->dev.sms * 8, 256, 0, A->stream>>>((const int4 *)A->d_flush_rd, (int64_t)(A->flush_bytes / 16),
+                                                                       (int *)((char *)A->d_flush_rd + A->flush_bytes));
+      LAUNCHED();
+    }
     CU(cudaEventRecord(ev[(size_t)2 * i], A->stream));
     int rc = do_spmv(A, algo, nullptr, nullptr, A->stream);
     if (rc) return rc;
@@ -2251,6 +2262,7 @@ int hspmv_build_sts(hspmv_matrix *A) {
   // leading packs that one CTA of 1024 threads finishes in ONE pass run on CTA 0 alone (a block barrier per pack, ~2 us);
   // larger packs are worth a grid barrier (~3.5 us).  (r2 measurements, profiles/r2_sts_vs_reference_*.jsonl)
   const int64_t solo_rows = 1024 / sts_vec(A);
+  A->graph_iters = 0; // a captured graph points at the old arrays
   A->solo_packs = 0;
   while (A->solo_packs < A->n_packs && A->h_pack[(size_t)A->solo_packs + 1] - A->h_pack[(size_t)A->solo_packs] <= solo_rows) ++A->solo_packs;
   A->bins_ready = false;

@@ -819,6 +819,17 @@ __global__ void scatter_kernel(int64_t n, const uint32_t *__restrict__ perm,
        i += (int64_t)gridDim.x * blockDim.x)
     dst[perm[i]] = src[i];
 }
+// hspmv_spmv_timed, flush mode 2: read a second buffer larger than L2 after the written one, so that L2 ends up full of
+// CLEAN foreign lines (a kernel timed right after a memset also pays for the write-back of the memset's dirty lines)
+static __global__ void flush_read_kernel(const int4 *__restrict__ p, int64_t n16, int *sink) {
+  int acc = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
+    const int4 v = p[i];
+    acc ^= v.x ^ v.y ^ v.z ^ v.w;
+  }
+  if (acc == 0x5bd1e995) *sink = acc; // never true for a zeroed buffer: keeps the loads alive
+}
+
 // hspmv_relabel_hub_columns: how often every column is referenced; then ci[j] = new_id[ci[j]]
 static __global__ void col_count_kernel(int64_t nnz, const int *__restrict__ ci, unsigned int *__restrict__ count) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x)

@@ -211,8 +211,11 @@ int hspmv_spmv_range(hspmv_matrix *A, int algo, int64_t row_lo, int64_t row_hi, 
  * drivers (cuda-spmv-csr/spmv.cu:248, cuda-spmv-csrk/cuda/spmv.cu:200). */
 int hspmv_sync(hspmv_matrix *A);
 /* N timed launches after `warmup` untimed ones; ms_out[i] = device time of launch i from
- * CUDA events on the launching stream.  flush_l2 != 0 overwrites an L2-sized scratch buffer
- * before every launch (outside the event pair).  Replaces the host-timer loops at
+ * CUDA events on the launching stream.  flush_l2 = 1 overwrites a scratch buffer of twice the L2
+ * size before every launch (outside the event pair); L2 is then full of DIRTY foreign lines, whose
+ * write-back the timed launch also pays for.  flush_l2 = 2 additionally reads a second such buffer
+ * after the write, so that L2 is full of CLEAN foreign lines: the cold-cache time of the product
+ * alone.  Replaces the host-timer loops at
  * cuda-spmv-csr/spmv.cu:240-260 / spmv-auto-ampere.cu:205-230. */
 int hspmv_spmv_timed(hspmv_matrix *A, int algo, int warmup, int iters, int flush_l2,
                      float *ms_out);

@@ -435,7 +435,27 @@ def test_end_to_end_host_call_and_spmv_h_compat(hs, oracle, gen):
     hs.omp_spmv(n, n, len(ci), rp, ci, v, 2 * x, y2)
     assert_within_bound(y2, 2 * y_ref, 2 * scale, np.float64, "omp_spmv cached")
     assert hs.launch_count() >= before + 2
-    hs.lib().hspmv_omp_spmv_cache_clear()
+    L = hs.lib()
+    assert L.hspmv_omp_spmv_cache_size() == 1
+    # the arrays are refilled IN PLACE (same addresses, same sizes) -- the cache must notice and upload again
+    v[:] = 2.0 * v
+    y3 = np.zeros(n)
+    hs.omp_spmv(n, n, len(ci), rp, ci, v, x, y3)
+    assert_within_bound(y3, 2 * y_ref, 2 * scale, np.float64, "omp_spmv after the values changed in place")
+    assert L.hspmv_omp_spmv_cache_size() == 1
+    v[:] = 0.5 * v
+    # ... and the cache is bounded: six different matrices leave at most four resident
+    keep = []
+    for g_ in (5, 6, 7, 8, 9, 10):
+        m_ = gen.stencil27(g_, mode="varied")
+        keep.append(m_)
+        xx = gen.vector_x(len(m_[0]) - 1)
+        yy = np.zeros(len(xx))
+        hs.omp_spmv(len(xx), len(xx), len(m_[1]), m_[0], m_[1], m_[2], xx, yy)
+        assert_within_bound(yy, oracle.csr_spmv(m_[0], m_[1], m_[2], xx), oracle.abs_rowsum(m_[0], m_[1], m_[2], xx), np.float64, "omp_spmv g=%d" % g_)
+    assert L.hspmv_omp_spmv_cache_size() <= 4
+    L.hspmv_omp_spmv_cache_clear()
+    assert L.hspmv_omp_spmv_cache_size() == 0
     # CSR-k handle: host x in original order -> host y in original order
     A = hs.Matrix.from_csr(rp, ci, v)
     A.build_csrk(3, [20, 10])
