@@ -26,7 +26,7 @@ F32, F64 = 0, 1
 ALGO_AUTO, ALGO_CSR_VECTOR, ALGO_CSR_STREAM, ALGO_CSR_MERGE, ALGO_CSRK, ALGO_CSR_BLOCK = 0, 1, 2, 3, 4, 5
 ALGO_NAMES = {0: "auto", 1: "csr_vector", 2: "csr_stream", 3: "csr_merge", 4: "csrk", 5: "csr_block"}
 (OPT_VEC, OPT_WARPS, OPT_STAGES, OPT_STAGE_NNZ, OPT_CTAS_PER_SM, OPT_ROWS_PER_TILE,
- OPT_L2_PERSIST_X, OPT_MERGE_TILE, OPT_THREADS, OPT_CHUNK, OPT_NO_PIPELINE, OPT_BANDK_HOST, OPT_TAIL, OPT_BLOCK_NNZ) = range(1, 15)
+ OPT_L2_PERSIST_X, OPT_MERGE_TILE, OPT_THREADS, OPT_CHUNK, OPT_NO_PIPELINE, OPT_BANDK_HOST, OPT_TAIL, OPT_BLOCK_NNZ, OPT_STS_BARRIERS) = range(1, 16)
 ARCH_VOLTA, ARCH_AMPERE, ARCH_MI100, ARCH_B200 = 0, 1, 2, 3
 
 _lib = None
@@ -461,6 +461,11 @@ class Matrix:
 
     def sts_solve(self, stream=None):
         _check(lib().hspmv_sts_solve(self.h, C.c_void_p(stream)))
+
+    def sts_status(self):
+        t = C.c_int()
+        _check(lib().hspmv_sts_status(self.h, C.byref(t)))
+        return {"timed_out": bool(t.value)}
 
     def sts_get_x(self, original_order=False):
         x = np.zeros(self.info()["m"], self.dtype)

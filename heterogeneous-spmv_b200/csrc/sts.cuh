@@ -111,4 +111,60 @@ __global__ void __launch_bounds__(1024) sts_solve_kernel(int n_packs, int solo_p
   }
 }
 
+// ---- the solve without barriers ------------------------------------------------------------------------------
+// Rows are dealt to groups of VEC lanes in increasing order (group g takes rows g, g + G, g + 2G, ...; every group
+// of the launch is resident: cooperative launch).  A row waits for exactly the x entries it reads: ready[c] holds the
+// epoch of the solve that last wrote x[c]; a lane spins (bounded) on ready[c] with an acquire load, reads x[c] from L2,
+// and after the group's sum one lane writes x[r], fences, and publishes ready[r] = epoch.  No deadlock: L is lower
+// triangular in this numbering, so the smallest unfinished row never waits, and the group that owns it is AT it
+// (its earlier rows are smaller).  Consecutive packs overlap: a row starts as soon as ITS dependencies are done, not
+// when the whole previous level is -- the level-scheduled kernel above pays a block or grid barrier (~2-3.5 us) per
+// pack, this one a flag round trip through L2 per dependency chain link.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(512) sts_flags_kernel(int n, int epoch, const int *__restrict__ rp, const int *__restrict__ diag,
+                                                        const int *__restrict__ ci, const T *__restrict__ val,
+                                                        const T *__restrict__ b, T *x, int *ready, int *timed_out) {
+  const int sub = threadIdx.x & (VEC - 1);
+  const int group = (blockIdx.x * blockDim.x + threadIdx.x) / VEC, n_groups = gridDim.x * blockDim.x / VEC;
+  const unsigned gmask = VEC == 32 ? 0xffffffffu : (((1u << VEC) - 1u) << ((threadIdx.x & 31) & ~(VEC - 1)));
+  for (int r = group; r < n; r += n_groups) {
+    const int rs = rp[r], d = diag[r];
+    const T rhs = b[r], dia = val[d];
+    T acc = 0;
+    for (int j0 = rs + sub; j0 < d; j0 += 4 * VEC) { // (per-group trip count: the shuffles below name the group only)
+      int c[4];
+      T v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool ok = j0 + u * VEC < d;
+        c[u] = ok ? ci[j0 + u * VEC] : -1;
+        v[u] = ok ? val[j0 + u * VEC] : (T)0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (c[u] < 0) continue;
+        int seen;
+        const long long t0 = clock64();
+        for (;;) {
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(ready + c[u]) : "memory");
+          if (seen == epoch) break;
+          if (clock64() - t0 > 2000000000LL) { // ~1 s: never in a correct run; do not hang the device
+            atomicExch(timed_out, 1);
+            break;
+          }
+          __nanosleep(32); // a spinning lane must not crowd out the groups whose rows it is waiting for
+        }
+        acc += v[u] * __ldcg(x + c[u]);
+      }
+    }
+#pragma unroll
+    for (int o = VEC >> 1; o > 0; o >>= 1) acc += __shfl_down_sync(gmask, acc, o, VEC);
+    if (sub == 0) {
+      x[r] = (rhs - acc) / dia;
+      __threadfence();
+      asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(ready + r), "r"(epoch) : "memory");
+    }
+  }
+}
+
 } // namespace hspmv

@@ -63,6 +63,8 @@ enum {
   HSPMV_OPT_NO_PIPELINE = 11, /* 1: hspmv_spmv_host copies, computes, copies back strictly in sequence */
   HSPMV_OPT_TAIL = 13,        /* TMA kernels: masked gathers per lane per round (compiled: see csrc/csrk_variants.h); 0 = default */
   HSPMV_OPT_BANDK_HOST = 12,  /* 1: hspmv_build_csrk runs entirely on the host (default: coarse graph + reorderA in HBM) */
+  HSPMV_OPT_STS_BARRIERS = 15,/* hspmv_sts_solve: 1 = level-scheduled kernel (a block / grid barrier per pack), 2 = barrier-free (per-row
+                                 ready flags), 0 = by the mean pack size (barrier-free below 256 rows per pack) */
   HSPMV_OPT_BLOCK_NNZ = 14,   /* CSR_BLOCK: nonzeros per row block (256..16384; 0 = 2048) */
   HSPMV_OPT_CHUNK = 10        /* TMA kernels: unmasked x gathers a lane keeps in flight per chunk; 0 = auto, < 0 = masked loop only */
 };
@@ -387,7 +389,12 @@ int hspmv_sts_compute_b(hspmv_matrix *A); /* b = L * 1 (compute_b), left to righ
 /* original_order = 0: the solver's (reordered) numbering, as the reference's b / x arrays; 1: the input matrix' */
 int hspmv_sts_set_b(hspmv_matrix *A, const void *b_host, int original_order);
 int hspmv_sts_get_b(hspmv_matrix *A, void *b_host, int original_order);
-int hspmv_sts_solve(hspmv_matrix *A, void *stream); /* lowerSTS: packs in order, one cooperative launch */
+/* lowerSTS in one cooperative launch, in one of two forms (HSPMV_OPT_STS_BARRIERS; default: chosen by the mean pack
+ * size).  Level-scheduled: packs in order with a block / grid barrier between them.  Barrier-free: rows dealt to lane
+ * groups in increasing order, every row waits (bounded spin) for the ready flags of exactly the x entries it reads, so
+ * consecutive packs overlap. */
+int hspmv_sts_solve(hspmv_matrix *A, void *stream);
+int hspmv_sts_status(hspmv_matrix *A, int *timed_out); /* synchronises; *timed_out = 1 if a dependency wait ever gave up */
 int hspmv_sts_get_x(hspmv_matrix *A, void *x_host, int original_order);
 int hspmv_sts_solve_timed(hspmv_matrix *A, int warmup, int iters, float *ms_out);
 

@@ -108,11 +108,17 @@ def test_sts_on_gpu_against_the_reference(dtype, hs, oracle, gen):
         assert np.array_equal(l_rp, want["l_rp"]) and np.array_equal(l_ci, want["l_ci"]) and np.array_equal(l_val, want["l_val"]), name
         G.compute_b()
         assert np.array_equal(G.A.sts_get_b(), want["b"]), name
-        G.lowerSTS()
-        x = G.A.sts_get_x()
-        assert np.all(np.isfinite(x)), name
-        assert np.max(np.abs(x.astype(np.float64) - want["x"])) <= tol * np.max(np.abs(want["x"])), "%s [%s]" % (name, G.A.last_kernel())
-        assert abs(G.checkError()) <= tol * n
+        for barriers in (2, 1, 0):          # the barrier-free solve, the level-scheduled one, the library's choice
+            G.A.set_option(hs.OPT_STS_BARRIERS, barriers)
+            for _ in range(2):              # twice: the ready flags carry an epoch
+                G.lowerSTS()
+            x = G.A.sts_get_x()
+            assert barriers == 0 or ("sts_flags" if barriers == 2 else "sts_solve") in G.A.last_kernel()
+            assert not G.A.sts_status()["timed_out"]
+            assert np.all(np.isfinite(x)), name
+            assert np.max(np.abs(x.astype(np.float64) - want["x"])) <= tol * np.max(np.abs(want["x"])), "%s [%s]" % (name, G.A.last_kernel())
+            assert abs(G.checkError()) <= tol * n
+        G.A.set_option(hs.OPT_STS_BARRIERS, 0)
         # another right-hand side, given in the ORIGINAL numbering; x back in the original numbering
         b2 = (1.0 + (np.arange(n) % 13) / 16.0).astype(dtype)
         G.A.sts_set_b(b2, original_order=True)

@@ -31,11 +31,18 @@ for name, make in (("cfg1 laplace5 1000^2 rcm", lambda: G.laplace2d_5pt(1000, rc
     build_s = time.time() - t0
     s = A.sts()
     A.sts_compute_b()
+    A.set_option(hs.OPT_STS_BARRIERS, 1)
+    ms_bar = A.sts_solve_timed(3, 10)
+    kern_bar = A.last_kernel()
+    A.set_option(hs.OPT_STS_BARRIERS, 2)
+    ms_flags = A.sts_solve_timed(3, 10)
+    A.set_option(hs.OPT_STS_BARRIERS, 0)
     ms = A.sts_solve_timed(3, 10)
     x = A.sts_get_x()
     nnz_l = (len(ci) + n) // 2
     rec = {"matrix": name, "n": n, "nnz_L": nnz_l, "packs": len(s["pack_ptr"]) - 1, "build_s": build_s, "gpu_ms": float(np.median(ms)),
-           "gpu_gflops": 2.0 * nnz_l / float(np.median(ms)) / 1e6, "max_abs_x_minus_1": float(np.max(np.abs(x - 1.0))), "kernel": A.last_kernel()}
+           "gpu_gflops": 2.0 * nnz_l / float(np.median(ms)) / 1e6, "max_abs_x_minus_1": float(np.max(np.abs(x - 1.0))), "kernel": A.last_kernel(),
+           "level_scheduled_ms": float(np.median(ms_bar)), "barrier_free_ms": float(np.median(ms_flags)), "level_scheduled_kernel": kern_bar, "timed_out": A.sts_status()["timed_out"]}
     if O.have_ref():
         t0 = time.time()
         R = O.RefSTS(rp, ci, v)
