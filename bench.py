@@ -451,7 +451,7 @@ def config_section(hs, np, peak, no_cpu):
                     cpu["csr%d" % k] = {"gflops": 2.0 * nnz / best[0] / 1e9, "ms": best[0] * 1e3,
                                         "sizes": [best[1]] if k == 2 else [best[1], 8]}
                 rec["cpu_reference"] = cpu
-            if key in ("cfg1", "cfg2"):
+            if key in ("cfg1", "cfg2", "cfg3"):
                 # triangular solve L x = b on the level-set-ordered matrix (k = 2, LS ordering), b = L * 1,
                 # beside the compiled reference's lowerSTS on the host cores
                 S = hs.Matrix.from_csr(rp, ci, v)

@@ -26,7 +26,7 @@ F32, F64 = 0, 1
 ALGO_AUTO, ALGO_CSR_VECTOR, ALGO_CSR_STREAM, ALGO_CSR_MERGE, ALGO_CSRK, ALGO_CSR_BLOCK = 0, 1, 2, 3, 4, 5
 ALGO_NAMES = {0: "auto", 1: "csr_vector", 2: "csr_stream", 3: "csr_merge", 4: "csrk", 5: "csr_block"}
 (OPT_VEC, OPT_WARPS, OPT_STAGES, OPT_STAGE_NNZ, OPT_CTAS_PER_SM, OPT_ROWS_PER_TILE,
- OPT_L2_PERSIST_X, OPT_MERGE_TILE, OPT_THREADS, OPT_CHUNK, OPT_NO_PIPELINE, OPT_BANDK_HOST, OPT_TAIL, OPT_BLOCK_NNZ, OPT_STS_BARRIERS) = range(1, 16)
+ OPT_L2_PERSIST_X, OPT_MERGE_TILE, OPT_THREADS, OPT_CHUNK, OPT_NO_PIPELINE, OPT_BANDK_HOST, OPT_TAIL, OPT_BLOCK_NNZ, OPT_STS_BARRIERS, OPT_STS_GROUPS) = range(1, 17)
 ARCH_VOLTA, ARCH_AMPERE, ARCH_MI100, ARCH_B200 = 0, 1, 2, 3
 
 _lib = None

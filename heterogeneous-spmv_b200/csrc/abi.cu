@@ -138,7 +138,7 @@ struct hspmv_matrix {
     std::vector<cudaEvent_t> ev_x, ev_k;
   } pipe;
 
-  int64_t opt[16] = {0};
+  int64_t opt[32] = {0};
   cudaStream_t stream = nullptr; // handle's own stream (timed runs, set_x/get_y)
   cudaStream_t last_stream = nullptr; // stream of the most recent hspmv_spmv (may be the caller's)
   bool last_stream_valid = false;
@@ -1404,7 +1404,7 @@ int hspmv_fill_x_segments(void *d_x, int dtype, int n_seg, const int64_t *lo, co
 
 // ---- hot path ---------------------------------------------------------------------------
 int hspmv_set_option(hspmv_matrix *A, int option, int64_t value) {
-  if (!A || option < 1 || option > 15) return fail(HSPMV_EINVAL, "bad option");
+  if (!A || option < 1 || option > 31) return fail(HSPMV_EINVAL, "bad option");
   if (option == HSPMV_OPT_BLOCK_NNZ && value != 0 && (value < 256 || value > 16384))
     return fail(HSPMV_EINVAL, "HSPMV_OPT_BLOCK_NNZ must be 0 or within [256, 16384]");
   if (option == HSPMV_OPT_VEC && value != 0 && (value < 1 || value > 32 || (value & (value - 1))))
@@ -2142,12 +2142,17 @@ int launch_sts_flags(hspmv_matrix *A, cudaStream_t st) {
   case 16: kern = hspmv::sts_flags_kernel<T, 16>; break;
   default: kern = hspmv::sts_flags_kernel<T, 32>; vec = 32; break;
   }
-  const int threads = 512;
+  const int threads = 256;
   int per_sm = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0));
   if (per_sm < 1) return fail(HSPMV_ECUDA, "sts_flags_kernel does not fit on an SM");
-  if (per_sm > 2) per_sm = 2;
-  int grid = A->dev.sms * per_sm;
+  // Resident lane groups: as many as the device takes.  (Fewer groups -- "only as many as can run" -- was measured and is
+  // slower at every size: config 3 2.7 ms with all of them, 10.7 ms with 4096; tools/sts_groups_sweep.py.)
+  int64_t want_groups = A->opt[HSPMV_OPT_STS_GROUPS];
+  if (want_groups <= 0) want_groups = INT32_MAX;
+  int64_t grid64 = (want_groups * vec + threads - 1) / threads;
+  grid64 = std::max<int64_t>(1, std::min<int64_t>(grid64, (int64_t)A->dev.sms * per_sm));
+  int grid = (int)grid64;
   if (++A->sts_epoch == INT32_MAX) { // epochs never repeat within the life of the flag array
     CU(cudaMemsetAsync(A->d_ready, 0, (size_t)(A->m + 1) * 4, st));
     A->sts_epoch = 1;

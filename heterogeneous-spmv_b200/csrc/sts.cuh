@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(1024) sts_solve_kernel(int n_packs, int solo_p
 // when the whole previous level is -- the level-scheduled kernel above pays a block or grid barrier (~2-3.5 us) per
 // pack, this one a flag round trip through L2 per dependency chain link.
 template <typename T, int VEC>
-__global__ void __launch_bounds__(512) sts_flags_kernel(int n, int epoch, const int *__restrict__ rp, const int *__restrict__ diag,
+__global__ void __launch_bounds__(256) sts_flags_kernel(int n, int epoch, const int *__restrict__ rp, const int *__restrict__ diag,
                                                         const int *__restrict__ ci, const T *__restrict__ val,
                                                         const T *__restrict__ b, T *x, int *ready, int *timed_out) {
   const int sub = threadIdx.x & (VEC - 1);

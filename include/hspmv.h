@@ -65,6 +65,7 @@ enum {
   HSPMV_OPT_BANDK_HOST = 12,  /* 1: hspmv_build_csrk runs entirely on the host (default: coarse graph + reorderA in HBM) */
   HSPMV_OPT_STS_BARRIERS = 15,/* hspmv_sts_solve: 1 = level-scheduled kernel (a block / grid barrier per pack), 2 = barrier-free (per-row
                                  ready flags), 0 = by the mean pack size (barrier-free below 256 rows per pack) */
+  HSPMV_OPT_STS_GROUPS = 16,  /* barrier-free STS solve: resident lane groups (0 = as many as the device takes) */
   HSPMV_OPT_BLOCK_NNZ = 14,   /* CSR_BLOCK: nonzeros per row block (256..16384; 0 = 2048) */
   HSPMV_OPT_CHUNK = 10        /* TMA kernels: unmasked x gathers a lane keeps in flight per chunk; 0 = auto, < 0 = masked loop only */
 };
