@@ -399,6 +399,38 @@ def parity_vs_numpy(A, hs, rp, ci, v, x, algo, tol=1e-12, perm_order=True):
             "max_err_over_scale": float(np.nanmax(err / np.maximum(scale, 1e-300))) if len(y) else 0.0}
 
 
+def copy_same_bytes(torch, nbytes, iters=20):
+    """What a plain device copy moving the SAME number of bytes (half read, half written) achieves at this size, with L2
+    flushed by a write + read pass before every copy and back to back: the size-matched version of the peak in
+    MEASURED_PEAKS.json (which is a 2 x 2 GiB copy; an 80 MB transfer never reaches it -- ramp-up and launch are
+    a fixed ~10 us)."""
+    n = max(1, nbytes // 16)
+    a = torch.empty(n, dtype=torch.float64, device="cuda").normal_()
+    b = torch.empty_like(a)
+    fl_w = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    fl_r = torch.zeros(256 << 20, dtype=torch.uint8, device="cuda")
+    ts = []
+    for i in range(iters):
+        fl_w.fill_(i & 0xff)
+        fl_r.sum()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        b.copy_(a)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(5):
+        b.copy_(a)
+    e0.record()
+    for _ in range(iters):
+        b.copy_(a)
+    e1.record()
+    torch.cuda.synchronize()
+    return {"bytes": int(n * 16), "ms_flushed_clean_l2": ts[len(ts) // 2], "ms_back_to_back": e0.elapsed_time(e1) / iters}
+
+
 def config_section(hs, np, peak, no_cpu):
     """BASELINE configs[0..2] (cfg1-cfg3) on one GPU: CSR (AUTO kernel) and CSR-k k = 2 / 3 (B200 heuristic sizes,
     Band-k built in HBM), each with whole-y parity against a numpy product, flushed and back-to-back times, roofline
@@ -417,6 +449,11 @@ def config_section(hs, np, peak, no_cpu):
             n, nnz = len(rp) - 1, len(ci)
             x = G.vector_x(n)
             rec = {"workload": name, "n": n, "nnz": nnz, "formats": {}}
+            try:
+                import torch
+                rec["copy_same_bytes"] = copy_same_bytes(torch, alg_bytes(n, n, nnz))
+            except Exception as e:      # noqa: BLE001
+                rec["copy_same_bytes"] = {"error": "%s: %s" % (type(e).__name__, e)}
             A = hs.Matrix.from_csr(rp, ci, v)
             f = timed_formats(A, hs, hs.ALGO_AUTO, n, nnz, 8, 0, peak)
             f["parity"] = parity_vs_numpy(A, hs, rp, ci, v, x, hs.ALGO_AUTO)
