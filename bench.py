@@ -712,6 +712,8 @@ def run_ours(args, rank, world, local_rank):
             cmin, cmax = 0, n - 1
             A = full
         algo = hs.ALGO_CSRK
+    if args.warps:
+        A.set_option(hs.OPT_WARPS, args.warps)
     info = A.info()
     m_loc, nnz_loc = info["m"], info["nnz"]
     win = cmax - cmin + 1
@@ -783,7 +785,11 @@ def run_ours(args, rank, world, local_rank):
         if args.no_exchange:   # diagnosis only: local kernels without the halo traffic (halo stays NaN; invalid as a result)
             compute(0, m_loc)
             return
-        if sh.peer is not None:
+        if sh.peer is not None and args.x_update == "main":
+            sh.peer.reuse_buffer()
+            write_next_x(t, x_bufs[(sh.peer.step + 1) % 2], torch.cuda.current_stream())
+            sh.step(overlap=not args.no_overlap)
+        elif sh.peer is not None:
             # The slices of step t's buffer were written on the COMM stream behind the pushes of step t-1 (below), i.e.
             # while the previous product was still running: the update of x is the test's scaffolding, not part of the
             # product, and stays off the main stream's critical path.  The main stream only waits for its event.
@@ -1155,6 +1161,10 @@ def main():
     ap.add_argument("--no-hub", action="store_true", help="R-MAT: skip the hub-column relabel (hspmv_relabel_hub_columns)")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity record (diagnosis only)")
     ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--x-update", default="main", choices=["main", "comm"],
+                    help="N > 1: where the per-step rewrite of the exchanged x slices is enqueued: main = on the product's stream, in "
+                         "front of the kernel (default); comm = on the comm stream behind the previous step's pushes")
+    ap.add_argument("--warps", type=int, default=0, help="diagnosis: warps per CTA of the tile engine (0 = the library's choice)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "peer-unfused", "nccl"],
                     help="halo exchange: peer = copy-engine NVLink copies into IPC-mapped neighbour buffers + one fused "
                          "kernel per step that waits on the halo flags itself (default); peer-unfused = same transport, "
