@@ -506,7 +506,11 @@ int run_csrk(hspmv_matrix *A, bool stream_mode, const T *x, T *y, cudaStream_t s
   const hspmv::CsrkVariant variant = pick_variant(vec, chunk, tail);
   int warps = (int)A->opt[HSPMV_OPT_WARPS];
   // r1 sweep: occupancy matters more than stage size; r2: the shapes that fit 96 registers run 18 warps (640-thread build)
-  const bool wide_ok = hspmv::csrk_has_wide(variant);
+  // ... but only for a launch over the whole matrix: on the 8-GPU shards (hspmv_spmv_halo, 8 M rows per rank) 18 warps
+  // measured 6 % SLOWER than 16 on one box in one run (0.4463 vs 0.4201 ms per step, profiles/r2_ab_n8_warps_xupdate.txt),
+  // so halo launches and row-range launches keep the 16-warp form that every multi-GPU number of this round was taken with
+  const bool whole = !halo && (!stream_mode || (row_lo == 0 && (row_hi < 0 || row_hi == A->m)));
+  const bool wide_ok = whole && hspmv::csrk_has_wide(variant);
   if (warps <= 0) warps = wide_ok ? hspmv::CSRK_WIDE_WARPS : 16;
   if (warps > (wide_ok ? 20 : 16)) warps = wide_ok ? 20 : 16;
   int stages = (int)A->opt[HSPMV_OPT_STAGES];
