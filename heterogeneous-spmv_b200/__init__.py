@@ -252,6 +252,19 @@ def block_rows_host(row_ptr, cap, max_rows):
     return out[: nb.value + 1].copy() if m > 0 else out[:1].copy()
 
 
+def bandk_group_rows_host(row_ptr, threshold, literal=False):
+    """Band-k's greedy grouping of consecutive rows (csrk.cpp:1278-1292): (start[], grp[n]); literal=True runs the
+    row-by-row statement of the rule, False the forward scan hspmv_build_csrk uses."""
+    row_ptr = np.ascontiguousarray(row_ptr, dtype=np.uint32)
+    n = len(row_ptr) - 1
+    start = np.zeros(n + 2, np.uint32)
+    grp = np.zeros(max(n, 1), np.uint32)
+    ns = C.c_int64()
+    _check(lib().hspmv_bandk_group_rows_host(C.c_int64(n), _p(row_ptr), C.c_uint32(int(threshold)), int(bool(literal)), _p(start),
+                                             C.byref(ns), _p(grp)))
+    return start[: ns.value].copy(), grp[:n].copy()
+
+
 def sts_levels_host(row_ptr, col_idx):
     """Level sets of the triangular solve (kernel "STS", order "LS", k = 2) without a device: dict(perm new->old, pack_ptr)."""
     row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int32)

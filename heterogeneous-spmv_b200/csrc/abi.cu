@@ -2109,6 +2109,20 @@ int hspmv_block_rows_host(int64_t m, const int32_t *row_ptr, int64_t cap, int64_
   *n_blocks = (int64_t)b.size() - 1;
   return HSPMV_OK;
 }
+// Band-k grouping rule, both statements (for the tests): start[] has room for n + 2 entries, grp[n]
+int hspmv_bandk_group_rows_host(int64_t n, const uint32_t *row_ptr, uint32_t threshold, int literal, uint32_t *start,
+                                int64_t *n_starts, uint32_t *grp) {
+  if (!row_ptr || !start || !n_starts || !grp || n < 0) return fail(HSPMV_EINVAL, "bad arguments");
+  std::vector<u32> s, g;
+  if (literal)
+    hspmv::bandk_group_rows_literal(row_ptr, n, threshold, s, g);
+  else
+    hspmv::bandk_group_rows_fast(row_ptr, n, threshold, s, g);
+  std::memcpy(start, s.data(), s.size() * 4);
+  if (n) std::memcpy(grp, g.data(), (size_t)n * 4);
+  *n_starts = (int64_t)s.size();
+  return HSPMV_OK;
+}
 // row bins of the CSR_VECTOR path, host (for the bit-exactness tests): rows[m], bin_ptr[9]
 int hspmv_bin_rows_host(int64_t m, const int32_t *row_ptr, int32_t *rows, int64_t *bin_ptr) {
   if (!row_ptr || !rows || !bin_ptr) return fail(HSPMV_EINVAL, "null");

@@ -22,6 +22,8 @@ struct CoarseGraph {
 };
 u32 bandk_threshold(int size, int64_t nnz, int64_t n);
 void bandk_group_rows(const u32 *rp, int64_t n, u32 T, std::vector<u32> &start);
+void bandk_group_rows_literal(const u32 *rp, int64_t n, u32 T, std::vector<u32> &start, std::vector<u32> &grp);
+void bandk_group_rows_fast(const u32 *rp, int64_t n, u32 T, std::vector<u32> &start, std::vector<u32> &grp);
 int bandk_finish(int64_t n, int k, const int *sizes, CoarseGraph &level1, std::vector<u32> &map1,
                  std::vector<u32> &perm, std::vector<u32> &sr_ptr, std::vector<u32> &ssr_ptr);
 void reorder_f32(int64_t n, const u32 *perm, const u32 *rp, const u32 *ci, const float *v,

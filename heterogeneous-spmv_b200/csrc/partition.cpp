@@ -5,6 +5,9 @@
 #include "host_index.h"
 
 #include <algorithm>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 namespace hspmv {
 
@@ -43,13 +46,26 @@ int block_col_range(const int32_t *rp, const int32_t *ci, int64_t row_lo, int64_
   return HSPMV_OK;
 }
 
+// These three walk every row of matrices with up to 64 M rows (twice during a Band-k build), so they run on all host
+// cores: per-thread counts over contiguous row ranges, combined in thread order (the results do not depend on the
+// number of threads; bin_rows keeps the rows of a bin in ascending order).
 void row_stats(int64_t m, const int32_t *rp, int64_t out[10]) {
   for (int i = 0; i < 10; ++i) out[i] = 0;
   int64_t mx = 0;
-  for (int64_t r = 0; r < m; ++r) {
-    const int64_t len = (int64_t)rp[r + 1] - rp[r];
-    ++out[bin_of_len(len)];
-    mx = std::max(mx, len);
+#pragma omp parallel if (m > (1 << 16))
+  {
+    int64_t loc[NUM_BINS] = {0}, lmx = 0;
+#pragma omp for schedule(static) nowait
+    for (int64_t r = 0; r < m; ++r) {
+      const int64_t len = (int64_t)rp[r + 1] - rp[r];
+      ++loc[bin_of_len(len)];
+      lmx = std::max(lmx, len);
+    }
+#pragma omp critical
+    {
+      for (int b = 0; b < NUM_BINS; ++b) out[b] += loc[b];
+      mx = std::max(mx, lmx);
+    }
   }
   out[8] = mx;
   out[9] = out[0];
@@ -60,9 +76,16 @@ int64_t row_len_percentile(int64_t m, const int32_t *rp, int pct) {
   if (m <= 0) return 0;
   const int64_t cap = 1 << 16;
   std::vector<int64_t> hist((size_t)cap + 1, 0);
-  for (int64_t r = 0; r < m; ++r) {
-    const int64_t len = (int64_t)rp[r + 1] - rp[r];
-    ++hist[(size_t)(len < cap ? len : cap)];
+#pragma omp parallel if (m > (1 << 16))
+  {
+    std::vector<int64_t> loc((size_t)cap + 1, 0);
+#pragma omp for schedule(static) nowait
+    for (int64_t r = 0; r < m; ++r) {
+      const int64_t len = (int64_t)rp[r + 1] - rp[r];
+      ++loc[(size_t)(len < cap ? len : cap)];
+    }
+#pragma omp critical
+    for (int64_t l = 0; l <= cap; ++l) hist[(size_t)l] += loc[(size_t)l];
   }
   const int64_t need = (m * pct + 99) / 100;
   int64_t seen = 0;
@@ -74,14 +97,43 @@ int64_t row_len_percentile(int64_t m, const int32_t *rp, int pct) {
 }
 
 void bin_rows(int64_t m, const int32_t *rp, std::vector<int32_t> &rows, int64_t bin_ptr[NUM_BINS + 1]) {
-  int64_t cnt[NUM_BINS] = {0};
-  for (int64_t r = 0; r < m; ++r) ++cnt[bin_of_len((int64_t)rp[r + 1] - rp[r])];
+  int nt = 1;
+#ifdef _OPENMP
+  nt = m > (1 << 16) ? omp_get_max_threads() : 1;
+#endif
+  // cnt[t][b] = rows of bin b in thread t's contiguous row range
+  std::vector<int64_t> cnt((size_t)nt * NUM_BINS, 0);
+#pragma omp parallel num_threads(nt)
+  {
+    int t = 0;
+#ifdef _OPENMP
+    t = omp_get_thread_num();
+#endif
+    const int64_t lo = m * t / nt, hi = m * (t + 1) / nt;
+    int64_t *c = &cnt[(size_t)t * NUM_BINS];
+    for (int64_t r = lo; r < hi; ++r) ++c[bin_of_len((int64_t)rp[r + 1] - rp[r])];
+  }
   bin_ptr[0] = 0;
-  for (int b = 0; b < NUM_BINS; ++b) bin_ptr[b + 1] = bin_ptr[b] + cnt[b];
+  for (int b = 0; b < NUM_BINS; ++b) {
+    int64_t tot = 0;
+    for (int t = 0; t < nt; ++t) tot += cnt[(size_t)t * NUM_BINS + b];
+    bin_ptr[b + 1] = bin_ptr[b] + tot;
+  }
   rows.resize((size_t)m);
-  int64_t cur[NUM_BINS];
-  for (int b = 0; b < NUM_BINS; ++b) cur[b] = bin_ptr[b];
-  for (int64_t r = 0; r < m; ++r) rows[(size_t)cur[bin_of_len((int64_t)rp[r + 1] - rp[r])]++] = (int32_t)r;
+#pragma omp parallel num_threads(nt)
+  {
+    int t = 0;
+#ifdef _OPENMP
+    t = omp_get_thread_num();
+#endif
+    int64_t cur[NUM_BINS];
+    for (int b = 0; b < NUM_BINS; ++b) {
+      cur[b] = bin_ptr[b];
+      for (int u = 0; u < t; ++u) cur[b] += cnt[(size_t)u * NUM_BINS + b];
+    }
+    const int64_t lo = m * t / nt, hi = m * (t + 1) / nt;
+    for (int64_t r = lo; r < hi; ++r) rows[(size_t)cur[bin_of_len((int64_t)rp[r + 1] - rp[r])]++] = (int32_t)r;
+  }
 }
 
 void block_rows(int64_t m, const int32_t *rp, int64_t cap, int64_t max_rows, std::vector<int32_t> &blk_row) {

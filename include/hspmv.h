@@ -412,6 +412,11 @@ int64_t hspmv_row_len_percentile_host(int64_t m, const int32_t *row_ptr, int pct
  * alone); blk_row needs room for m + 2 entries. */
 int hspmv_block_rows_host(int64_t m, const int32_t *row_ptr, int64_t cap, int64_t max_rows, int32_t *blk_row,
                           int64_t *n_blocks);
+/* Band-k level grouping (handCoarsen's greedy walk, spmv-csrk/csrk.cpp:1278-1292): start[] of the groups (room for
+ * n + 2 entries), *n_starts entries written, grp[n] = group of every row.  literal != 0 runs the row-by-row statement
+ * of the rule, 0 the forward scan of row_ptr that hspmv_build_csrk uses; the tests compare the two. */
+int hspmv_bandk_group_rows_host(int64_t n, const uint32_t *row_ptr, uint32_t threshold, int literal, uint32_t *start,
+                                int64_t *n_starts, uint32_t *grp);
 /* CSR_VECTOR bins: rows[m] grouped by bin in ascending row order, bin_ptr[9]. */
 int hspmv_bin_rows_host(int64_t m, const int32_t *row_ptr, int32_t *rows, int64_t *bin_ptr);
 

@@ -50,8 +50,23 @@ CASES = [
 ]
 
 
+# The RCM of the coarse graph has two walks in the product (csrc/bandk.cpp): the serial queue walk and the level-
+# synchronous one that large graphs get.  HSPMV_RCM / HSPMV_RCM_CUTOFF force either on any graph, so every Band-k test
+# below runs as "auto" (serial at these sizes), with the level-synchronous walk forking on every level (cutoff 1), and
+# with it forking only on levels of >= 7 vertices (mixed serial / forked levels inside one search).
+RCM_MODES = [None, ("parallel", 1), ("parallel", 7)]
+
+
+@pytest.fixture(params=RCM_MODES, ids=["rcm-auto", "rcm-levelsync-cut1", "rcm-levelsync-cut7"])
+def rcm_mode(request, monkeypatch):
+    if request.param is not None:
+        monkeypatch.setenv("HSPMV_RCM", request.param[0])
+        monkeypatch.setenv("HSPMV_RCM_CUTOFF", str(request.param[1]))
+    return request.param
+
+
 @pytest.mark.parametrize("case", CASES, ids=["%s-k%d-%s" % (c[0], c[2], "x".join(map(str, c[3]))) for c in CASES])
-def test_bandk_host_bit_exact(case, hs, oracle, gen):
+def test_bandk_host_bit_exact(case, hs, oracle, gen, rcm_mode):
     g, kw, k, sizes = case
     rp, ci, v = getattr(gen, g)(**kw)
     a = hs.bandk_host(rp, ci, k, sizes)
@@ -67,7 +82,7 @@ def test_bandk_host_bit_exact(case, hs, oracle, gen):
             assert np.array_equal(p, q)
 
 
-def test_bandk_random_symmetric_graphs_against_oracle_and_reference(hs, oracle):
+def test_bandk_random_symmetric_graphs_against_oracle_and_reference(hs, oracle, rcm_mode):
     """60 random structurally symmetric matrices with a diagonal (disconnected pieces, hubs, many equal
     multiplicities -> RCM tie order): product builder == oracle restatement == the compiled reference."""
     import scipy.sparse as sp
@@ -93,7 +108,7 @@ def test_bandk_random_symmetric_graphs_against_oracle_and_reference(hs, oracle):
         want = oracle.bandk_build(rp, ci, k, sizes)
         for key in want:
             assert np.array_equal(got[key], want[key]), (trial, key, n, k, sizes)
-        if oracle.have_ref() and trial % 4 == 0:
+        if oracle.have_ref() and trial % 4 == 0 and rcm_mode != RCM_MODES[2]:
             R = oracle.RefCSRk(rp, ci, np.ones(len(ci), np.float32), k, sizes)
             maps = R.maps()
             perm = R.matrix()[0]
@@ -103,7 +118,7 @@ def test_bandk_random_symmetric_graphs_against_oracle_and_reference(hs, oracle):
                 assert np.array_equal(maps[1], got["ssr_ptr"]), (trial, "reference ssr")
 
 
-def test_bandk_golden_vectors(hs, gen):
+def test_bandk_golden_vectors(hs, gen, rcm_mode):
     import importlib.util
     gold = os.path.join(os.path.dirname(__file__), "golden")
     spec = importlib.util.spec_from_file_location("mg", os.path.join(gold, "make_golden.py"))
@@ -117,6 +132,41 @@ def test_bandk_golden_vectors(hs, gen):
         assert np.array_equal(a["perm"], g["perm"]) and np.array_equal(a["sr_ptr"], g["sr_ptr"]), path
         if k == 3:
             assert np.array_equal(a["ssr_ptr"], g["ssr_ptr"]), path
+
+
+def test_level_synchronous_rcm_equals_serial_walk_on_larger_graphs(hs, gen, monkeypatch):
+    """The two RCM walks on graphs whose levels are wide enough to be cut into several chunks, with odd thread counts,
+    on a graph of many components and on one with a hub: permutation and maps identical."""
+    import ctypes as C
+    import scipy.sparse as sp
+    rng = np.random.default_rng(7)
+    n = 30000
+    e = int(0.6 * n)                                                         # near the percolation threshold: pieces of every size
+    a = sp.coo_matrix((np.ones(e), (rng.integers(0, n, e), rng.integers(0, n, e))), shape=(n, n)).tocsr()
+    many_pieces = (a + a.T + sp.identity(n)).tocsr()                         # thousands of small components + a giant one
+    spokes = rng.choice(n, size=n // 4, replace=False)
+    star = sp.coo_matrix((np.ones(len(spokes)), (np.full(len(spokes), 5), spokes)), shape=(n, n)).tocsr()
+    hub = (many_pieces + star + star.T).tocsr()
+    graphs = [gen.stencil27(36)[:2], gen.laplace2d_5pt(300, rcm=True)[:2]]
+    for m in (many_pieces, hub):
+        m.sort_indices()
+        graphs.append((m.indptr.astype(np.int32), m.indices.astype(np.int32)))
+    gomp = C.CDLL("libgomp.so.1", mode=C.RTLD_GLOBAL)
+    before = gomp.omp_get_max_threads()
+    try:
+        for gi, (rp, ci) in enumerate(graphs):
+            for k, sizes in ((2, [3]), (3, [2, 3])):
+                monkeypatch.setenv("HSPMV_RCM", "serial")
+                want = hs.bandk_host(rp, ci, k, sizes)
+                for threads, cutoff in ((3, 1), (5, 64), (before, 300)):
+                    gomp.omp_set_num_threads(threads)
+                    monkeypatch.setenv("HSPMV_RCM", "parallel")
+                    monkeypatch.setenv("HSPMV_RCM_CUTOFF", str(cutoff))
+                    got = hs.bandk_host(rp, ci, k, sizes)
+                    for key in want:
+                        assert np.array_equal(got[key], want[key]), (gi, k, threads, cutoff, key)
+    finally:
+        gomp.omp_set_num_threads(before)
 
 
 def test_bandk_rejects_directed_graph_without_upper_entries(hs):
@@ -419,3 +469,70 @@ def test_block_rows_bit_exact(hs, gen):
             nnz = rp[b[1:]].astype(np.int64) - rp[b[:-1]]
             rows = np.diff(b)
             assert np.all((nnz <= cap) | (rows == 1)) and np.all(rows <= max_rows)
+
+
+def test_bandk_grouping_forward_scan_equals_the_literal_rule(hs):
+    """handCoarsen's greedy grouping (csrk.cpp:1278-1292) two ways: the row-by-row loop and the forward scan of
+    row_ptr the product uses -- same starts and same group of every row, for random row lengths (empty rows, empty
+    tails, rows longer than the threshold) and every small threshold, T = 0 included."""
+    rng = np.random.default_rng(5)
+    cases = 0
+    for trial in range(300):
+        n = int(rng.integers(1, 200))
+        kind = trial % 4
+        if kind == 0:
+            lens = rng.integers(0, 4, n)
+        elif kind == 1:
+            lens = rng.integers(0, 60, n)
+        elif kind == 2:
+            lens = np.where(rng.random(n) < 0.7, 0, rng.integers(1, 9, n))
+        else:
+            lens = np.full(n, int(rng.integers(0, 5)))
+        if trial % 5 == 0:
+            lens[int(rng.integers(0, n)):] = 0                       # trailing empty rows: no closing start
+        rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint32)
+        for T in [0, 1, 2, 3, int(rng.integers(1, 100)), int(rp[-1]) + 1]:
+            a_start, a_grp = hs.bandk_group_rows_host(rp, T, literal=True)
+            b_start, b_grp = hs.bandk_group_rows_host(rp, T, literal=False)
+            assert np.array_equal(a_start, b_start), (trial, T, lens.tolist())
+            assert np.array_equal(a_grp, b_grp), (trial, T, lens.tolist())
+            cases += 1
+    assert cases == 1800
+    # the literal rule itself, restated in Python, on one case
+    rp = np.array([0, 3, 3, 10, 11, 11, 12, 20], np.uint32)
+    start, grp = hs.bandk_group_rows_host(rp, 4, literal=True)
+    acc, g, want_s, want_g = 0, 0, [0], []
+    for v in range(7):
+        ln = int(rp[v + 1] - rp[v])
+        if acc < 4:
+            acc += ln
+        else:
+            g, acc = g + 1, ln
+            want_s.append(v)
+        want_g.append(g)
+    want_s.append(7)
+    assert start.tolist() == want_s and grp.tolist() == want_g
+
+
+def test_row_walks_do_not_depend_on_the_thread_count(hs):
+    """bin_rows / row_len_percentile run on all host cores above 65536 rows: same answer as the numpy rule with 1, 3
+    and all threads (rows of a bin stay in ascending order)."""
+    import ctypes as C
+    rng = np.random.default_rng(3)
+    m = 150_001
+    lens = rng.integers(0, 70, m)
+    lens[rng.integers(0, m, 50)] = 5000
+    lens[rng.integers(0, m, 5000)] = 0
+    rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    want_rows, want_bp = PO.bin_rows(rp)
+    gomp = C.CDLL("libgomp.so.1", mode=C.RTLD_GLOBAL)
+    before = gomp.omp_get_max_threads()
+    try:
+        for nt in (1, 3, before):
+            gomp.omp_set_num_threads(nt)
+            rows, bp = hs.bin_rows_host(rp)
+            assert np.array_equal(rows, want_rows) and np.array_equal(bp, want_bp), nt
+            for pct in (50, 90, 100):
+                assert hs.row_len_percentile(rp, pct) == PO.row_len_percentile(rp, pct), (nt, pct)
+    finally:
+        gomp.omp_set_num_threads(before)
