@@ -79,6 +79,7 @@ struct hspmv_matrix {
   int *d_rp = nullptr, *d_ci = nullptr;
   void *d_val = nullptr, *d_x = nullptr, *d_y = nullptr, *d_tmp = nullptr;
   u32 *d_sr = nullptr, *d_ssr = nullptr, *d_sr_e = nullptr, *d_perm = nullptr;
+  u32 *d_dims = nullptr; // hspmv_device_view_get: {n_rows, n_cols, nnz, n_coarsest} as device words
 
   // CSR_VECTOR bins
   bool bins_ready = false;
@@ -165,7 +166,7 @@ void free_device(hspmv_matrix *A) {
   void *ptrs[] = {A->d_rp, A->d_ci, A->d_val, A->d_x, A->d_y, A->d_tmp, A->d_sr, A->d_ssr,
                   A->d_sr_e, A->d_perm, A->d_bin_rows, A->d_long_seg, A->d_long_ptr, A->d_long_partial,
                   A->d_tile_row, A->d_carry_row, A->d_blk_row, A->d_diag, A->d_pack, A->d_ready, A->d_sts_b, A->d_sts_x,
-                  A->d_carry_val, A->d_flush, A->d_flush_rd};
+                  A->d_carry_val, A->d_flush, A->d_flush_rd, A->d_dims};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   for (int i = 0; i < 3; ++i) {
@@ -1364,6 +1365,26 @@ int hspmv_sync(hspmv_matrix *A) {
   if (!A) return fail(HSPMV_EINVAL, "null handle");
   if (A->last_stream_valid) CU(cudaStreamSynchronize(A->last_stream));
   CU(cudaStreamSynchronize(A->stream));
+  return HSPMV_OK;
+}
+
+int hspmv_device_view_get(hspmv_matrix *A, hspmv_device_view *out) {
+  if (!A || !out) return fail(HSPMV_EINVAL, "null");
+  const int64_t coarsest = A->k == 3 ? A->n_ssr : A->k == 2 ? A->n_sr : A->m;
+  if (!A->d_dims) CU(cudaMalloc(&A->d_dims, 4 * sizeof(u32)));
+  const u32 dims[4] = {(u32)A->m, (u32)A->n, (u32)A->nnz, (u32)coarsest};
+  CU(cudaMemcpy(A->d_dims, dims, sizeof(dims), cudaMemcpyHostToDevice));
+  out->row_ptr = A->d_rp;
+  out->col_idx = A->d_ci;
+  out->val = A->d_val;
+  out->x = A->d_x;
+  out->y = A->d_y;
+  out->sr_ptr = A->k >= 2 ? A->d_sr : nullptr;
+  out->ssr_ptr = A->k == 3 ? A->d_ssr : nullptr;
+  out->dims = A->d_dims;
+  out->n_coarsest = coarsest;
+  out->dtype = A->dtype;
+  out->k = A->k;
   return HSPMV_OK;
 }
 

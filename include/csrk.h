@@ -39,6 +39,13 @@ class CSRk_Graph {
   std::vector<unsigned int> perm_;
   val_type *y_;
 
+  // include/csrk.cuh (the CUDA flavour) points the reference's device-pointer globals at the handle's arrays here
+  void bind_() {
+#ifdef HSPMV_CSRK_BIND_DEVICE_GLOBALS
+    HSPMV_CSRK_BIND_DEVICE_GLOBALS(A_);
+#endif
+  }
+
   static void die(const char *what) {
     std::cout << what << ": " << hspmv_last_error() << std::endl;
     std::exit(1);
@@ -59,6 +66,7 @@ public:
     if (hspmv_create_csr(&A_, nRows, nCols, nnz, (const int32_t *)rVec, (const int32_t *)cVec, value,
                          HSPMV_VAL_DTYPE, 0, /*keep_host=*/1))
       die("CSRk_Graph");
+    bind_();
   }
 
   ~CSRk_Graph() { hspmv_destroy(A_); }
@@ -68,6 +76,7 @@ public:
     if (hspmv_build_csrk(A_, k_, sizes_.data())) die("putInCSRkFormat");
     perm_.resize((size_t)N_);
     if (hspmv_csrk_get(A_, perm_.data(), NULL, NULL)) die("getPermutation");
+    bind_(); // the reordered arrays replaced the uploaded ones
   }
 
   unsigned int *getPermutation() { return perm_.empty() ? NULL : perm_.data(); }

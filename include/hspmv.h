@@ -186,6 +186,22 @@ int hspmv_set_y(hspmv_matrix *A, const void *y_host);
 /* Library-owned device vectors of the handle (x in kernel order, n entries; y, m entries). */
 void *hspmv_x_device(hspmv_matrix *A);
 void *hspmv_y_device(hspmv_matrix *A);
+/* The device arrays behind a handle, for callers that launch their OWN kernels on them the way the reference's
+ * CUDA drivers do -- cuda-spmv-csrk/cuda/spmv.cu:33-44 declares these as `extern` device-pointer globals
+ * (r_vec_gpu, c_vec_gpu, val_gpu, x_test_gpu, y_gpu, mapCoarseToFinerRows_gpu_outer / _inner, and the device WORDS
+ * N_gpu, M_gpu, NNZ_gpu, numCoarsestRows_gpu) that csrk.cu:putInCSRkFormat fills; include/csrk.cuh binds them from
+ * this view.  All pointers are library-owned device memory, valid until the handle is destroyed or reordered
+ * (hspmv_build_csrk / hspmv_build_sts / hspmv_relabel_hub_columns replace the matrix arrays: fetch the view again).
+ * sr_ptr / ssr_ptr are NULL when the level does not exist; dims = device uint32[4] {n_rows, n_cols, nnz, n_coarsest}
+ * with n_coarsest = n_ssr (k = 3), n_sr (k = 2) or n_rows (k = 1). */
+typedef struct hspmv_device_view {
+  void *row_ptr, *col_idx, *val, *x, *y; /* uint32[m+1], uint32[nnz], T[nnz], T[n], T[m] */
+  void *sr_ptr, *ssr_ptr;                /* uint32[n_sr+1], uint32[n_ssr+1] */
+  void *dims;                            /* device uint32[4] */
+  int64_t n_coarsest;
+  int dtype, k;
+} hspmv_device_view;
+int hspmv_device_view_get(hspmv_matrix *A, hspmv_device_view *out);
 /* x_i = 1 + ((global_offset + i) mod 97)/128 written straight into the handle's device x
  * (generators.py:vector_x; the non-constant x the parity tests use instead of the reference's
  * x = 1, which is blind to permutation errors -- SURVEY.md section 4). */
