@@ -26,7 +26,9 @@
 // For speed, replace the launch line by A_mat.SpMV(): same result, the library's own launch.
 #ifndef HSPMV_COMPAT_CSRK_CUH
 #define HSPMV_COMPAT_CSRK_CUH
+#ifndef HSPMV_COMPAT_HOST_EMULATION // tests/compat/emulate_cuda.h runs the kernels below on host threads instead
 #include <cuda_runtime.h>
+#endif
 
 struct hspmv_matrix;
 static inline void hspmv_compat_bind_device_globals(hspmv_matrix *A);
