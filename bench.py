@@ -467,7 +467,8 @@ def config_section(hs, np, peak, no_cpu):
                 tb = time.time() - tb
                 i = B.info()
                 f = timed_formats(B, hs, hs.ALGO_CSRK, n, nnz, 8, (i["n_sr"] + i["n_ssr"] + 2) * 4, peak)
-                f.update({"sizes": sizes[: k - 1], "n_sr": i["n_sr"], "n_ssr": i["n_ssr"], "bandk_build_s": tb})
+                f.update({"sizes": sizes[: k - 1], "n_sr": i["n_sr"], "n_ssr": i["n_ssr"], "bandk_build_s": tb,
+                          "bandk_phases_s": B.build_phases()})
                 f["parity"] = parity_vs_numpy(B, hs, rp, ci, v, x, hs.ALGO_CSRK)
                 rec["formats"]["csr%d" % k] = f
                 B.close()
@@ -1087,7 +1088,7 @@ def run_ours(args, rank, world, local_rank):
                 gbs = alg_bytes(n, n, nnz_total, 8, (i["n_sr"] + i["n_ssr"] + 2) * 4) / (t * 1e-3) / 1e9
                 formats["csr%d" % k] = {"gflops": 2.0 * nnz_total / (t * 1e-3) / 1e9, "ms": t, "sizes": sizes[: k - 1],
                                         "n_sr": i["n_sr"], "n_ssr": i["n_ssr"], "bandk_build_s": tb,
-                                        "gbs": gbs, "frac_measured": gbs / peak_gbs, "frac_nominal": gbs / NOMINAL_GBS,
+                                        "bandk_phases_s": B.build_phases(), "gbs": gbs, "frac_measured": gbs / peak_gbs, "frac_nominal": gbs / NOMINAL_GBS,
                                         "kernel": B.last_kernel()}
                 B.close()
             line["formats"] = formats

@@ -430,6 +430,13 @@ class Matrix:
         sizes = (C.c_int * 2)(*(list(sup_row_sizes) + [0])[:2])
         _check(lib().hspmv_build_csrk(self.h, int(k), sizes))
 
+    def build_phases(self):
+        """wall seconds of the last build_csrk by phase (device builder; zeros when the host builder ran)"""
+        out = (C.c_double * 6)()
+        _check(lib().hspmv_build_phases(self.h, out, 6))
+        names = ["host_prep", "coarse_graph_device", "rcm_levels_host", "reorder_device", "maps_stats", "total"]
+        return {k: float(v) for k, v in zip(names, out)}
+
     def csrk(self):
         i = self.info()
         perm = np.zeros(i["m"], np.uint32)

@@ -7,6 +7,8 @@
 #include "merge.cuh"
 #include "csrk_variants.h"
 #include "bandk_gpu.h"
+
+#include <chrono>
 #include "sts.cuh"
 
 #include <algorithm>
@@ -79,6 +81,10 @@ struct hspmv_matrix {
   int *d_rp = nullptr, *d_ci = nullptr;
   void *d_val = nullptr, *d_x = nullptr, *d_y = nullptr, *d_tmp = nullptr;
   u32 *d_sr = nullptr, *d_ssr = nullptr, *d_sr_e = nullptr, *d_perm = nullptr;
+  // wall seconds of the last hspmv_build_csrk by phase (hspmv_build_phases): 0 host prep (row_ptr download, row
+  // statistics, grouping), 1 level-1 coarse graph in HBM + its download, 2 RCM / level 2 / uncoarsening on the host
+  // cores, 3 A' = P A P^T (permutation upload, reorder, row_ptr download), 4 maps + statistics of the new matrix, 5 total
+  double build_phase[6] = {0, 0, 0, 0, 0, 0};
   u32 *d_dims = nullptr; // hspmv_device_view_get: {n_rows, n_cols, nnz, n_coarsest} as device words
 
   // CSR_VECTOR bins
@@ -1137,6 +1143,15 @@ const char *bandk_error(int rc) {
 // Returns BANDK_USE_HOST when the host builder has to take over.
 int build_csrk_device(hspmv_matrix *A, int k, const int *sizes) {
   const size_t vs = A->vsize();
+  typedef std::chrono::steady_clock Clock;
+  Clock::time_point t_prev = Clock::now();
+  const Clock::time_point t_begin = t_prev;
+  for (double &d : A->build_phase) d = 0;
+  auto lap = [&](int phase) {
+    const Clock::time_point now = Clock::now();
+    A->build_phase[phase] += std::chrono::duration<double>(now - t_prev).count();
+    t_prev = now;
+  };
   if (A->h_rp.empty()) {
     A->h_rp.resize((size_t)A->m + 1);
     CU(cudaMemcpy(A->h_rp.data(), A->d_rp, (size_t)(A->m + 1) * 4, cudaMemcpyDeviceToHost));
@@ -1148,6 +1163,7 @@ int build_csrk_device(hspmv_matrix *A, int k, const int *sizes) {
   std::vector<u32> start;
   hspmv::bandk_group_rows((const u32 *)A->h_rp.data(), A->m, hspmv::bandk_threshold(sizes[0], A->nnz, A->m), start);
   if (start.back() != (u32)A->m) return hspmv::BANDK_USE_HOST; // trailing empty rows: the host path reports it
+  lap(0);
   hspmv::CoarseGraph level1;
   int64_t launches = 0;
   int rc = hspmv::coarse_level1_device(A->m, A->nnz, (const u32 *)A->d_rp, (const u32 *)A->d_ci, start, A->dev.sms,
@@ -1156,9 +1172,11 @@ int build_csrk_device(hspmv_matrix *A, int k, const int *sizes) {
   if (rc == hspmv::BANDK_USE_HOST) return rc;
   if (rc == HSPMV_ECUDA) return fail(rc, std::string("Band-k device build: ") + cudaGetErrorString(cudaGetLastError()));
   if (rc) return fail(rc, bandk_error(rc));
+  lap(1);
   std::vector<u32> perm, sr, ssr;
   rc = hspmv::bandk_finish(A->m, k, sizes, level1, start, perm, sr, ssr);
   if (rc) return fail(rc, bandk_error(rc));
+  lap(2);
 
   // reordered arrays next to the old ones, then swap
   int *rp2 = nullptr, *ci2 = nullptr;
@@ -1199,7 +1217,11 @@ int build_csrk_device(hspmv_matrix *A, int k, const int *sizes) {
   CU(cudaMemcpy(A->h_rp.data(), A->d_rp, (size_t)(A->m + 1) * 4, cudaMemcpyDeviceToHost));
   std::vector<int32_t>().swap(A->h_ci); // host copies of the un-reordered entries are stale now
   std::vector<unsigned char>().swap(A->h_val);
-  return finish_csrk(A, k, perm, sr, ssr);
+  lap(3);
+  rc = finish_csrk(A, k, perm, sr, ssr);
+  lap(4);
+  A->build_phase[5] = std::chrono::duration<double>(Clock::now() - t_begin).count();
+  return rc;
 }
 
 } // namespace
@@ -1365,6 +1387,12 @@ int hspmv_sync(hspmv_matrix *A) {
   if (!A) return fail(HSPMV_EINVAL, "null handle");
   if (A->last_stream_valid) CU(cudaStreamSynchronize(A->last_stream));
   CU(cudaStreamSynchronize(A->stream));
+  return HSPMV_OK;
+}
+
+int hspmv_build_phases(const hspmv_matrix *A, double *seconds, int n) {
+  if (!A || !seconds || n < 0) return fail(HSPMV_EINVAL, "null");
+  for (int i = 0; i < n; ++i) seconds[i] = i < 6 ? A->build_phase[i] : 0.0;
   return HSPMV_OK;
 }
 

@@ -186,6 +186,12 @@ int hspmv_set_y(hspmv_matrix *A, const void *y_host);
 /* Library-owned device vectors of the handle (x in kernel order, n entries; y, m entries). */
 void *hspmv_x_device(hspmv_matrix *A);
 void *hspmv_y_device(hspmv_matrix *A);
+/* Wall seconds of the last hspmv_build_csrk that ran the device builder, by phase (up to n = 6 entries): 0 host
+ * preparation (row_ptr download, row statistics, greedy grouping -- csrk.cpp:1278-1292), 1 level-1 coarse graph in HBM
+ * and its download (handCoarsen, :1243-1437), 2 RCM / level 2 / uncoarsening on the host cores (:2289-2475, :1148-1224),
+ * 3 A' = P A P^T in HBM (reorderA, :548-676), 4 CSR-k maps and statistics of the new matrix, 5 total.  All zero when
+ * the host builder ran.  bench.py prints them beside `bandk_build_s`. */
+int hspmv_build_phases(const hspmv_matrix *A, double *seconds, int n);
 /* The device arrays behind a handle, for callers that launch their OWN kernels on them the way the reference's
  * CUDA drivers do -- cuda-spmv-csrk/cuda/spmv.cu:33-44 declares these as `extern` device-pointer globals
  * (r_vec_gpu, c_vec_gpu, val_gpu, x_test_gpu, y_gpu, mapCoarseToFinerRows_gpu_outer / _inner, and the device WORDS
