@@ -113,8 +113,9 @@ int destroy_shards(hspmv_mg *M) {
   return HSPMV_OK;
 }
 
-// `full` lives on devices[0]; cut it into shards, one per device.  Takes ownership of `full`.
-int build_shards(hspmv_mg *M, hspmv_matrix *full, const int *devices, int n_dev) {
+// `full` lives on devices[0]; cut it into shards, one per device.  Takes ownership of `full`: it is destroyed (and the
+// caller's pointer cleared) once the shards exist; on an earlier failure the caller still holds it and frees it.
+int build_shards(hspmv_mg *M, hspmv_matrix *&full, const int *devices, int n_dev) {
   int k = 1;
   int64_t n_sr = 0, n_ssr = 0;
   MGRC(hspmv_matrix_info(full, &M->m, &M->n, &M->nnz, &M->dtype, &k, &n_sr, &n_ssr));
@@ -211,6 +212,7 @@ int build_shards(hspmv_mg *M, hspmv_matrix *full, const int *devices, int n_dev)
   }
   MGCU(cudaSetDevice(devices[0]));
   hspmv_destroy(full);
+  full = nullptr;
   if (M->replicated || n_dev == 1) return HSPMV_OK;
   // ---- exchange plan
   for (int d = 0; d < n_dev; ++d) {
@@ -272,8 +274,14 @@ int finish_create(hspmv_mg **out, hspmv_matrix *full, const int *devices, int n_
   hspmv_mg *M = new hspmv_mg();
   int rc = build_shards(M, full, devices, n_dev);
   if (rc) {
+    const std::string why = g_mg_err; // the clean-up below must not replace the reason
     destroy_shards(M);
     delete M;
+    if (full) {
+      cudaSetDevice(devices[0]);
+      hspmv_destroy(full);
+    }
+    g_mg_err = why;
     return rc;
   }
   *out = M;
