@@ -349,10 +349,12 @@ struct RcmPar {
       : g(gr), nt(threads), cutoff(cut), open((size_t)gr.n, 1), seen((size_t)gr.n, NONE), posn((size_t)gr.n, NONE),
         order((size_t)gr.n, 0), cbuf((size_t)threads * 8), coff((size_t)threads * 8 + 1, 0) {}
 
-  template <typename W> static inline void atomic_min(W *p, W v) {
-    W cur = __atomic_load_n(p, __ATOMIC_RELAXED);
-    while (v < cur && !__atomic_compare_exchange_n(p, &cur, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
-    }
+  // atomic min; true when THIS call lowered the word (the caller then holds the claim until a smaller one arrives)
+  static inline bool claim_min(u32 *p, u32 v) {
+    u32 cur = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v < cur)
+      if (__atomic_compare_exchange_n(p, &cur, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) return true;
+    return false;
   }
   size_t chunks_of(size_t len) const { return std::max<size_t>(1, std::min<size_t>((len + 255) / 256, cbuf.size())); }
   template <typename W> static inline W peek(const W *p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
@@ -377,12 +379,7 @@ struct RcmPar {
     coff[0] = cnt;
 #pragma omp parallel num_threads(nt)
     {
-#pragma omp for schedule(dynamic, 128)
-      for (int64_t i = (int64_t)begin; i < (int64_t)end; ++i) {
-        const int v = order[(size_t)i];
-        const u32 mine = (u32)i + 1;
-        for (u32 e = g.rp[(size_t)v]; e < g.rp[(size_t)v + 1]; ++e) atomic_min(&seen[g.adj[e]], mine);
-      }
+      // phase A: claims; a chunk remembers (in walk order) the neighbours it claimed and for which position
 #pragma omp for schedule(dynamic, 1)
       for (int64_t c = 0; c < (int64_t)nchunk; ++c) {
         std::vector<u32> &buf = cbuf[(size_t)c];
@@ -393,12 +390,24 @@ struct RcmPar {
           const u32 mine = (u32)i + 1;
           for (u32 e = g.rp[(size_t)v]; e < g.rp[(size_t)v + 1]; ++e) {
             const u32 w = g.adj[e];
-            if (peek(&seen[w]) == mine) {
-              poke(&seen[w], 0u);
+            if (claim_min(&seen[w], mine)) {
               buf.push_back(w);
+              buf.push_back(mine);
             }
           }
         }
+      }
+      // phase B: what a chunk claimed and still owns (no smaller position took it since) is its find, in walk order
+#pragma omp for schedule(dynamic, 1)
+      for (int64_t c = 0; c < (int64_t)nchunk; ++c) {
+        std::vector<u32> &buf = cbuf[(size_t)c];
+        size_t kept = 0;
+        for (size_t t = 0; t < buf.size(); t += 2)
+          if (peek(&seen[buf[t]]) == buf[t + 1]) {
+            poke(&seen[buf[t]], 0u);
+            buf[kept++] = buf[t];
+          }
+        buf.resize(kept);
       }
 #pragma omp single
       for (size_t c = 0; c < nchunk; ++c) coff[c + 1] = coff[c] + cbuf[c].size();
@@ -500,12 +509,8 @@ struct RcmPar {
         coff[0] = end;
 #pragma omp parallel num_threads(nt)
         {
-#pragma omp for schedule(dynamic, 128)
-          for (int64_t i = (int64_t)begin; i < (int64_t)end; ++i) {
-            const u32 p = q[(size_t)i];
-            const u32 mine = UNNUMBERED | (u32)i;
-            for (u32 e = g.rp[p]; e < g.rp[(size_t)p + 1]; ++e) atomic_min(&posn[g.adj[e]], mine); // numbers are smaller: untouched
-          }
+          // phase A: every p builds and sorts its list once and claims its unnumbered entries in sorted order; the chunk
+          // remembers what it claimed (numbers are smaller than any claim, so an atomic min leaves numbered vertices alone)
           std::vector<DegId> cand;
 #pragma omp for schedule(dynamic, 1)
           for (int64_t c = 0; c < (int64_t)nchunk; ++c) {
@@ -516,11 +521,23 @@ struct RcmPar {
               candidates(q[i], (u32)i, cand);
               const u32 mine = UNNUMBERED | (u32)i;
               for (size_t k = 0; k < cand.size(); ++k)
-                if (peek(&posn[cand[k].id]) == mine) {
-                  poke(&posn[cand[k].id], TAKEN);
+                if (claim_min(&posn[cand[k].id], mine)) {
                   buf.push_back(cand[k].id);
+                  buf.push_back(mine);
                 }
             }
+          }
+          // phase B: keep what is still owned, in (p, rank in p's sorted list) order
+#pragma omp for schedule(dynamic, 1)
+          for (int64_t c = 0; c < (int64_t)nchunk; ++c) {
+            std::vector<u32> &buf = cbuf[(size_t)c];
+            size_t kept = 0;
+            for (size_t t = 0; t < buf.size(); t += 2)
+              if (peek(&posn[buf[t]]) == buf[t + 1]) {
+                poke(&posn[buf[t]], TAKEN);
+                buf[kept++] = buf[t];
+              }
+            buf.resize(kept);
           }
 #pragma omp single
           for (size_t c = 0; c < nchunk; ++c) coff[c + 1] = coff[c] + cbuf[c].size();

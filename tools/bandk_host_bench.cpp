@@ -46,6 +46,16 @@ int main(int argc, char **argv) {
     std::printf("RCM serial walk %.3f s   level-synchronous %.3f s   identical permutation: %s\n", t1 - t0, t2 - t1,
                 (a == c && b == d) ? "yes" : "NO");
   }
+  { // where the level-synchronous walk spends its time (first component only: the stand-in is connected)
+    RcmPar s(g, nt, cutoff);
+    std::vector<u32> q((size_t)g.n);
+    double t0 = now();
+    const int root = s.peripheral(0);
+    double t1 = now();
+    s.number_component(root, 0, q);
+    double t2 = now();
+    std::printf("level-synchronous walk: pseudo-peripheral search (%zu levels) %.3f s, numbering %.3f s\n", s.lvl_ptr.size() - 1, t1 - t0, t2 - t1);
+  }
   const int64_t n = 64000000;
   std::vector<u32> rp((size_t)n + 1);
   rp[0] = 0;
