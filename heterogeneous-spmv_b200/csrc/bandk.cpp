@@ -312,16 +312,17 @@ void rcm_order(const Coarse &g, std::vector<u32> &new2old, std::vector<u32> &old
 // half of the whole Band-k build.  Both of its pieces are breadth-first searches, so they can run one LEVEL at
 // a time on every core and still produce the serial visit order bit for bit:
 //   * rooted level structure (levels_from): a vertex of level L+1 is discovered by the frontier vertex with
-//     the SMALLEST position that lists it, and within one discoverer in adjacency order.  Phase A lets every
-//     frontier position claim its undiscovered neighbours with an atomic min; phase B walks the frontier in
-//     contiguous chunks and keeps the neighbours whose claim is the walker's own position, in adjacency
-//     order; the chunks are concatenated in chunk order.
+//     the SMALLEST position that lists it, and within one discoverer in adjacency order.  Phase A walks the
+//     frontier in contiguous chunks; every frontier position claims its undiscovered neighbours with an atomic
+//     min on one word per vertex, and a chunk remembers, in walk order, the claims that succeeded.  Phase B keeps
+//     the remembered claims the chunk still owns (no smaller position took them since); the chunks are
+//     concatenated in chunk order.
 //   * Cuthill-McKee numbering: the serial queue marks a vertex when it is DEQUEUED, so the candidate list of a
 //     vertex p is "every neighbour that is dequeued after p" -- the neighbours not numbered yet plus those of
 //     p's own level with a larger number -- sorted with the same std::sort call on the same sequence; the
 //     vertex is numbered where it FIRST enters the queue, i.e. by its smallest-numbered neighbour, at its rank
-//     in that neighbour's sorted list.  Phase A claims as above, phase B builds and sorts each p's list and
-//     emits the entries p owns in sorted order.
+//     in that neighbour's sorted list.  Phase A builds and sorts each p's list once and claims its unnumbered
+//     entries in sorted order; phase B keeps what is still owned, as above.
 // Levels below `cutoff` vertices are expanded by one thread (no fork), so a long thin graph costs what the
 // serial walk costs.  tests/test_host_index.py runs both walks against the oracle and the compiled reference.
 struct RcmPar {
