@@ -24,6 +24,7 @@
 #include <vector>
 
 using hspmv::u32;
+using hspmv::uvec;
 
 namespace {
 
@@ -132,7 +133,7 @@ struct hspmv_matrix {
   // host copies (kept on request; needed for Band-k)
   std::vector<int32_t> h_rp, h_ci;
   std::vector<unsigned char> h_val;
-  std::vector<u32> h_perm, h_sr, h_ssr;
+  uvec h_perm, h_sr, h_ssr;
 
   // pipelined host call (hspmv_spmv_host on large regular matrices): x pieces go up, row chunks
   // are computed as soon as the pieces they reference have landed, y chunks go down meanwhile
@@ -1084,7 +1085,7 @@ int hspmv_row_stats(const hspmv_matrix *A, int64_t out[10]) {
 int hspmv_bandk_host(int64_t n, int64_t nnz, const uint32_t *row_ptr, const uint32_t *col_idx, int k,
                      const int *sup_row_sizes, uint32_t *perm, uint32_t *sr_ptr, int64_t *n_sr,
                      uint32_t *ssr_ptr, int64_t *n_ssr) {
-  std::vector<u32> p, sr, ssr;
+  uvec p, sr, ssr;
   int rc = hspmv::bandk_build(n, nnz, row_ptr, col_idx, k, sup_row_sizes, p, sr, ssr);
   if (rc) return fail(rc, rc == HSPMV_EUNSUPPORTED
                               ? "Band-k: a coarse vertex has no upper/diagonal entry (matrix must be structurally symmetric with a stored diagonal)"
@@ -1115,7 +1116,7 @@ int hspmv_reorder_host(int64_t n, int64_t nnz, const uint32_t *perm, const uint3
 namespace {
 
 // CSR-k bookkeeping shared by the host and the device builder: maps, stats, stale caches
-int finish_csrk(hspmv_matrix *A, int k, std::vector<u32> &perm, std::vector<u32> &sr, std::vector<u32> &ssr) {
+int finish_csrk(hspmv_matrix *A, int k, uvec &perm, uvec &sr, uvec &ssr) {
   A->k = k;
   A->h_perm.swap(perm);
   A->h_sr.swap(sr);
@@ -1160,7 +1161,7 @@ int build_csrk_device(hspmv_matrix *A, int k, const int *sizes) {
   int rc0 = ensure_stats(A);
   if (rc0) return rc0;
   if (A->stats[8] > hspmv::BANDK_MAX_ROW) return hspmv::BANDK_USE_HOST; // longest row vs the warp sorter
-  std::vector<u32> start;
+  uvec start;
   hspmv::bandk_group_rows((const u32 *)A->h_rp.data(), A->m, hspmv::bandk_threshold(sizes[0], A->nnz, A->m), start);
   if (start.back() != (u32)A->m) return hspmv::BANDK_USE_HOST; // trailing empty rows: the host path reports it
   lap(0);
@@ -1173,7 +1174,7 @@ int build_csrk_device(hspmv_matrix *A, int k, const int *sizes) {
   if (rc == HSPMV_ECUDA) return fail(rc, std::string("Band-k device build: ") + cudaGetErrorString(cudaGetLastError()));
   if (rc) return fail(rc, bandk_error(rc));
   lap(1);
-  std::vector<u32> perm, sr, ssr;
+  uvec perm, sr, ssr;
   rc = hspmv::bandk_finish(A->m, k, sizes, level1, start, perm, sr, ssr);
   if (rc) return fail(rc, bandk_error(rc));
   lap(2);
@@ -1251,7 +1252,7 @@ int hspmv_build_csrk(hspmv_matrix *A, int k, const int *sup_row_sizes) {
     A->h_val.resize((size_t)A->nnz * vs);
     if (A->nnz) CU(cudaMemcpy(A->h_val.data(), A->d_val, (size_t)A->nnz * vs, cudaMemcpyDeviceToHost));
   }
-  std::vector<u32> perm, sr, ssr;
+  uvec perm, sr, ssr;
   int rc = hspmv::bandk_build(A->m, A->nnz, (const u32 *)A->h_rp.data(), (const u32 *)A->h_ci.data(), k,
                               sup_row_sizes, perm, sr, ssr);
   if (rc) return fail(rc, bandk_error(rc));
@@ -1291,7 +1292,7 @@ int hspmv_relabel_hub_columns(hspmv_matrix *A, uint32_t *perm_out) {
     hspmv::col_count_kernel<<<grid_for(A->nnz, 256, A->dev.sms * 16), 256, 0, A->stream>>>(A->nnz, A->d_ci, d_cnt);
     LAUNCHED();
   }
-  std::vector<u32> cnt((size_t)A->n), perm((size_t)A->n), inv((size_t)A->n);
+  uvec cnt((size_t)A->n), perm((size_t)A->n), inv((size_t)A->n);
   CU(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)A->n * 4, cudaMemcpyDeviceToHost, A->stream));
   CU(cudaStreamSynchronize(A->stream));
   // counting sort by descending count, ascending column id inside a count (deterministic, O(n + max count))
@@ -1984,7 +1985,7 @@ int hspmv_slice_rows(const hspmv_matrix *A, int64_t row_lo, int64_t row_hi, int6
   // CSR-k: the cut must not split a super-row (k = 2) / super-super-row (k = 3)
   int64_t s0 = 0, s1 = 0, t0 = 0, t1 = 0;
   if (A->k >= 2) {
-    auto find = [](const std::vector<u32> &v, int64_t x) -> int64_t {
+    auto find = [](const uvec &v, int64_t x) -> int64_t {
       auto it = std::lower_bound(v.begin(), v.end(), (u32)x);
       return (it != v.end() && *it == (u32)x) ? (int64_t)(it - v.begin()) : -1;
     };
@@ -2162,7 +2163,7 @@ int hspmv_block_rows_host(int64_t m, const int32_t *row_ptr, int64_t cap, int64_
 int hspmv_bandk_group_rows_host(int64_t n, const uint32_t *row_ptr, uint32_t threshold, int literal, uint32_t *start,
                                 int64_t *n_starts, uint32_t *grp) {
   if (!row_ptr || !start || !n_starts || !grp || n < 0) return fail(HSPMV_EINVAL, "bad arguments");
-  std::vector<u32> s, g;
+  uvec s, g;
   if (literal)
     hspmv::bandk_group_rows_literal(row_ptr, n, threshold, s, g);
   else
@@ -2278,7 +2279,7 @@ int hspmv_sts_levels_host(int64_t n, int64_t nnz, const int32_t *row_ptr, const 
                           int64_t *n_packs) {
   (void)nnz;
   if (!row_ptr || !col_idx || !perm || !pack_ptr || !n_packs) return fail(HSPMV_EINVAL, "null");
-  std::vector<u32> p;
+  uvec p;
   std::vector<int32_t> pk;
   int rc = hspmv::sts_levels(n, row_ptr, col_idx, p, pk);
   if (rc) return fail(rc, rc == HSPMV_EUNSUPPORTED ? "STS: a row has no stored diagonal, or the level search stalled (unsymmetric structure)" : "STS: bad arguments");
@@ -2301,7 +2302,7 @@ int hspmv_build_sts(hspmv_matrix *A) {
     A->h_ci.resize((size_t)A->nnz);
     if (A->nnz) CU(cudaMemcpy(A->h_ci.data(), A->d_ci, (size_t)A->nnz * 4, cudaMemcpyDeviceToHost));
   }
-  std::vector<u32> perm;
+  uvec perm;
   std::vector<int32_t> pack;
   int rc = hspmv::sts_levels(A->m, A->h_rp.data(), A->h_ci.data(), perm, pack);
   if (rc) return fail(rc, rc == HSPMV_EUNSUPPORTED ? "STS: a row has no stored diagonal, or the level search stalled (unsymmetric structure)" : "STS: bad arguments");

@@ -55,7 +55,7 @@ struct Phase {
 // Greedy contiguous grouping (csrk.cpp:1278-1292): a group is closed by the vertex that makes
 // the running nnz reach the threshold; the next vertex opens a new group.  This literal form is
 // kept for T == 0 (every vertex, the first included, opens a group) and as the statement of the rule.
-void group_rows_literal(const u32 *rp, int64_t n, u32 T, std::vector<u32> &start, std::vector<u32> &grp) {
+void group_rows_literal(const u32 *rp, int64_t n, u32 T, uvec &start, uvec &grp) {
   grp.resize((size_t)n);
   start.clear();
   start.push_back(0);
@@ -78,9 +78,9 @@ void group_rows_literal(const u32 *rp, int64_t n, u32 T, std::vector<u32> &start
 // rp[v] - rp[s], so (for T > 0) the next group starts at the first v > s with rp[v] >= rp[s] + T -- a forward scan of
 // rp, 4x faster than the literal loop at 64 M rows (0.32 -> 0.08 s), which matters because the device builder
 // (bandk_gpu.cu) only needs the starts.
-void group_starts(const u32 *rp, int64_t n, u32 T, std::vector<u32> &start) {
+void group_starts(const u32 *rp, int64_t n, u32 T, uvec &start) {
   if (T == 0 || n <= 0) {
-    std::vector<u32> grp;
+    uvec grp;
     group_rows_literal(rp, n, T, start, grp);
     return;
   }
@@ -98,7 +98,7 @@ void group_starts(const u32 *rp, int64_t n, u32 T, std::vector<u32> &start) {
   if (rp[n] - rp[s] > 0) start.push_back((u32)n);
 }
 
-void group_rows(const u32 *rp, int64_t n, u32 T, std::vector<u32> &start, std::vector<u32> &grp) {
+void group_rows(const u32 *rp, int64_t n, u32 T, uvec &start, uvec &grp) {
   if (T == 0 || n <= 0) {
     group_rows_literal(rp, n, T, start, grp);
     return;
@@ -113,16 +113,16 @@ void group_rows(const u32 *rp, int64_t n, u32 T, std::vector<u32> &start, std::v
   }
 }
 
-int build_coarse(const u32 *rp, const u32 *adj, const std::vector<u32> &start,
-                 const std::vector<u32> &grp, Coarse &out) {
+int build_coarse(const u32 *rp, const u32 *adj, const uvec &start,
+                 const uvec &grp, Coarse &out) {
   const int64_t nc = (int64_t)start.size() - 1;
   out.n = nc;
-  std::vector<u32> up_cnt((size_t)nc + 1, 0);
+  uvec up_cnt((size_t)nc + 1, 0);
   int nthreads = 1;
 #ifdef _OPENMP
   nthreads = omp_get_max_threads();
 #endif
-  std::vector<std::vector<u32>> buf_adj((size_t)nthreads), buf_mult((size_t)nthreads);
+  std::vector<uvec> buf_adj((size_t)nthreads), buf_mult((size_t)nthreads);
   std::vector<int64_t> first_cv((size_t)nthreads + 1, nc);
 
 #pragma omp parallel num_threads(nthreads)
@@ -134,8 +134,8 @@ int build_coarse(const u32 *rp, const u32 *adj, const std::vector<u32> &start,
 #endif
     const int64_t lo = nc * tid / nt, hi = nc * (tid + 1) / nt;
     first_cv[(size_t)tid] = lo;
-    std::vector<u32> scratch;
-    std::vector<u32> &oa = buf_adj[(size_t)tid], &om = buf_mult[(size_t)tid];
+    uvec scratch;
+    uvec &oa = buf_adj[(size_t)tid], &om = buf_mult[(size_t)tid];
     for (int64_t cv = lo; cv < hi; ++cv) {
       scratch.clear();
       const u32 gs = start[(size_t)cv];
@@ -157,21 +157,21 @@ int build_coarse(const u32 *rp, const u32 *adj, const std::vector<u32> &start,
   }
 
   // stitch the per-thread upper lists into one CSR (threads own contiguous vertex ranges)
-  std::vector<u32> up_rp((size_t)nc + 1, 0);
+  uvec up_rp((size_t)nc + 1, 0);
   for (int64_t v = 0; v < nc; ++v) up_rp[(size_t)v + 1] = up_rp[(size_t)v] + up_cnt[(size_t)v];
-  std::vector<u32> up_adj(up_rp[(size_t)nc]), up_mult(up_rp[(size_t)nc]);
+  uvec up_adj(up_rp[(size_t)nc]), up_mult(up_rp[(size_t)nc]);
   for (int t = 0; t < nthreads; ++t) {
     if (buf_adj[(size_t)t].empty()) continue;
     const u32 dst = up_rp[(size_t)first_cv[(size_t)t]];
     std::memcpy(&up_adj[dst], buf_adj[(size_t)t].data(), buf_adj[(size_t)t].size() * sizeof(u32));
     std::memcpy(&up_mult[dst], buf_mult[(size_t)t].data(), buf_mult[(size_t)t].size() * sizeof(u32));
-    std::vector<u32>().swap(buf_adj[(size_t)t]);
-    std::vector<u32>().swap(buf_mult[(size_t)t]);
+    uvec().swap(buf_adj[(size_t)t]);
+    uvec().swap(buf_mult[(size_t)t]);
   }
 
   // transpose of the strict upper part = lower part; filling in increasing source order
   // leaves every lower list sorted ascending
-  std::vector<u32> low_cnt((size_t)nc + 1, 0);
+  uvec low_cnt((size_t)nc + 1, 0);
   for (int64_t v = 0; v < nc; ++v)
     for (u32 e = up_rp[(size_t)v]; e < up_rp[(size_t)v + 1]; ++e)
       if (up_adj[e] != (u32)v) ++low_cnt[up_adj[e]];
@@ -184,7 +184,7 @@ int build_coarse(const u32 *rp, const u32 *adj, const std::vector<u32> &start,
   }
   out.adj.resize(out.rp[(size_t)nc]);
   out.mult.resize(out.rp[(size_t)nc]);
-  std::vector<u32> cursor(out.rp.begin(), out.rp.end() - 1);
+  uvec cursor(out.rp.begin(), out.rp.end() - 1);
   for (int64_t v = 0; v < nc; ++v)
     for (u32 e = up_rp[(size_t)v]; e < up_rp[(size_t)v + 1]; ++e) {
       const u32 t = up_adj[e];
@@ -206,7 +206,7 @@ int build_coarse(const u32 *rp, const u32 *adj, const std::vector<u32> &start,
 struct Rcm {
   const Coarse &g;
   std::vector<unsigned char> open; // 1 = not yet numbered ("mask" in the reference)
-  std::vector<u32> stamp;          // BFS visit epoch
+  uvec stamp;          // BFS visit epoch
   u32 epoch = 0;
   std::vector<int> order, lvl_ptr;
 
@@ -273,7 +273,7 @@ struct DegId { // layout of rev_deg_id_pair, csrk.h:477-490
 };
 inline bool heavier_first(DegId a, DegId b) { return a.deg > b.deg; } // csrk.cpp:65-67
 
-void rcm_order(const Coarse &g, std::vector<u32> &new2old, std::vector<u32> &old2new) {
+void rcm_order(const Coarse &g, uvec &new2old, uvec &old2new) {
   Rcm s(g);
   new2old.assign((size_t)g.n, 0);
   old2new.assign((size_t)g.n, 0);
@@ -337,13 +337,13 @@ struct RcmPar {
   //   i + 1        claimed by frontier position i in the level being expanded
   //   0xFFFFFFFF   not reached by the current search (levels_from resets the words it set when the next search starts)
   // so "claim" is a plain atomic min and leaves closed / discovered words alone.
-  std::vector<u32> seen;
-  std::vector<u32> posn; // Cuthill-McKee number, or >= UNNUMBERED: NONE / UNNUMBERED|i = claimed by number i / TAKEN
+  uvec seen;
+  uvec posn; // Cuthill-McKee number, or >= UNNUMBERED: NONE / UNNUMBERED|i = claimed by number i / TAKEN
   std::vector<int> order, lvl_ptr; // order[0 .. cnt)
   size_t cnt = 0;
   // a level is cut into up to 8 chunks per thread, handed out dynamically (a core that is late does not hold the
   // level up); chunk c's finds go to cbuf[c] and the chunks are concatenated in chunk order
-  std::vector<std::vector<u32>> cbuf;
+  std::vector<uvec> cbuf;
   std::vector<size_t> coff;
 
   RcmPar(const Coarse &gr, int threads, size_t cut)
@@ -383,7 +383,7 @@ struct RcmPar {
       // phase A: claims; a chunk remembers (in walk order) the neighbours it claimed and for which position
 #pragma omp for schedule(dynamic, 1)
       for (int64_t c = 0; c < (int64_t)nchunk; ++c) {
-        std::vector<u32> &buf = cbuf[(size_t)c];
+        uvec &buf = cbuf[(size_t)c];
         buf.clear();
         const size_t lo = begin + len * (size_t)c / nchunk, hi = begin + len * ((size_t)c + 1) / nchunk;
         for (size_t i = lo; i < hi; ++i) {
@@ -401,7 +401,7 @@ struct RcmPar {
       // phase B: what a chunk claimed and still owns (no smaller position took it since) is its find, in walk order
 #pragma omp for schedule(dynamic, 1)
       for (int64_t c = 0; c < (int64_t)nchunk; ++c) {
-        std::vector<u32> &buf = cbuf[(size_t)c];
+        uvec &buf = cbuf[(size_t)c];
         size_t kept = 0;
         for (size_t t = 0; t < buf.size(); t += 2)
           if (peek(&seen[buf[t]]) == buf[t + 1]) {
@@ -414,7 +414,7 @@ struct RcmPar {
       for (size_t c = 0; c < nchunk; ++c) coff[c + 1] = coff[c] + cbuf[c].size();
 #pragma omp for schedule(dynamic, 1) nowait
       for (int64_t c = 0; c < (int64_t)nchunk; ++c) {
-        const std::vector<u32> &buf = cbuf[(size_t)c];
+        const uvec &buf = cbuf[(size_t)c];
         for (size_t t = 0; t < buf.size(); ++t) order[coff[(size_t)c] + t] = (int)buf[t];
       }
     }
@@ -488,7 +488,7 @@ struct RcmPar {
   }
 
   // Cuthill-McKee numbers first, first+1, ... of the component of `root` into q[]; returns the next free number
-  int64_t number_component(int root, int64_t first, std::vector<u32> &q) {
+  int64_t number_component(int root, int64_t first, uvec &q) {
     forget();
     size_t begin = (size_t)first, end = begin + 1;
     q[begin] = (u32)root;
@@ -515,7 +515,7 @@ struct RcmPar {
           std::vector<DegId> cand;
 #pragma omp for schedule(dynamic, 1)
           for (int64_t c = 0; c < (int64_t)nchunk; ++c) {
-            std::vector<u32> &buf = cbuf[(size_t)c];
+            uvec &buf = cbuf[(size_t)c];
             buf.clear();
             const size_t lo = begin + len * (size_t)c / nchunk, hi = begin + len * ((size_t)c + 1) / nchunk;
             for (size_t i = lo; i < hi; ++i) {
@@ -531,7 +531,7 @@ struct RcmPar {
           // phase B: keep what is still owned, in (p, rank in p's sorted list) order
 #pragma omp for schedule(dynamic, 1)
           for (int64_t c = 0; c < (int64_t)nchunk; ++c) {
-            std::vector<u32> &buf = cbuf[(size_t)c];
+            uvec &buf = cbuf[(size_t)c];
             size_t kept = 0;
             for (size_t t = 0; t < buf.size(); t += 2)
               if (peek(&posn[buf[t]]) == buf[t + 1]) {
@@ -544,7 +544,7 @@ struct RcmPar {
           for (size_t c = 0; c < nchunk; ++c) coff[c + 1] = coff[c] + cbuf[c].size();
 #pragma omp for schedule(dynamic, 1) nowait
           for (int64_t c = 0; c < (int64_t)nchunk; ++c) {
-            const std::vector<u32> &buf = cbuf[(size_t)c];
+            const uvec &buf = cbuf[(size_t)c];
             for (size_t t = 0; t < buf.size(); ++t) {
               q[coff[(size_t)c] + t] = buf[t];
               posn[buf[t]] = (u32)(coff[(size_t)c] + t);
@@ -567,7 +567,7 @@ struct RcmPar {
   }
 };
 
-void rcm_order_parallel(const Coarse &g, int nt, size_t cutoff, std::vector<u32> &new2old, std::vector<u32> &old2new) {
+void rcm_order_parallel(const Coarse &g, int nt, size_t cutoff, uvec &new2old, uvec &old2new) {
   RcmPar s(g, nt, cutoff);
   new2old.assign((size_t)g.n, 0);
   old2new.assign((size_t)g.n, 0);
@@ -585,7 +585,7 @@ void rcm_order_parallel(const Coarse &g, int nt, size_t cutoff, std::vector<u32>
 
 // serial walk for small graphs, level-synchronous walk on all cores for large ones (HSPMV_RCM=serial|parallel and
 // HSPMV_RCM_CUTOFF=<frontier size> override the choice; the tests use them to run both on the same graphs)
-void rcm_order_auto(const Coarse &g, std::vector<u32> &new2old, std::vector<u32> &old2new) {
+void rcm_order_auto(const Coarse &g, uvec &new2old, uvec &old2new) {
   int nt = 1;
 #ifdef _OPENMP
   nt = omp_get_max_threads();
@@ -605,7 +605,7 @@ void rcm_order_auto(const Coarse &g, std::vector<u32> &new2old, std::vector<u32>
 }
 
 // relabel + sort adjacency by new id (csrk.cpp:3012-3115)
-void relabel(Coarse &g, const std::vector<u32> &new2old, const std::vector<u32> &old2new) {
+void relabel(Coarse &g, const uvec &new2old, const uvec &old2new) {
   Coarse src;
   src.rp.swap(g.rp);
   src.adj.swap(g.adj);
@@ -635,11 +635,12 @@ void relabel(Coarse &g, const std::vector<u32> &new2old, const std::vector<u32> 
   }
 }
 
-// csrk.cpp:1148-1224: group starts rewritten in permuted order; finer permutation composed
-void expand_level(std::vector<u32> &map, const std::vector<u32> &perm_coarse,
-                  std::vector<u32> &perm_fine) {
+// csrk.cpp:1148-1224: group starts rewritten in permuted order; finer permutation composed.  An EMPTY perm_fine
+// stands for the identity (level 0, csrk.cpp:886-890: the rows themselves), which is then never materialised.
+void expand_level(uvec &map, const uvec &perm_coarse, uvec &perm_fine) {
   const size_t nc = perm_coarse.size();
-  std::vector<u32> new_map(nc + 1, 0), composed(perm_fine.size());
+  const bool identity = perm_fine.empty();
+  uvec new_map(nc + 1, 0), composed(identity ? (size_t)map[nc] : perm_fine.size());
   for (size_t j = 0; j < nc; ++j) {
     const u32 o = perm_coarse[j];
     new_map[j + 1] = new_map[j] + (map[o + 1] - map[o]);
@@ -648,8 +649,12 @@ void expand_level(std::vector<u32> &map, const std::vector<u32> &perm_coarse,
   for (int64_t j = 0; j < (int64_t)nc; ++j) {
     const u32 o = perm_coarse[(size_t)j];
     u32 dst = new_map[(size_t)j];
-    for (u32 t = map[o]; t < map[o + 1]; ++t) composed[dst++] = perm_fine[t];
+    if (identity)
+      for (u32 t = map[o]; t < map[o + 1]; ++t) composed[dst++] = t;
+    else
+      for (u32 t = map[o]; t < map[o + 1]; ++t) composed[dst++] = perm_fine[t];
   }
+  for (size_t t = new_map[nc]; t < composed.size(); ++t) composed[t] = 0; // rows no group covers (trailing empty rows)
   map.swap(new_map);
   perm_fine.swap(composed);
 }
@@ -657,26 +662,33 @@ void expand_level(std::vector<u32> &map, const std::vector<u32> &perm_coarse,
 } // namespace
 
 // csrk.cpp:896-897: unsigned * long / long, truncated to int, compared as unsigned
+void first_touch(void *p, size_t bytes) {
+  volatile unsigned char *b = (volatile unsigned char *)p;
+  const int64_t pages = (int64_t)((bytes + 4095) / 4096);
+#pragma omp parallel for schedule(static) if (pages > 1024)
+  for (int64_t i = 0; i < pages; ++i) b[(size_t)i * 4096] = 0;
+}
+
 u32 bandk_threshold(int size, int64_t nnz, int64_t n) {
   return (u32)(int)((long)(unsigned)size * (long)nnz / (long)n);
 }
 
-void bandk_group_rows(const u32 *rp, int64_t n, u32 T, std::vector<u32> &start) { group_starts(rp, n, T, start); }
+void bandk_group_rows(const u32 *rp, int64_t n, u32 T, uvec &start) { group_starts(rp, n, T, start); }
 
 // for the tests: both statements of the grouping rule side by side
-void bandk_group_rows_literal(const u32 *rp, int64_t n, u32 T, std::vector<u32> &start, std::vector<u32> &grp) {
+void bandk_group_rows_literal(const u32 *rp, int64_t n, u32 T, uvec &start, uvec &grp) {
   group_rows_literal(rp, n, T, start, grp);
 }
-void bandk_group_rows_fast(const u32 *rp, int64_t n, u32 T, std::vector<u32> &start, std::vector<u32> &grp) {
+void bandk_group_rows_fast(const u32 *rp, int64_t n, u32 T, uvec &start, uvec &grp) {
   group_rows(rp, n, T, start, grp);
 }
 
 // Levels 1 .. k-1.  `first` (optional) is the level-1 coarse graph with its group starts in
 // `first_map`, built elsewhere (bandk_gpu.cu); without it level 1 is built here from (rp, adj).
 static int bandk_levels(int64_t n, int64_t nnz, const u32 *rp, const u32 *adj, int k, const int *sizes,
-                        CoarseGraph *first, std::vector<u32> *first_map, std::vector<u32> &perm,
-                        std::vector<u32> &sr_ptr, std::vector<u32> &ssr_ptr) {
-  std::vector<std::vector<u32>> perms((size_t)k), maps((size_t)k);
+                        CoarseGraph *first, uvec *first_map, uvec &perm,
+                        uvec &sr_ptr, uvec &ssr_ptr) {
+  std::vector<uvec> perms((size_t)k), maps((size_t)k);
   Coarse level[3];
 
   const u32 *cur_rp = rp, *cur_adj = adj;
@@ -690,7 +702,7 @@ static int bandk_levels(int64_t n, int64_t nnz, const u32 *rp, const u32 *adj, i
       maps[1].swap(*first_map);
     } else {
       const u32 T = bandk_threshold(sizes[lvl - 1], cur_nnz, cur_n);
-      std::vector<u32> grp;
+      uvec grp;
       {
         Phase ph("group rows");
         group_rows(cur_rp, cur_n, T, maps[(size_t)lvl], grp);
@@ -699,7 +711,7 @@ static int bandk_levels(int64_t n, int64_t nnz, const u32 *rp, const u32 *adj, i
       int rc = build_coarse(cur_rp, cur_adj, maps[(size_t)lvl], grp, level[lvl]);
       if (rc) return rc;
     }
-    std::vector<u32> o2n;
+    uvec o2n;
     {
       Phase ph("RCM of the coarse graph");
       rcm_order_auto(level[lvl], perms[(size_t)lvl], o2n);
@@ -717,9 +729,12 @@ static int bandk_levels(int64_t n, int64_t nnz, const u32 *rp, const u32 *adj, i
   // level-(k-1) ... level-1: rewrite the maps, compose down to rows (csrk.cpp:1015-1034)
   Phase ph("uncoarsen");
   if (k == 3) expand_level(maps[2], perms[2], perms[1]);
-  perms[0].resize((size_t)n);
+  perms[0].clear(); // level 0 is the identity: not materialised ...
+  if ((int64_t)maps[1].back() != n) { // ... unless trailing empty rows are left uncovered (the callers report that case)
+    perms[0].resize((size_t)n);
 #pragma omp parallel for schedule(static)
-  for (int64_t i = 0; i < n; ++i) perms[0][(size_t)i] = (u32)i;
+    for (int64_t i = 0; i < n; ++i) perms[0][(size_t)i] = (u32)i;
+  }
   expand_level(maps[1], perms[1], perms[0]);
 
   perm.swap(perms[0]);
@@ -732,14 +747,14 @@ static int bandk_levels(int64_t n, int64_t nnz, const u32 *rp, const u32 *adj, i
 }
 
 int bandk_build(int64_t n, int64_t nnz, const u32 *rp, const u32 *adj, int k, const int *sizes,
-                std::vector<u32> &perm, std::vector<u32> &sr_ptr, std::vector<u32> &ssr_ptr) {
+                uvec &perm, uvec &sr_ptr, uvec &ssr_ptr) {
   if (k < 2 || k > 3 || n <= 0 || !rp || !adj || !sizes) return HSPMV_EINVAL;
   if (rp[n] != (u32)nnz) return HSPMV_EINVAL;
   return bandk_levels(n, nnz, rp, adj, k, sizes, nullptr, nullptr, perm, sr_ptr, ssr_ptr);
 }
 
-int bandk_finish(int64_t n, int k, const int *sizes, CoarseGraph &level1, std::vector<u32> &map1,
-                 std::vector<u32> &perm, std::vector<u32> &sr_ptr, std::vector<u32> &ssr_ptr) {
+int bandk_finish(int64_t n, int k, const int *sizes, CoarseGraph &level1, uvec &map1,
+                 uvec &perm, uvec &sr_ptr, uvec &ssr_ptr) {
   if (k < 2 || k > 3 || n <= 0 || !sizes) return HSPMV_EINVAL;
   return bandk_levels(n, 0, nullptr, nullptr, k, sizes, &level1, &map1, perm, sr_ptr, ssr_ptr);
 }
@@ -747,7 +762,7 @@ int bandk_finish(int64_t n, int k, const int *sizes, CoarseGraph &level1, std::v
 template <typename T>
 static void reorder_impl(int64_t n, const u32 *perm, const u32 *rp, const u32 *ci, const T *v,
                          u32 *rp2, u32 *ci2, T *v2) {
-  std::vector<u32> fwd((size_t)n);
+  uvec fwd((size_t)n);
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < n; ++i) fwd[perm[i]] = (u32)i;
   rp2[0] = 0;

@@ -405,7 +405,7 @@ int grid_of(int64_t items, int per_block, int sms, int per_sm) {
 
 } // namespace
 
-int coarse_level1_device(int64_t n, int64_t nnz, const u32 *d_rp, const u32 *d_ci, const std::vector<u32> &start,
+int coarse_level1_device(int64_t n, int64_t nnz, const u32 *d_rp, const u32 *d_ci, const uvec &start,
                          int sms, cudaStream_t st, CoarseGraph &out, int64_t *launches_out) {
   const int64_t nc = (int64_t)start.size() - 1;
   if (nc < 1 || start.back() != (u32)n) return BANDK_USE_HOST;
@@ -456,6 +456,8 @@ int coarse_level1_device(int64_t n, int64_t nnz, const u32 *d_rp, const u32 *d_c
   out.rp.resize((size_t)nc + 1);
   out.adj.resize((size_t)cnnz);
   out.mult.resize((size_t)cnnz);
+  first_touch(out.adj.data(), (size_t)cnnz * 4); // uvec: nothing has written these pages yet
+  first_touch(out.mult.data(), (size_t)cnnz * 4);
   BK_CU(cudaMemcpyAsync(out.rp.data(), crp, (size_t)(nc + 1) * 4, cudaMemcpyDeviceToHost, st));
   BK_CU(cudaMemcpyAsync(out.adj.data(), cadj, (size_t)cnnz * 4, cudaMemcpyDeviceToHost, st));
   BK_CU(cudaMemcpyAsync(out.mult.data(), cmult, (size_t)cnnz * 4, cudaMemcpyDeviceToHost, st));

@@ -14,7 +14,7 @@ enum { BANDK_MAX_ROW = 1024 };
 
 // Level-1 coarse graph of the CSR matrix (d_rp, d_ci) in HBM for the row groups `start`
 // (bandk_group_rows).  Same arrays, bit for bit, as build_coarse() in bandk.cpp.
-int coarse_level1_device(int64_t n, int64_t nnz, const u32 *d_rp, const u32 *d_ci, const std::vector<u32> &start,
+int coarse_level1_device(int64_t n, int64_t nnz, const u32 *d_rp, const u32 *d_ci, const uvec &start,
                          int sms, cudaStream_t st, CoarseGraph &out, int64_t *launches);
 
 // A' = P A P^T in HBM: row i of A' is row perm[i] of A with columns renumbered by the inverse

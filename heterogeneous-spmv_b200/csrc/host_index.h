@@ -11,21 +11,42 @@ namespace hspmv {
 
 typedef uint32_t u32;
 
+// uvec whose resize() / sized constructor leave the new elements UNINITIALISED (value-constructing forms --
+// v(n, 0), assign(n, 0) -- still write).  The index arrays of a Band-k build at config 5 are 256 MB (permutation) to
+// 420 MB (coarse graph) each; std::vector would zero them on one core -- page faults included, 0.15-0.25 s apiece --
+// before the parallel loop or the download that overwrites every element.  With this type the first touch happens in
+// that parallel loop, or in first_touch() right before a download.
+template <typename T> struct RawAlloc {
+  typedef T value_type;
+  RawAlloc() noexcept {}
+  template <class U> RawAlloc(const RawAlloc<U> &) noexcept {}
+  T *allocate(size_t n) { return static_cast<T *>(::operator new(n * sizeof(T))); }
+  void deallocate(T *p, size_t) noexcept { ::operator delete(p); }
+  template <class U> void construct(U *p) noexcept { ::new ((void *)p) U; } // default-init: nothing for u32
+  template <class U, class... A> void construct(U *p, A &&...a) { ::new ((void *)p) U(static_cast<A &&>(a)...); }
+  template <class U> bool operator==(const RawAlloc<U> &) const noexcept { return true; }
+  template <class U> bool operator!=(const RawAlloc<U> &) const noexcept { return false; }
+};
+typedef std::vector<u32, RawAlloc<u32>> uvec;
+// one write per page of [p, p + bytes) from all host cores (the pages of a fresh allocation are faulted in there,
+// not one by one under a single-threaded copy)
+void first_touch(void *p, size_t bytes);
+
 // ---- bandk.cpp
 int bandk_build(int64_t n, int64_t nnz, const u32 *rp, const u32 *adj, int k, const int *sizes,
-                std::vector<u32> &perm, std::vector<u32> &sr_ptr, std::vector<u32> &ssr_ptr);
+                uvec &perm, uvec &sr_ptr, uvec &ssr_ptr);
 // pieces of bandk_build that the device builder (bandk_gpu.cu) reuses: the grouping threshold and
 // walk, and everything from the level-1 coarse graph on (RCM, level 2, uncoarsening)
 struct CoarseGraph {
   int64_t n = 0;
-  std::vector<u32> rp, adj, mult;
+  uvec rp, adj, mult;
 };
 u32 bandk_threshold(int size, int64_t nnz, int64_t n);
-void bandk_group_rows(const u32 *rp, int64_t n, u32 T, std::vector<u32> &start);
-void bandk_group_rows_literal(const u32 *rp, int64_t n, u32 T, std::vector<u32> &start, std::vector<u32> &grp);
-void bandk_group_rows_fast(const u32 *rp, int64_t n, u32 T, std::vector<u32> &start, std::vector<u32> &grp);
-int bandk_finish(int64_t n, int k, const int *sizes, CoarseGraph &level1, std::vector<u32> &map1,
-                 std::vector<u32> &perm, std::vector<u32> &sr_ptr, std::vector<u32> &ssr_ptr);
+void bandk_group_rows(const u32 *rp, int64_t n, u32 T, uvec &start);
+void bandk_group_rows_literal(const u32 *rp, int64_t n, u32 T, uvec &start, uvec &grp);
+void bandk_group_rows_fast(const u32 *rp, int64_t n, u32 T, uvec &start, uvec &grp);
+int bandk_finish(int64_t n, int k, const int *sizes, CoarseGraph &level1, uvec &map1,
+                 uvec &perm, uvec &sr_ptr, uvec &ssr_ptr);
 void reorder_f32(int64_t n, const u32 *perm, const u32 *rp, const u32 *ci, const float *v,
                  u32 *rp2, u32 *ci2, float *v2);
 void reorder_f64(int64_t n, const u32 *perm, const u32 *rp, const u32 *ci, const double *v,
@@ -78,7 +99,7 @@ void tile_rows(int64_t m, const int32_t *rp, int64_t tile, std::vector<int32_t> 
 void block_rows(int64_t m, const int32_t *rp, int64_t cap, int64_t max_rows, std::vector<int32_t> &blk_row);
 
 // ---- sts.cpp: level sets of the triangular solve (kernel "STS", order "LS", k = 2), bit-exact vs oracle/sts_oracle.cpp
-int sts_levels(int64_t n, const int32_t *rp, const int32_t *ci, std::vector<u32> &perm, std::vector<int32_t> &pack_ptr);
+int sts_levels(int64_t n, const int32_t *rp, const int32_t *ci, uvec &perm, std::vector<int32_t> &pack_ptr);
 
 // ---- heuristics.cpp
 int auto_params(int64_t nnz, int64_t n_rows, int arch, int sizes[2], int *veclevel, int *block_dim_y);

@@ -30,7 +30,7 @@ bool compare_deg_id_pair(degree_id_pair p1, degree_id_pair p2) { return p1.deg <
 // perm: new -> old; pack_ptr: n_packs + 1 entries.  HSPMV_EUNSUPPORTED when a row has no stored diagonal or the
 // search stalls (structurally unsymmetric matrix) -- the reference prints "Number of vertices did not change in
 // level" and goes on with garbage (csrk.cpp:2797-2800).
-int sts_levels(int64_t n, const int32_t *rp, const int32_t *ci, std::vector<u32> &perm, std::vector<int32_t> &pack_ptr) {
+int sts_levels(int64_t n, const int32_t *rp, const int32_t *ci, uvec &perm, std::vector<int32_t> &pack_ptr) {
   if (n <= 0 || !rp || !ci) return HSPMV_EINVAL;
   std::vector<int32_t> lower((size_t)n);
   for (int64_t v = 0; v < n; ++v) { // entries before the diagonal; the diagonal must be there

@@ -36,7 +36,7 @@ int main(int argc, char **argv) {
   nt = omp_get_max_threads();
 #endif
   std::printf("coarse graph: %lld vertices, %zu entries; %d threads, frontier cutoff %zu\n", (long long)g.n, g.adj.size(), nt, cutoff);
-  std::vector<u32> a, b, c, d;
+  uvec a, b, c, d;
   for (int rep = 0; rep < 3; rep++) {
     double t0 = now();
     rcm_order(g, a, b);
@@ -48,7 +48,7 @@ int main(int argc, char **argv) {
   }
   { // where the level-synchronous walk spends its time (first component only: the stand-in is connected)
     RcmPar s(g, nt, cutoff);
-    std::vector<u32> q((size_t)g.n);
+    uvec q((size_t)g.n);
     double t0 = now();
     const int root = s.peripheral(0);
     double t1 = now();
@@ -56,12 +56,25 @@ int main(int argc, char **argv) {
     double t2 = now();
     std::printf("level-synchronous walk: pseudo-peripheral search (%zu levels) %.3f s, numbering %.3f s\n", s.lvl_ptr.size() - 1, t1 - t0, t2 - t1);
   }
+  for (int k = 2; k <= 3; ++k) { // everything the device builder leaves to the host after the level-1 coarse graph: bandk_finish
+    CoarseGraph level1;
+    level1.n = g.n;
+    level1.rp = g.rp;
+    level1.adj = g.adj;
+    level1.mult = g.mult;
+    uvec map1((size_t)g.n + 1), perm, sr, ssr;
+    for (int64_t i = 0; i <= g.n; ++i) map1[(size_t)i] = (u32)(16 * i); // 16 rows per level-1 group
+    const int sizes[2] = {16, 16};
+    double t0 = now();
+    int rc = bandk_finish(16 * g.n, k, sizes, level1, map1, perm, sr, ssr);
+    std::printf("bandk_finish k=%d on %lld rows: %.3f s (rc %d)  [HSPMV_BANDK_TRACE=1 prints the phases]\n", k, (long long)(16 * g.n), now() - t0, rc);
+  }
   const int64_t n = 64000000;
-  std::vector<u32> rp((size_t)n + 1);
+  uvec rp((size_t)n + 1);
   rp[0] = 0;
   for (int64_t i = 0; i < n; i++) rp[(size_t)i + 1] = rp[(size_t)i] + ((i % 400 == 0 || i % 400 == 399) ? 18 : 27);
   for (int rep = 0; rep < 3; rep++) {
-    std::vector<u32> s1, s2, grp;
+    uvec s1, s2, grp;
     double t0 = now();
     group_rows_literal(rp.data(), n, 429, s1, grp);
     double t1 = now();
