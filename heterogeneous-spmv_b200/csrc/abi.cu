@@ -246,32 +246,36 @@ int grid_for(int64_t items, int threads, int cap) {
 #define LAUNCHED() g_launches.fetch_add(1, std::memory_order_relaxed)
 
 // ---- bins ---------------------------------------------------------------------------
-int ensure_host_rp(hspmv_matrix *A, std::vector<int32_t> &rp) {
+// host row pointers of the handle: the kept copy itself (no 256 MB duplicate at config 5), else a download into `scratch`
+int ensure_host_rp(hspmv_matrix *A, std::vector<int32_t> &scratch, const int32_t *&rp) {
   if (!A->h_rp.empty()) {
-    rp = A->h_rp;
+    rp = A->h_rp.data();
     return HSPMV_OK;
   }
-  rp.resize((size_t)A->m + 1);
-  CU(cudaMemcpy(rp.data(), A->d_rp, (size_t)(A->m + 1) * 4, cudaMemcpyDeviceToHost));
+  scratch.resize((size_t)A->m + 1);
+  CU(cudaMemcpy(scratch.data(), A->d_rp, (size_t)(A->m + 1) * 4, cudaMemcpyDeviceToHost));
+  rp = scratch.data();
   return HSPMV_OK;
 }
 
 int ensure_stats(hspmv_matrix *A) {
   if (A->stats_ready) return HSPMV_OK;
-  std::vector<int32_t> rp;
-  int rc = ensure_host_rp(A, rp);
+  std::vector<int32_t> scratch;
+  const int32_t *rp = nullptr;
+  int rc = ensure_host_rp(A, scratch, rp);
   if (rc) return rc;
-  hspmv::row_stats(A->m, rp.data(), A->stats);
+  hspmv::row_stats(A->m, rp, A->stats);
   A->stats_ready = true;
   return HSPMV_OK;
 }
 
 int ensure_bins(hspmv_matrix *A) {
   if (A->bins_ready) return HSPMV_OK;
-  std::vector<int32_t> rp, rows;
-  int rc = ensure_host_rp(A, rp);
+  std::vector<int32_t> scratch, rows;
+  const int32_t *rp = nullptr;
+  int rc = ensure_host_rp(A, scratch, rp);
   if (rc) return rc;
-  hspmv::bin_rows(A->m, rp.data(), rows, A->bin_ptr);
+  hspmv::bin_rows(A->m, rp, rows, A->bin_ptr);
   if (A->d_bin_rows) cudaFree(A->d_bin_rows);
   CU(cudaMalloc(&A->d_bin_rows, (size_t)(A->m + 1) * 4));
   if (A->m) CU(cudaMemcpy(A->d_bin_rows, rows.data(), (size_t)A->m * 4, cudaMemcpyHostToDevice));
@@ -485,10 +489,11 @@ int run_csrk(hspmv_matrix *A, bool stream_mode, const T *x, T *y, cudaStream_t s
   int ragged_rpt = 0;
   if (ragged) {
     if (A->len_p90 < 0) {
-      std::vector<int32_t> rp;
-      int rc = ensure_host_rp(A, rp);
+      std::vector<int32_t> scratch;
+      const int32_t *rp = nullptr;
+      int rc = ensure_host_rp(A, scratch, rp);
       if (rc) return rc;
-      A->len_p90 = hspmv::row_len_percentile(A->m, rp.data(), 90);
+      A->len_p90 = hspmv::row_len_percentile(A->m, rp, 90);
     }
     const int64_t cover = A->len_p90 > 4 ? A->len_p90 : 4;
     vec = 1;
@@ -665,10 +670,11 @@ int run_csr_block(hspmv_matrix *A, const T *x, T *y, cudaStream_t st) {
   int64_t max_rows = cap; // a block never needs more row slots than nonzero slots + empty rows; bounded for shared memory
   if (max_rows > 2048) max_rows = 2048;
   if (A->block_cap != cap || A->block_max_rows != max_rows || !A->d_blk_row) {
-    std::vector<int32_t> rp, blk;
-    int rc = ensure_host_rp(A, rp);
+    std::vector<int32_t> scratch, blk;
+    const int32_t *rp = nullptr;
+    int rc = ensure_host_rp(A, scratch, rp);
     if (rc) return rc;
-    hspmv::block_rows(A->m, rp.data(), cap, max_rows, blk);
+    hspmv::block_rows(A->m, rp, cap, max_rows, blk);
     if (A->d_blk_row) cudaFree(A->d_blk_row);
     A->d_blk_row = nullptr;
     CU(cudaMalloc(&A->d_blk_row, blk.size() * 4 + 16));
