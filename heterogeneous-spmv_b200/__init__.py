@@ -265,6 +265,20 @@ def bandk_group_rows_host(row_ptr, threshold, literal=False):
     return start[: ns.value].copy(), grp[:n].copy()
 
 
+def pipe_plan_host(m, n, vsize=8, chunk_cmax=None):
+    """Plan of the pipelined host call (hspmv_spmv_host): row chunk bounds; with chunk_cmax also (x piece bounds, need)."""
+    row_lo = np.zeros(66, np.int64)
+    nc = C.c_int()
+    if chunk_cmax is None:
+        _check(lib().hspmv_pipe_plan_host(C.c_int64(m), C.c_int64(n), int(vsize), None, _p(row_lo), C.byref(nc), None, None))
+        return row_lo[: nc.value + 1].copy()
+    cm = np.ascontiguousarray(chunk_cmax, dtype=np.int64)
+    x_lo = np.zeros(66, np.int64)
+    need = np.zeros(65, np.int32)
+    _check(lib().hspmv_pipe_plan_host(C.c_int64(m), C.c_int64(n), int(vsize), _p(cm), _p(row_lo), C.byref(nc), _p(x_lo), _p(need)))
+    return row_lo[: nc.value + 1].copy(), x_lo[: nc.value + 1].copy(), need[: nc.value].copy()
+
+
 def sts_levels_host(row_ptr, col_idx):
     """Level sets of the triangular solve (kernel "STS", order "LS", k = 2) without a device: dict(perm new->old, pack_ptr)."""
     row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int32)

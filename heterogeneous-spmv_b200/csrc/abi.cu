@@ -1707,20 +1707,11 @@ int build_pipe(hspmv_matrix *A) {
   P.tried = true;
   const size_t vs = A->vsize();
   if (A->d_perm || A->k != 1 || (size_t)A->m * vs < ((size_t)32 << 20)) return HSPMV_OK; // small or permuted: plain path
-  // pieces of ~4 MB of y (and of x): fine enough that the three legs of the pipeline overlap on a shard of a few million
-  // rows (r2, N = 8: with four 16 MB pieces a call took twice the PCIe floor), coarse enough to amortise a copy's set-up
-  int C = (int)((size_t)A->m * vs / ((size_t)4 << 20));
-  if (C < 4) C = 4;
-  if (C > 32) C = 32;
+  // row chunks with ramped sizes, and x pieces cut where the chunks' column ranges end (partition.cpp: pipe_chunks,
+  // pipe_pieces -- host rules, property-tested without a device through hspmv_pipe_plan_host)
+  hspmv::pipe_chunks(A->m, (int64_t)vs, P.row_lo);
+  const int C = (int)P.row_lo.size() - 1;
   P.chunks = C;
-  P.row_lo.resize((size_t)C + 1);
-  P.x_lo.resize((size_t)C + 1);
-  for (int c = 0; c <= C; ++c) {
-    P.row_lo[(size_t)c] = ((A->m * c / C) + 3) & ~(int64_t)3; // 32 B-aligned y pieces
-    P.x_lo[(size_t)c] = ((A->n * c / C) + 3) & ~(int64_t)3;
-  }
-  P.row_lo[(size_t)C] = A->m;
-  P.x_lo[(size_t)C] = A->n;
   // highest column each row chunk references -> the last x piece it has to wait for
   std::vector<int> e((size_t)C + 1);
   for (int c = 0; c <= C; ++c)
@@ -1742,13 +1733,9 @@ int build_pipe(hspmv_matrix *A) {
   CU(cudaStreamSynchronize(A->stream));
   CU(cudaMemcpy(init.data(), d, (size_t)C * 8, cudaMemcpyDeviceToHost));
   cudaFree(d);
-  P.need.assign((size_t)C, 0);
-  for (int c = 0; c < C; ++c) {
-    const int64_t cmax = init[(size_t)2 * c + 1];
-    int piece = 0;
-    while (piece + 1 < C && P.x_lo[(size_t)piece + 1] <= cmax) ++piece;
-    P.need[(size_t)c] = piece;
-  }
+  std::vector<int64_t> cmax((size_t)C);
+  for (int c = 0; c < C; ++c) cmax[(size_t)c] = init[(size_t)2 * c + 1];
+  hspmv::pipe_pieces(A->n, cmax, P.x_lo, P.need);
   CU(cudaStreamCreateWithFlags(&P.s_h2d, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&P.s_d2h, cudaStreamNonBlocking));
   P.ev_x.resize((size_t)C);
@@ -2177,6 +2164,25 @@ int hspmv_bandk_group_rows_host(int64_t n, const uint32_t *row_ptr, uint32_t thr
   std::memcpy(start, s.data(), s.size() * 4);
   if (n) std::memcpy(grp, g.data(), (size_t)n * 4);
   *n_starts = (int64_t)s.size();
+  return HSPMV_OK;
+}
+// plan of the pipelined host call, host rules (for the property tests): row_lo / x_lo have room for 66 entries, need for 65
+int hspmv_pipe_plan_host(int64_t m, int64_t n, int vsize, const int64_t *chunk_cmax, int64_t *row_lo, int *n_chunks, int64_t *x_lo,
+                         int *need) {
+  if (!row_lo || !n_chunks || (vsize != 4 && vsize != 8)) return fail(HSPMV_EINVAL, "bad arguments");
+  std::vector<int64_t> rl, xl;
+  std::vector<int> nd;
+  hspmv::pipe_chunks(m, vsize, rl);
+  const int C = (int)rl.size() - 1;
+  if (C > 64) return fail(HSPMV_EINVAL, "more than 64 chunks");
+  std::memcpy(row_lo, rl.data(), rl.size() * 8);
+  *n_chunks = C;
+  if (chunk_cmax && x_lo && need) {
+    std::vector<int64_t> cm(chunk_cmax, chunk_cmax + C);
+    hspmv::pipe_pieces(n, cm, xl, nd);
+    std::memcpy(x_lo, xl.data(), xl.size() * 8);
+    std::memcpy(need, nd.data(), nd.size() * 4);
+  }
   return HSPMV_OK;
 }
 // row bins of the CSR_VECTOR path, host (for the bit-exactness tests): rows[m], bin_ptr[9]

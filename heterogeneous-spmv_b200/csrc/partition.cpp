@@ -150,6 +150,67 @@ void block_rows(int64_t m, const int32_t *rp, int64_t cap, int64_t max_rows, std
   if (m > 0) blk_row.push_back((int32_t)m);
 }
 
+// ---- plan of the pipelined host call (hspmv_spmv_host, abi.cu:spmv_host_pipelined) ----------------------------------
+// Row chunks: y goes down (and the kernel runs) chunk by chunk.  The call's time is the PCIe time of x up and y down
+// plus what cannot overlap: the first x piece (nothing can run before it has landed) and the last y chunk (nothing is
+// left to overlap it with).  So the chunks ramp up from an eighth of the regular size and ramp down again at the end;
+// the regular size is total / 32 clamped to [4 MB, 16 MB] (r2 measurements: 16 MB pieces on a 512 MB vector, 4 MB on
+// the 64 MB shards of an 8-GPU run).  Boundaries are multiples of 4 rows (32 B-aligned copies).
+void pipe_chunks(int64_t m, int64_t vs, std::vector<int64_t> &row_lo) {
+  row_lo.assign(1, 0);
+  if (m <= 0) {
+    row_lo.push_back(m < 0 ? 0 : m);
+    return;
+  }
+  const int64_t total = m * vs;
+  int64_t cap = total / 32;
+  if (cap < ((int64_t)4 << 20)) cap = (int64_t)4 << 20;
+  if (cap > ((int64_t)16 << 20)) cap = (int64_t)16 << 20;
+  if (total / cap > 56) cap = (total + 55) / 56; // never more than 64 chunks (vectors beyond 900 MB get larger pieces)
+  const int64_t ramp[3] = {cap / 8, cap / 4, cap / 2};
+  const int64_t ramps = 2 * (ramp[0] + ramp[1] + ramp[2]);
+  std::vector<int64_t> bytes;
+  if (total < ramps + cap) { // too small for ramps: four equal chunks, as before
+    for (int c = 0; c < 4; ++c) bytes.push_back(total / 4);
+  } else {
+    for (int i = 0; i < 3; ++i) bytes.push_back(ramp[i]);
+    const int64_t mid = total - ramps, k = (mid + cap - 1) / cap;
+    for (int64_t i = 0; i < k; ++i) bytes.push_back(mid / k);
+    for (int i = 2; i >= 0; --i) bytes.push_back(ramp[i]);
+  }
+  int64_t acc = 0;
+  for (size_t c = 0; c + 1 < bytes.size(); ++c) {
+    acc += bytes[c];
+    int64_t r = ((acc / vs) + 3) & ~(int64_t)3;
+    if (r > m) r = m;
+    if (r < row_lo.back()) r = row_lo.back();
+    row_lo.push_back(r);
+  }
+  row_lo.push_back(m);
+}
+
+// x pieces, one per row chunk: piece c ends right behind the highest column chunk c references (chunk_cmax[c], -1 for a
+// chunk without entries), so that for a banded matrix chunk c waits for piece c only -- with equal pieces it waited for
+// piece c + 1, because a block of rows references a little more than its own slice of x.  Piece ends never decrease and
+// the last piece ends at n; need[c] = the last piece chunk c has to wait for (pieces are uploaded in order).
+void pipe_pieces(int64_t n, const std::vector<int64_t> &chunk_cmax, std::vector<int64_t> &x_lo, std::vector<int> &need) {
+  const size_t C = chunk_cmax.size();
+  x_lo.assign(C + 1, 0);
+  for (size_t c = 0; c < C; ++c) {
+    int64_t e = ((chunk_cmax[c] + 1) + 3) & ~(int64_t)3;
+    if (e > n) e = n;
+    if (e < x_lo[c]) e = x_lo[c];
+    x_lo[c + 1] = e;
+  }
+  if (C) x_lo[C] = n;
+  need.assign(C, 0);
+  for (size_t c = 0; c < C; ++c) {
+    int piece = 0;
+    while ((size_t)piece + 1 < C && x_lo[(size_t)piece + 1] <= chunk_cmax[c]) ++piece;
+    need[c] = piece;
+  }
+}
+
 void tile_rows(int64_t m, const int32_t *rp, int64_t tile, std::vector<int32_t> &tile_row) {
   const int64_t nnz = rp[m];
   const int64_t n_tiles = (nnz + tile - 1) / tile;
