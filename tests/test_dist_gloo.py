@@ -148,3 +148,16 @@ def test_partition_closed_form_matches_library():
     lo = bench.partition_stencil(400, 8)
     nnz = [bench.stencil27_before(lo[i + 1], 400) - bench.stencil27_before(lo[i], 400) for i in range(8)]
     assert max(nnz) - min(nnz) <= 2 * 27
+
+
+def test_three_rank_halo_exchange_middle_rank_has_two_neighbours(tmp_path):
+    """world size 3: the middle rank receives a halo on both sides and pushes to both neighbours; the outer ranks
+    exchange with the middle one only (same assertions as the two-rank worker: plan == oracle plan, halo filled
+    exactly, y == whole-matrix product, interior rows never touch the halo)."""
+    port = 29900 + (os.getpid() % 90)
+    mp.spawn(_worker, args=(3, port, 13, str(tmp_path), True), nprocs=3, join=True)
+    got = [open(str(tmp_path / ("ok%d" % r))).read().split() for r in range(3)]
+    assert int(got[0][1]) == int(got[1][0]) and int(got[1][1]) == int(got[2][0]) and int(got[2][1]) == 13 ** 3
+    half_bw = 13 * 13 + 13 + 1
+    assert 13 * 13 <= int(got[0][2]) <= half_bw and 13 * 13 <= int(got[2][2]) <= half_bw
+    assert 2 * 13 * 13 <= int(got[1][2]) <= 2 * half_bw                  # both sides
