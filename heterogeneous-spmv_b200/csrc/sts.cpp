@@ -13,6 +13,8 @@
 #include "host_index.h"
 
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 namespace hspmv {
@@ -30,8 +32,106 @@ bool compare_deg_id_pair(degree_id_pair p1, degree_id_pair p2) { return p1.deg <
 // perm: new -> old; pack_ptr: n_packs + 1 entries.  HSPMV_EUNSUPPORTED when a row has no stored diagonal or the
 // search stalls (structurally unsymmetric matrix) -- the reference prints "Number of vertices did not change in
 // level" and goes on with garbage (csrk.cpp:2797-2800).
+// levels sorted by size with the reference's call, then written out as perm / pack_ptr (shared by both finders)
+static void emit_packs(int64_t n, const std::vector<int32_t> &order, const std::vector<int32_t> &level_ptr, uvec &perm,
+                       std::vector<int32_t> &pack_ptr) {
+  const int n_levels = (int)level_ptr.size() - 1;
+  std::vector<degree_id_pair> sizes((size_t)n_levels);
+  for (int i = 0; i < n_levels; ++i) sizes[(size_t)i] = degree_id_pair(level_ptr[(size_t)i + 1] - level_ptr[(size_t)i], i);
+  std::sort(sizes.begin(), sizes.begin() + n_levels, compare_deg_id_pair);
+  perm.resize((size_t)n);
+  pack_ptr.assign(1, 0);
+  for (int i = 0; i < n_levels; ++i) {
+    const int old = sizes[(size_t)i].id;
+    pack_ptr.push_back(pack_ptr.back() + (level_ptr[(size_t)old + 1] - level_ptr[(size_t)old]));
+  }
+#pragma omp parallel for schedule(dynamic, 16)
+  for (int i = 0; i < n_levels; ++i) {
+    const int old = sizes[(size_t)i].id;
+    int32_t dst = pack_ptr[(size_t)i];
+    for (int32_t j = level_ptr[(size_t)old]; j < level_ptr[(size_t)old + 1]; ++j) perm[(size_t)dst++] = (u32)order[(size_t)j];
+  }
+}
+
+// The same level sets for a STRUCTURALLY SYMMETRIC matrix, without the level-by-level bookkeeping.  With (u, v) stored
+// whenever (v, u) is, the search above reduces to:
+//   * level(v) = 0 when row v has nothing before its diagonal, else 1 + max level(u) over its lower neighbours u < v --
+//     one pass over the rows in index order (a vertex enters the level after the one that removed its last lower
+//     neighbour, and it is always a candidate then: that neighbour lists it);
+//   * order inside level L+1 = the order in which the scan of level L (its vertices in order, their neighbours in
+//     storage order) first meets each vertex of level L+1 -- candidates that fail are forgotten at the end of a level,
+//     so only this scan decides; level 0 is in index order.
+// The symmetry test (every entry's mirror found by binary search) runs on all cores; the two passes are O(nnz) with no
+// searches.  Returns 1 when the matrix is not symmetric (the caller then runs the literal search, which also covers
+// the inputs the reference accepts by accident), HSPMV_EUNSUPPORTED for a missing diagonal.
+static int sts_levels_symmetric(int64_t n, const int32_t *rp, const int32_t *ci, std::vector<int32_t> &order,
+                                std::vector<int32_t> &level_ptr) {
+  std::vector<int32_t> diag((size_t)n);
+  int bad_diag = 0, asym = 0;
+#pragma omp parallel for schedule(dynamic, 4096) reduction(| : bad_diag, asym)
+  for (int64_t v = 0; v < n; ++v) {
+    const int32_t *b = ci + rp[v], *e = ci + rp[v + 1];
+    const int32_t *d = std::lower_bound(b, e, (int32_t)v);
+    if (d == e || *d != (int32_t)v) {
+      bad_diag = 1;
+      diag[(size_t)v] = 0;
+      continue;
+    }
+    diag[(size_t)v] = (int32_t)(d - b);
+    for (const int32_t *p = b; p < e; ++p) {
+      const int32_t u = *p;
+      if (u == (int32_t)v) continue;
+      if (u < 0 || u >= n || (p > b && p[-1] >= u) || !std::binary_search(ci + rp[u], ci + rp[u + 1], (int32_t)v)) asym = 1;
+    }
+  }
+  if (bad_diag) return HSPMV_EUNSUPPORTED;
+  if (asym) return 1;
+  std::vector<int32_t> level((size_t)n);
+  int32_t n_levels = 0;
+  for (int64_t v = 0; v < n; ++v) {
+    int32_t lv = -1;
+    const int32_t *b = ci + rp[v];
+    for (int32_t t = 0; t < diag[(size_t)v]; ++t) lv = std::max(lv, level[(size_t)b[t]]);
+    level[(size_t)v] = lv + 1;
+    n_levels = std::max(n_levels, lv + 2);
+  }
+  level_ptr.assign((size_t)n_levels + 1, 0);
+  for (int64_t v = 0; v < n; ++v) ++level_ptr[(size_t)level[(size_t)v] + 1];
+  for (int32_t l = 0; l < n_levels; ++l) level_ptr[(size_t)l + 1] += level_ptr[(size_t)l];
+  order.resize((size_t)n);
+  int32_t filled = 0;
+  for (int64_t v = 0; v < n; ++v)
+    if (level[(size_t)v] == 0) order[(size_t)filled++] = (int32_t)v;
+  std::vector<char> placed((size_t)n, 0);
+  for (int32_t l = 0; l + 1 < n_levels; ++l) {
+    int32_t dst = level_ptr[(size_t)l + 1];
+    for (int32_t i = level_ptr[(size_t)l]; i < level_ptr[(size_t)l + 1]; ++i) {
+      const int32_t g = order[(size_t)i];
+      for (int32_t j = rp[g]; j < rp[g + 1]; ++j) {
+        const int32_t nb = ci[j];
+        if (level[(size_t)nb] == l + 1 && !placed[(size_t)nb]) {
+          placed[(size_t)nb] = 1;
+          order[(size_t)dst++] = nb;
+        }
+      }
+    }
+    if (dst != level_ptr[(size_t)l + 2]) return 1; // (cannot happen for a symmetric matrix; let the literal search decide)
+  }
+  return HSPMV_OK;
+}
+
 int sts_levels(int64_t n, const int32_t *rp, const int32_t *ci, uvec &perm, std::vector<int32_t> &pack_ptr) {
   if (n <= 0 || !rp || !ci) return HSPMV_EINVAL;
+  const char *mode = std::getenv("HSPMV_STS_LEVELS"); // "literal" forces the level-by-level search (tests)
+  if (!(mode && std::strcmp(mode, "literal") == 0)) {
+    std::vector<int32_t> order, level_ptr;
+    const int rc = sts_levels_symmetric(n, rp, ci, order, level_ptr);
+    if (rc == HSPMV_OK) {
+      emit_packs(n, order, level_ptr, perm, pack_ptr);
+      return HSPMV_OK;
+    }
+    if (rc != 1) return rc;
+  }
   std::vector<int32_t> lower((size_t)n);
   for (int64_t v = 0; v < n; ++v) { // entries before the diagonal; the diagonal must be there
     const int32_t *b = ci + rp[v], *e = ci + rp[v + 1];
@@ -82,18 +182,7 @@ int sts_levels(int64_t n, const int32_t *rp, const int32_t *ci, uvec &perm, std:
     }
     level_ptr.push_back((int32_t)order.size());
   }
-  const int n_levels = (int)level_ptr.size() - 1;
-  std::vector<degree_id_pair> sizes((size_t)n_levels);
-  for (int i = 0; i < n_levels; ++i) sizes[(size_t)i] = degree_id_pair(level_ptr[(size_t)i + 1] - level_ptr[(size_t)i], i);
-  std::sort(sizes.begin(), sizes.begin() + n_levels, compare_deg_id_pair);
-  perm.clear();
-  perm.reserve((size_t)n);
-  pack_ptr.assign(1, 0);
-  for (int i = 0; i < n_levels; ++i) {
-    const int old = sizes[(size_t)i].id;
-    for (int32_t j = level_ptr[(size_t)old]; j < level_ptr[(size_t)old + 1]; ++j) perm.push_back((u32)order[(size_t)j]);
-    pack_ptr.push_back((int32_t)perm.size());
-  }
+  emit_packs(n, order, level_ptr, perm, pack_ptr);
   return HSPMV_OK;
 }
 

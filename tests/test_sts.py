@@ -139,3 +139,39 @@ def test_sts_on_gpu_against_the_reference(dtype, hs, oracle, gen):
         y_ref = oracle.csr_spmv(rp, ci, v, xx)
         assert np.max(np.abs(y - y_ref)) <= (1e-12 if dtype == np.float64 else 1e-5) * np.max(oracle.abs_rowsum(rp, ci, v, xx)), name
         G.A.close()
+
+
+def test_direct_level_computation_equals_the_literal_search(hs, oracle, monkeypatch):
+    """csrc/sts.cpp has two finders: the level-by-level search (the reference's decisions, literally) and, for
+    structurally symmetric matrices, levels straight from 'one more than the deepest lower neighbour' plus the order in
+    which the previous level's scan first meets each vertex.  Random symmetric matrices (hubs, disconnected pieces, long
+    chains): both finders == oracle; matrices with extra one-sided UPPER entries (accepted by the reference: only lower
+    entries need a mirror) must take the literal path and still match."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(99)
+    for trial in range(80):
+        n = int(rng.integers(2, 500))
+        e = int(n * float(rng.choice([0.3, 1.0, 3.0, 8.0])))
+        a = sp.coo_matrix((np.ones(e), (rng.integers(0, n, e), rng.integers(0, n, e))), shape=(n, n)).tocsr()
+        if trial % 6 == 0:                                   # a hub
+            spokes = rng.choice(n, size=max(1, n // 3), replace=False)
+            a = a + sp.coo_matrix((np.ones(len(spokes)), (np.full(len(spokes), int(rng.integers(0, n))), spokes)), shape=(n, n)).tocsr()
+        if trial % 5 == 0:                                   # a chain: as many levels as vertices
+            a = a + sp.diags([np.ones(n - 1)], [1], shape=(n, n)).tocsr()
+        a = (a + a.T + sp.identity(n)).tocsr()
+        if trial % 4 == 3:                                   # one-sided upper entries: (g, v) with g < v and no (v, g)
+            g = rng.integers(0, n, 5)
+            v = rng.integers(0, n, 5)
+            keep = g < v
+            extra = sp.coo_matrix((np.ones(int(keep.sum())), (g[keep], v[keep])), shape=(n, n)).tocsr()
+            a = (a + extra).tocsr()
+        a.sort_indices()
+        rp, ci = a.indptr.astype(np.int32), a.indices.astype(np.int32)
+        want = oracle.sts_levels(rp, ci)
+        monkeypatch.delenv("HSPMV_STS_LEVELS", raising=False)
+        got = hs.sts_levels_host(rp, ci)
+        monkeypatch.setenv("HSPMV_STS_LEVELS", "literal")
+        lit = hs.sts_levels_host(rp, ci)
+        for key in ("perm", "pack_ptr"):
+            assert np.array_equal(got[key], want[key]), (trial, key, "direct")
+            assert np.array_equal(lit[key], want[key]), (trial, key, "literal")
