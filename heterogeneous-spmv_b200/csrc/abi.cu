@@ -25,6 +25,7 @@
 
 using hspmv::u32;
 using hspmv::uvec;
+using hspmv::ivec;
 
 namespace {
 
@@ -131,7 +132,7 @@ struct hspmv_matrix {
   void *d_carry_val = nullptr;
 
   // host copies (kept on request; needed for Band-k)
-  std::vector<int32_t> h_rp, h_ci;
+  ivec h_rp, h_ci;
   std::vector<unsigned char> h_val;
   uvec h_perm, h_sr, h_ssr;
 
@@ -975,7 +976,7 @@ int hspmv_create_csr(hspmv_matrix **out, int64_t m, int64_t n, int64_t nnz, cons
   if (keep_host) {
     A->h_val.assign((const unsigned char *)val, (const unsigned char *)val + (size_t)nnz * vs);
   } else {
-    std::vector<int32_t>().swap(A->h_ci);
+    ivec().swap(A->h_ci);
   }
   hspmv::row_stats(m, A->h_rp.data(), A->stats);
   A->stats_ready = true;
@@ -1161,6 +1162,7 @@ int build_csrk_device(hspmv_matrix *A, int k, const int *sizes) {
   };
   if (A->h_rp.empty()) {
     A->h_rp.resize((size_t)A->m + 1);
+    hspmv::first_touch(A->h_rp.data(), (size_t)(A->m + 1) * 4);
     CU(cudaMemcpy(A->h_rp.data(), A->d_rp, (size_t)(A->m + 1) * 4, cudaMemcpyDeviceToHost));
   }
   if (A->nnz == 0 || A->h_rp[(size_t)A->m] != (int32_t)A->nnz) return hspmv::BANDK_USE_HOST;
@@ -1222,7 +1224,7 @@ int build_csrk_device(hspmv_matrix *A, int k, const int *sizes) {
   A->d_ci = ci2;
   A->d_val = val2;
   CU(cudaMemcpy(A->h_rp.data(), A->d_rp, (size_t)(A->m + 1) * 4, cudaMemcpyDeviceToHost));
-  std::vector<int32_t>().swap(A->h_ci); // host copies of the un-reordered entries are stale now
+  ivec().swap(A->h_ci); // host copies of the un-reordered entries are stale now
   std::vector<unsigned char>().swap(A->h_val);
   lap(3);
   rc = finish_csrk(A, k, perm, sr, ssr);
@@ -1248,10 +1250,12 @@ int hspmv_build_csrk(hspmv_matrix *A, int k, const int *sup_row_sizes) {
   // host copy of the CSR arrays: kept at creation, or fetched back from HBM
   if (A->h_rp.empty()) {
     A->h_rp.resize((size_t)A->m + 1);
+    hspmv::first_touch(A->h_rp.data(), (size_t)(A->m + 1) * 4);
     CU(cudaMemcpy(A->h_rp.data(), A->d_rp, (size_t)(A->m + 1) * 4, cudaMemcpyDeviceToHost));
   }
   if (A->h_ci.size() != (size_t)A->nnz) {
     A->h_ci.resize((size_t)A->nnz);
+    hspmv::first_touch(A->h_ci.data(), (size_t)A->nnz * 4);
     if (A->nnz) CU(cudaMemcpy(A->h_ci.data(), A->d_ci, (size_t)A->nnz * 4, cudaMemcpyDeviceToHost));
   }
   if (A->h_val.size() != (size_t)A->nnz * vs) {
@@ -1264,7 +1268,7 @@ int hspmv_build_csrk(hspmv_matrix *A, int k, const int *sup_row_sizes) {
   if (rc) return fail(rc, bandk_error(rc));
   if (sr.back() != (u32)A->m) return fail(HSPMV_EUNSUPPORTED, "Band-k: trailing empty rows are not covered by a super-row");
   // A' = P A P^T on the host, then one upload of the REORDERED arrays
-  std::vector<int32_t> rp2((size_t)A->m + 1), ci2((size_t)A->nnz);
+  ivec rp2((size_t)A->m + 1), ci2((size_t)A->nnz);
   std::vector<unsigned char> val2((size_t)A->nnz * vs);
   if (A->dtype == HSPMV_F64)
     hspmv::reorder_f64(A->m, perm.data(), (const u32 *)A->h_rp.data(), (const u32 *)A->h_ci.data(),
@@ -1320,7 +1324,7 @@ int hspmv_relabel_hub_columns(hspmv_matrix *A, uint32_t *perm_out) {
   CU(cudaMemcpy(A->d_perm, perm.data(), (size_t)A->n * 4, cudaMemcpyHostToDevice));
   A->cols_only_perm = true;
   A->graph_iters = 0; // (the arrays stay where they are, but a replay must not be mistaken for the un-relabelled product)
-  std::vector<int32_t>().swap(A->h_ci); // host copy (if any) is stale
+  ivec().swap(A->h_ci); // host copy (if any) is stale
   free_pipe(A);
   if (perm_out) std::memcpy(perm_out, perm.data(), perm.size() * 4);
   A->h_perm.swap(perm);
@@ -2308,10 +2312,12 @@ int hspmv_build_sts(hspmv_matrix *A) {
   const size_t vs = A->vsize();
   if (A->h_rp.empty()) {
     A->h_rp.resize((size_t)A->m + 1);
+    hspmv::first_touch(A->h_rp.data(), (size_t)(A->m + 1) * 4);
     CU(cudaMemcpy(A->h_rp.data(), A->d_rp, (size_t)(A->m + 1) * 4, cudaMemcpyDeviceToHost));
   }
   if (A->h_ci.size() != (size_t)A->nnz) {
     A->h_ci.resize((size_t)A->nnz);
+    hspmv::first_touch(A->h_ci.data(), (size_t)A->nnz * 4);
     if (A->nnz) CU(cudaMemcpy(A->h_ci.data(), A->d_ci, (size_t)A->nnz * 4, cudaMemcpyDeviceToHost));
   }
   uvec perm;
@@ -2345,7 +2351,7 @@ int hspmv_build_sts(hspmv_matrix *A) {
         A->d_val = val2;
         A->d_perm = d_perm;
         CU(cudaMemcpy(A->h_rp.data(), A->d_rp, (size_t)(A->m + 1) * 4, cudaMemcpyDeviceToHost));
-        std::vector<int32_t>().swap(A->h_ci);
+        ivec().swap(A->h_ci);
         std::vector<unsigned char>().swap(A->h_val);
         done = true;
       }
@@ -2363,7 +2369,7 @@ int hspmv_build_sts(hspmv_matrix *A) {
       A->h_val.resize((size_t)A->nnz * vs);
       if (A->nnz) CU(cudaMemcpy(A->h_val.data(), A->d_val, (size_t)A->nnz * vs, cudaMemcpyDeviceToHost));
     }
-    std::vector<int32_t> rp2((size_t)A->m + 1), ci2((size_t)A->nnz);
+    ivec rp2((size_t)A->m + 1), ci2((size_t)A->nnz);
     std::vector<unsigned char> val2((size_t)A->nnz * vs);
     if (A->dtype == HSPMV_F64)
       hspmv::reorder_f64(A->m, perm.data(), (const u32 *)A->h_rp.data(), (const u32 *)A->h_ci.data(), (const double *)A->h_val.data(),
@@ -2372,7 +2378,7 @@ int hspmv_build_sts(hspmv_matrix *A) {
       hspmv::reorder_f32(A->m, perm.data(), (const u32 *)A->h_rp.data(), (const u32 *)A->h_ci.data(), (const float *)A->h_val.data(),
                          (u32 *)rp2.data(), (u32 *)ci2.data(), (float *)val2.data());
     A->h_rp.swap(rp2);
-    std::vector<int32_t>().swap(A->h_ci);
+    ivec().swap(A->h_ci);
     std::vector<unsigned char>().swap(A->h_val);
     CU(cudaMemcpy(A->d_rp, A->h_rp.data(), (size_t)(A->m + 1) * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(A->d_ci, ci2.data(), (size_t)A->nnz * 4, cudaMemcpyHostToDevice));

@@ -28,6 +28,7 @@ template <typename T> struct RawAlloc {
   template <class U> bool operator!=(const RawAlloc<U> &) const noexcept { return false; }
 };
 typedef std::vector<u32, RawAlloc<u32>> uvec;
+typedef std::vector<int32_t, RawAlloc<int32_t>> ivec; // the handle's host copies of row_ptr / col_idx (up to 6.9 GB at config 5)
 // one write per page of [p, p + bytes) from all host cores (the pages of a fresh allocation are faulted in there,
 // not one by one under a single-threaded copy)
 void first_touch(void *p, size_t bytes);
