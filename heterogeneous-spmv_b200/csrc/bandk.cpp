@@ -326,8 +326,8 @@ void rcm_order(const Coarse &g, uvec &new2old, uvec &old2new) {
 // Levels below `cutoff` vertices are expanded by one thread (no fork), so a long thin graph costs what the
 // serial walk costs.  tests/test_host_index.py runs both walks against the oracle and the compiled reference.
 struct RcmPar {
-  static const u32 UNNUMBERED = 0x80000000u; // posn: numbers are < 2^31; >= 2^31 = not numbered yet (NONE, a claim, TAKEN)
-  static const u32 NONE = 0xFFFFFFFFu, TAKEN = 0xFFFFFFFEu;
+  static constexpr u32 UNNUMBERED = 0x80000000u; // posn: numbers are < 2^31; >= 2^31 = not numbered yet (NONE, a claim, TAKEN)
+  static constexpr u32 NONE = 0xFFFFFFFFu, TAKEN = 0xFFFFFFFEu;
   const Coarse &g;
   const int nt;
   const size_t cutoff;

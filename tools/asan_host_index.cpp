@@ -1,0 +1,44 @@
+// AddressSanitizer / UBSan pass over the host index work (Band-k with both RCM walks, STS level sets, bins, blocks, tiles,
+// partition, pipeline plan) on 200 random symmetric matrices:
+//   cd heterogeneous-spmv_b200/csrc && g++ -O1 -g -std=c++17 -fopenmp -fsanitize=address,undefined ../../tools/asan_host_index.cpp bandk.cpp sts.cpp partition.cpp -o /tmp/asan_host
+//   HSPMV_RCM=parallel HSPMV_RCM_CUTOFF=3 ASAN_OPTIONS=detect_leaks=0 /tmp/asan_host   # and once without the variables
+#include "../heterogeneous-spmv_b200/csrc/host_index.h"
+#include <cstdio>
+#include <random>
+#include <set>
+using namespace hspmv;
+int main() {
+  std::mt19937 rng(5);
+  for (int trial = 0; trial < 200; ++trial) {
+    int n = 2 + rng() % 3000;
+    std::vector<std::set<int>> adj(n);
+    int e = n * (1 + rng() % 6);
+    for (int i = 0; i < e; ++i) { int a = rng() % n, b = rng() % n; adj[a].insert(b); adj[b].insert(a); }
+    for (int i = 0; i < n; ++i) adj[i].insert(i);
+    if (trial % 7 == 0) for (int i = 0; i + 1 < n; ++i) { adj[i].insert(i + 1); adj[i + 1].insert(i); }
+    std::vector<int32_t> rp(1, 0), ci;
+    for (int i = 0; i < n; ++i) { for (int c : adj[i]) ci.push_back(c); rp.push_back((int32_t)ci.size()); }
+    uvec perm; std::vector<int32_t> pack;
+    int rc = sts_levels(n, rp.data(), ci.data(), perm, pack);
+    if (rc || (int)perm.size() != n || pack.back() != n) { printf("sts fail %d\n", rc); return 1; }
+    std::vector<int32_t> rows; int64_t bp[NUM_BINS + 1];
+    bin_rows(n, rp.data(), rows, bp);
+    int64_t st[10]; row_stats(n, rp.data(), st);
+    row_len_percentile(n, rp.data(), 90);
+    std::vector<int32_t> blk; block_rows(n, rp.data(), 64, 16, blk);
+    std::vector<int32_t> tr; tile_rows(n, rp.data(), 37, tr);
+    int64_t lo[9]; partition_rows(n, rp.data(), 8, nullptr, 0, lo);
+    uvec p2, sr, ssr; int sizes[2] = {1 + (int)(rng() % 9), 1 + (int)(rng() % 5)};
+    int k = 2 + trial % 2;
+    rc = bandk_build(n, (int64_t)ci.size(), (const u32 *)rp.data(), (const u32 *)ci.data(), k, sizes, p2, sr, ssr);
+    if (rc) { printf("bandk fail %d\n", rc); return 1; }
+  }
+  for (int64_t m : {4200000LL, 64000000LL, 2147483000LL}) {
+    std::vector<int64_t> rl, xl; std::vector<int> need;
+    pipe_chunks(m, 8, rl);
+    std::vector<int64_t> cm(rl.size() - 1);
+    for (size_t c = 0; c + 1 < rl.size(); ++c) cm[c] = std::min<int64_t>(m - 1, rl[c + 1] + 1000);
+    pipe_pieces(m, cm, xl, need);
+  }
+  printf("ok\n");
+}

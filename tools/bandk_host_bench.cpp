@@ -69,7 +69,7 @@ int main(int argc, char **argv) {
     int rc = bandk_finish(16 * g.n, k, sizes, level1, map1, perm, sr, ssr);
     std::printf("bandk_finish k=%d on %lld rows: %.3f s (rc %d)  [HSPMV_BANDK_TRACE=1 prints the phases]\n", k, (long long)(16 * g.n), now() - t0, rc);
   }
-  const int64_t n = 64000000;
+  const int64_t n = argc > 5 ? std::atoll(argv[5]) : 64000000;
   uvec rp((size_t)n + 1);
   rp[0] = 0;
   for (int64_t i = 0; i < n; i++) rp[(size_t)i + 1] = rp[(size_t)i] + ((i % 400 == 0 || i % 400 == 399) ? 18 : 27);
