@@ -4,12 +4,14 @@
 //   HSPMV_RCM=parallel HSPMV_RCM_CUTOFF=3 ASAN_OPTIONS=detect_leaks=0 /tmp/asan_host   # and once without the variables
 #include "../heterogeneous-spmv_b200/csrc/host_index.h"
 #include <cstdio>
+#include <cstdlib>
 #include <random>
 #include <set>
 using namespace hspmv;
-int main() {
+int main(int argc, char **argv) {
   std::mt19937 rng(5);
-  for (int trial = 0; trial < 200; ++trial) {
+  const int trials = argc > 1 ? std::atoi(argv[1]) : 200;
+  for (int trial = 0; trial < trials; ++trial) {
     int n = 2 + rng() % 3000;
     std::vector<std::set<int>> adj(n);
     int e = n * (1 + rng() % 6);
