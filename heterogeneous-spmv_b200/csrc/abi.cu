@@ -1711,8 +1711,8 @@ int build_pipe(hspmv_matrix *A) {
   P.tried = true;
   const size_t vs = A->vsize();
   if (A->d_perm || A->k != 1 || (size_t)A->m * vs < ((size_t)32 << 20)) return HSPMV_OK; // small or permuted: plain path
-  // row chunks with ramped sizes, and x pieces cut where the chunks' column ranges end (partition.cpp: pipe_chunks,
-  // pipe_pieces -- host rules, property-tested without a device through hspmv_pipe_plan_host)
+  // equal row chunks, and x pieces cut where the chunks' column ranges end (partition.cpp: pipe_chunks, pipe_pieces --
+  // host rules, property-tested without a device through hspmv_pipe_plan_host)
   hspmv::pipe_chunks(A->m, (int64_t)vs, P.row_lo);
   const int C = (int)P.row_lo.size() - 1;
   P.chunks = C;

@@ -151,37 +151,23 @@ void block_rows(int64_t m, const int32_t *rp, int64_t cap, int64_t max_rows, std
 }
 
 // ---- plan of the pipelined host call (hspmv_spmv_host, abi.cu:spmv_host_pipelined) ----------------------------------
-// Row chunks: y goes down (and the kernel runs) chunk by chunk.  The call's time is the PCIe time of x up and y down
-// plus what cannot overlap: the first x piece (nothing can run before it has landed) and the last y chunk (nothing is
-// left to overlap it with).  So the chunks ramp up from an eighth of the regular size and ramp down again at the end;
-// the regular size is total / 32 clamped to [4 MB, 16 MB] (r2 measurements: 16 MB pieces on a 512 MB vector, 4 MB on
-// the 64 MB shards of an 8-GPU run).  Boundaries are multiples of 4 rows (32 B-aligned copies).
+// Row chunks: y goes down (and the kernel runs) chunk by chunk.  Equal chunks of ~4 MB of y, at least 4 and at most 32
+// of them (the plan every r2 measurement was taken with: 32 x 16 MB on config 5, 16 x 4 MB on the 64 MB shards of an
+// 8-GPU run); boundaries are multiples of 4 rows (32 B-aligned copies).  A timeline model of the three legs
+// (tools/pipe_model.py) says that chunk sizes ramped up at the start and down at the end buy nothing -- the y leg
+// always trails the x leg by one regular chunk -- so the sizes stay equal; what does pay is where the x pieces are cut
+// (pipe_pieces below).
 void pipe_chunks(int64_t m, int64_t vs, std::vector<int64_t> &row_lo) {
   row_lo.assign(1, 0);
   if (m <= 0) {
-    row_lo.push_back(m < 0 ? 0 : m);
+    row_lo.push_back(0);
     return;
   }
-  const int64_t total = m * vs;
-  int64_t cap = total / 32;
-  if (cap < ((int64_t)4 << 20)) cap = (int64_t)4 << 20;
-  if (cap > ((int64_t)16 << 20)) cap = (int64_t)16 << 20;
-  if (total / cap > 56) cap = (total + 55) / 56; // never more than 64 chunks (vectors beyond 900 MB get larger pieces)
-  const int64_t ramp[3] = {cap / 8, cap / 4, cap / 2};
-  const int64_t ramps = 2 * (ramp[0] + ramp[1] + ramp[2]);
-  std::vector<int64_t> bytes;
-  if (total < ramps + cap) { // too small for ramps: four equal chunks, as before
-    for (int c = 0; c < 4; ++c) bytes.push_back(total / 4);
-  } else {
-    for (int i = 0; i < 3; ++i) bytes.push_back(ramp[i]);
-    const int64_t mid = total - ramps, k = (mid + cap - 1) / cap;
-    for (int64_t i = 0; i < k; ++i) bytes.push_back(mid / k);
-    for (int i = 2; i >= 0; --i) bytes.push_back(ramp[i]);
-  }
-  int64_t acc = 0;
-  for (size_t c = 0; c + 1 < bytes.size(); ++c) {
-    acc += bytes[c];
-    int64_t r = ((acc / vs) + 3) & ~(int64_t)3;
+  int64_t C = m * vs / ((int64_t)4 << 20);
+  if (C < 4) C = 4;
+  if (C > 32) C = 32;
+  for (int64_t c = 1; c < C; ++c) {
+    int64_t r = ((m * c / C) + 3) & ~(int64_t)3;
     if (r > m) r = m;
     if (r < row_lo.back()) r = row_lo.back();
     row_lo.push_back(r);

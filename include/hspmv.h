@@ -439,11 +439,11 @@ int hspmv_block_rows_host(int64_t m, const int32_t *row_ptr, int64_t cap, int64_
  * of the rule, 0 the forward scan of row_ptr that hspmv_build_csrk uses; the tests compare the two. */
 int hspmv_bandk_group_rows_host(int64_t n, const uint32_t *row_ptr, uint32_t threshold, int literal, uint32_t *start,
                                 int64_t *n_starts, uint32_t *grp);
-/* Plan of the pipelined host call (hspmv_spmv_host on a large plain-CSR handle): row chunks row_lo[0..C] with sizes
- * that ramp up at the start and down at the end (the first x piece and the last y chunk are what cannot overlap), and --
- * when chunk_cmax[C] (highest column each chunk references, -1 = none) is given -- the x pieces x_lo[0..C] cut where
- * the chunks' column ranges end and need[c] = the last piece chunk c waits for.  row_lo / x_lo need room for 66
- * entries, need for 65.  Host rule behind the call the bench's `e2e` leg times; exposed for the property tests. */
+/* Plan of the pipelined host call (hspmv_spmv_host on a large plain-CSR handle): equal row chunks row_lo[0..C] (~4 MB
+ * of y each, 4 <= C <= 32) and -- when chunk_cmax[C] (highest column each chunk references, -1 = none) is given -- the
+ * x pieces x_lo[0..C], cut where the chunks' column ranges end so that a banded chunk waits for its own piece only,
+ * and need[c] = the last piece chunk c waits for.  row_lo / x_lo need room for 66 entries, need for 65.  Host rule
+ * behind the call the bench's `e2e` leg times; exposed for the property tests. */
 int hspmv_pipe_plan_host(int64_t m, int64_t n, int vsize, const int64_t *chunk_cmax, int64_t *row_lo, int *n_chunks, int64_t *x_lo,
                          int *need);
 /* CSR_VECTOR bins: rows[m] grouped by bin in ascending row order, bin_ptr[9]. */
