@@ -265,6 +265,16 @@ def bandk_group_rows_host(row_ptr, threshold, literal=False):
     return start[: ns.value].copy(), grp[:n].copy()
 
 
+def hub_order_host(count):
+    """Column order of relabel_hub_columns for the reference counts `count`: (perm new->old, inv old->new)."""
+    count = np.ascontiguousarray(count, dtype=np.uint32)
+    n = len(count)
+    perm = np.zeros(max(n, 1), np.uint32)
+    inv = np.zeros(max(n, 1), np.uint32)
+    _check(lib().hspmv_hub_order_host(C.c_int64(n), _p(count), _p(perm), _p(inv)))
+    return perm[:n].copy(), inv[:n].copy()
+
+
 def pipe_plan_host(m, n, vsize=8, chunk_cmax=None):
     """Plan of the pipelined host call (hspmv_spmv_host): row chunk bounds; with chunk_cmax also (x piece bounds, need)."""
     row_lo = np.zeros(66, np.int64)

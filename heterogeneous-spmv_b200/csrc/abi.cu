@@ -1302,17 +1302,12 @@ int hspmv_relabel_hub_columns(hspmv_matrix *A, uint32_t *perm_out) {
     hspmv::col_count_kernel<<<grid_for(A->nnz, 256, A->dev.sms * 16), 256, 0, A->stream>>>(A->nnz, A->d_ci, d_cnt);
     LAUNCHED();
   }
-  uvec cnt((size_t)A->n), perm((size_t)A->n), inv((size_t)A->n);
+  uvec cnt((size_t)A->n), perm, inv;
+  hspmv::first_touch(cnt.data(), (size_t)A->n * 4);
   CU(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)A->n * 4, cudaMemcpyDeviceToHost, A->stream));
   CU(cudaStreamSynchronize(A->stream));
-  // counting sort by descending count, ascending column id inside a count (deterministic, O(n + max count))
-  u32 mx = 0;
-  for (u32 c : cnt) mx = std::max(mx, c);
-  std::vector<int64_t> start((size_t)mx + 2, 0);
-  for (u32 c : cnt) ++start[(size_t)(mx - c) + 1];
-  for (size_t i = 1; i < start.size(); ++i) start[i] += start[i - 1];
-  for (int64_t c = 0; c < A->n; ++c) perm[(size_t)start[(size_t)(mx - cnt[(size_t)c])]++] = (u32)c;
-  for (int64_t i = 0; i < A->n; ++i) inv[perm[(size_t)i]] = (u32)i;
+  // counting sort by descending count, ascending column id inside a count (deterministic; partition.cpp: hub_order)
+  hspmv::hub_order(A->n, cnt.data(), perm, inv);
   CU(cudaMemcpyAsync(d_cnt, inv.data(), (size_t)A->n * 4, cudaMemcpyHostToDevice, A->stream)); // reuse as new_id[]
   if (A->nnz) {
     hspmv::col_relabel_kernel<<<grid_for(A->nnz, 256, A->dev.sms * 16), 256, 0, A->stream>>>(A->nnz, d_cnt, A->d_ci);
@@ -2168,6 +2163,15 @@ int hspmv_bandk_group_rows_host(int64_t n, const uint32_t *row_ptr, uint32_t thr
   std::memcpy(start, s.data(), s.size() * 4);
   if (n) std::memcpy(grp, g.data(), (size_t)n * 4);
   *n_starts = (int64_t)s.size();
+  return HSPMV_OK;
+}
+// column order of the hub relabel, host rule (for the tests): perm[new] = old, inv[old] = new
+int hspmv_hub_order_host(int64_t n, const uint32_t *count, uint32_t *perm, uint32_t *inv) {
+  if (n < 0 || (n > 0 && (!count || !perm || !inv))) return fail(HSPMV_EINVAL, "bad arguments");
+  uvec p, q;
+  hspmv::hub_order(n, count, p, q);
+  if (n) std::memcpy(perm, p.data(), (size_t)n * 4);
+  if (n) std::memcpy(inv, q.data(), (size_t)n * 4);
   return HSPMV_OK;
 }
 // plan of the pipelined host call, host rules (for the property tests): row_lo / x_lo have room for 66 entries, need for 65

@@ -99,6 +99,8 @@ void tile_rows(int64_t m, const int32_t *rp, int64_t tile, std::vector<int32_t> 
 // blk_row[n_blocks] = m (oracle/partition_oracle.py: block_rows restates the rule).
 void block_rows(int64_t m, const int32_t *rp, int64_t cap, int64_t max_rows, std::vector<int32_t> &blk_row);
 
+// column order of hspmv_relabel_hub_columns: descending reference count, ascending id inside a count
+void hub_order(int64_t n, const u32 *cnt, uvec &perm, uvec &inv);
 // plan of the pipelined host call: row chunks and the x piece every chunk waits for (partition.cpp)
 void pipe_chunks(int64_t m, int64_t vs, std::vector<int64_t> &row_lo);
 void pipe_pieces(int64_t n, const std::vector<int64_t> &chunk_cmax, std::vector<int64_t> &x_lo, std::vector<int> &need);

@@ -197,6 +197,56 @@ void pipe_pieces(int64_t n, const std::vector<int64_t> &chunk_cmax, std::vector<
   }
 }
 
+// Order of the columns for hspmv_relabel_hub_columns: by descending reference count, ascending column id inside a
+// count (perm[new] = old, inv[old] = new).  A stable counting sort on key = max - count; on all cores when the
+// per-thread histograms stay small (threads take contiguous column ranges, so concatenating their slots per key in
+// thread order keeps the ids ascending), else on one.
+void hub_order(int64_t n, const u32 *cnt, uvec &perm, uvec &inv) {
+  perm.resize((size_t)(n > 0 ? n : 0));
+  inv.resize((size_t)(n > 0 ? n : 0));
+  if (n <= 0) return;
+  u32 mx = 0;
+#pragma omp parallel for schedule(static) reduction(max : mx) if (n > (1 << 16))
+  for (int64_t c = 0; c < n; ++c) mx = std::max(mx, cnt[c]);
+  int nt = 1;
+#ifdef _OPENMP
+  nt = n > (1 << 16) ? omp_get_max_threads() : 1;
+#endif
+  const int64_t keys = (int64_t)mx + 1;
+  if (keys * nt > n) nt = 1; // histograms larger than the data: one core, one histogram
+  std::vector<int64_t> slot((size_t)(keys * nt), 0); // slot[t * keys + k]: first count, then first output position
+#pragma omp parallel num_threads(nt)
+  {
+    int t = 0;
+#ifdef _OPENMP
+    t = omp_get_thread_num();
+#endif
+    int64_t *h = &slot[(size_t)t * (size_t)keys];
+    const int64_t lo = n * t / nt, hi = n * (t + 1) / nt;
+    for (int64_t c = lo; c < hi; ++c) ++h[mx - cnt[c]];
+  }
+  int64_t run = 0;
+  for (int64_t k = 0; k < keys; ++k)
+    for (int t = 0; t < nt; ++t) {
+      int64_t &v = slot[(size_t)t * (size_t)keys + (size_t)k];
+      const int64_t c = v;
+      v = run;
+      run += c;
+    }
+#pragma omp parallel num_threads(nt)
+  {
+    int t = 0;
+#ifdef _OPENMP
+    t = omp_get_thread_num();
+#endif
+    int64_t *h = &slot[(size_t)t * (size_t)keys];
+    const int64_t lo = n * t / nt, hi = n * (t + 1) / nt;
+    for (int64_t c = lo; c < hi; ++c) perm[(size_t)h[mx - cnt[c]]++] = (u32)c;
+  }
+#pragma omp parallel for schedule(static) if (n > (1 << 16))
+  for (int64_t i = 0; i < n; ++i) inv[perm[(size_t)i]] = (u32)i;
+}
+
 void tile_rows(int64_t m, const int32_t *rp, int64_t tile, std::vector<int32_t> &tile_row) {
   const int64_t nnz = rp[m];
   const int64_t n_tiles = (nnz + tile - 1) / tile;

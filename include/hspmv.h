@@ -439,6 +439,9 @@ int hspmv_block_rows_host(int64_t m, const int32_t *row_ptr, int64_t cap, int64_
  * of the rule, 0 the forward scan of row_ptr that hspmv_build_csrk uses; the tests compare the two. */
 int hspmv_bandk_group_rows_host(int64_t n, const uint32_t *row_ptr, uint32_t threshold, int literal, uint32_t *start,
                                 int64_t *n_starts, uint32_t *grp);
+/* Column order of hspmv_relabel_hub_columns, host rule: columns by descending reference count, ascending id inside a
+ * count; perm[new] = old, inv[old] = new (n entries each).  Exposed for the tests. */
+int hspmv_hub_order_host(int64_t n, const uint32_t *count, uint32_t *perm, uint32_t *inv);
 /* Plan of the pipelined host call (hspmv_spmv_host on a large plain-CSR handle): equal row chunks row_lo[0..C] (~4 MB
  * of y each, 4 <= C <= 32) and -- when chunk_cmax[C] (highest column each chunk references, -1 = none) is given -- the
  * x pieces x_lo[0..C], cut where the chunks' column ranges end so that a banded chunk waits for its own piece only,

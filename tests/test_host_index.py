@@ -576,3 +576,44 @@ def test_pipelined_host_call_plan_properties(hs):
                     assert cmax[c] < x_lo[need[c] + 1], (m, vs, trial, c)
                     if need[c] > 0:
                         assert x_lo[need[c]] <= cmax[c], (m, vs, trial, c)            # and no later piece than necessary
+
+
+def test_hub_column_order_is_a_stable_sort_by_descending_count(hs):
+    """hspmv_relabel_hub_columns' host rule (partition.cpp: hub_order): columns by descending reference count, ascending
+    id inside a count -- against numpy's stable sort, for power-law counts, ties, all-equal counts, one count larger
+    than n (histograms larger than the data: single-core path), and with 1, 3 and all threads above 65536 columns."""
+    import ctypes as C
+    rng = np.random.default_rng(21)
+
+    def check(cnt, tag):
+        perm, inv = hs.hub_order_host(cnt)
+        want = np.argsort(-cnt.astype(np.int64), kind="stable").astype(np.uint32)
+        assert np.array_equal(perm, want), tag
+        assert np.array_equal(inv[perm], np.arange(len(cnt), dtype=np.uint32)), tag
+
+    check(np.zeros(0, np.uint32), "empty")
+    check(np.array([5], np.uint32), "one")
+    for trial in range(40):
+        n = int(rng.integers(1, 3000))
+        kind = trial % 4
+        if kind == 0:
+            cnt = rng.integers(0, 4, n)
+        elif kind == 1:
+            cnt = np.minimum(4.0 / rng.random(n) ** 2, 3e5).astype(np.int64)          # power law
+        elif kind == 2:
+            cnt = np.full(n, int(rng.integers(0, 9)))
+        else:
+            cnt = rng.integers(0, 50, n)
+            cnt[int(rng.integers(0, n))] = 10 * n + 7                                   # a hub referenced more often than there are columns
+        check(cnt.astype(np.uint32), (trial, kind))
+    gomp = C.CDLL("libgomp.so.1", mode=C.RTLD_GLOBAL)
+    before = gomp.omp_get_max_threads()
+    try:
+        big = np.minimum(4.0 / rng.random(200_003) ** 2, 2.4e5).astype(np.uint32)
+        flat = rng.integers(0, 3, 150_000).astype(np.uint32)
+        for nt in (1, 3, before):
+            gomp.omp_set_num_threads(nt)
+            check(big, ("big", nt))
+            check(flat, ("flat", nt))
+    finally:
+        gomp.omp_set_num_threads(before)
