@@ -30,6 +30,10 @@ int main(int argc, char **argv) {
     std::vector<int32_t> blk; block_rows(n, rp.data(), 64, 16, blk);
     std::vector<int32_t> tr; tile_rows(n, rp.data(), 37, tr);
     int64_t lo[9]; partition_rows(n, rp.data(), 8, nullptr, 0, lo);
+    uvec hc((size_t)n), hp, hi;
+    for (int i = 0; i < n; ++i) hc[(size_t)i] = (trial % 5 == 0 && i == n / 2) ? (u32)(20 * n) : (u32)(rng() % 40);
+    hub_order(n, hc.data(), hp, hi);
+    for (int i = 0; i < n; ++i) if (hi[hp[(size_t)i]] != (u32)i) { printf("hub_order fail\n"); return 1; }
     uvec p2, sr, ssr; int sizes[2] = {1 + (int)(rng() % 9), 1 + (int)(rng() % 5)};
     int k = 2 + trial % 2;
     rc = bandk_build(n, (int64_t)ci.size(), (const u32 *)rp.data(), (const u32 *)ci.data(), k, sizes, p2, sr, ssr);
