@@ -213,6 +213,12 @@ void hub_order(int64_t n, const u32 *cnt, uvec &perm, uvec &inv) {
   nt = n > (1 << 16) ? omp_get_max_threads() : 1;
 #endif
   const int64_t keys = (int64_t)mx + 1;
+  if (keys > 4 * n + 1024) { // a count range far larger than the number of columns: no histogram at all
+    for (int64_t c = 0; c < n; ++c) perm[(size_t)c] = (u32)c;
+    std::stable_sort(perm.begin(), perm.end(), [&](u32 a, u32 b) { return cnt[a] > cnt[b]; });
+    for (int64_t i = 0; i < n; ++i) inv[perm[(size_t)i]] = (u32)i;
+    return;
+  }
   if (keys * nt > n) nt = 1; // histograms larger than the data: one core, one histogram
   std::vector<int64_t> slot((size_t)(keys * nt), 0); // slot[t * keys + k]: first count, then first output position
 #pragma omp parallel num_threads(nt)

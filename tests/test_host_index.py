@@ -604,7 +604,7 @@ def test_hub_column_order_is_a_stable_sort_by_descending_count(hs):
             cnt = np.full(n, int(rng.integers(0, 9)))
         else:
             cnt = rng.integers(0, 50, n)
-            cnt[int(rng.integers(0, n))] = 10 * n + 7                                   # a hub referenced more often than there are columns
+            cnt[int(rng.integers(0, n))] = (10 * n + 7) if trial % 8 == 3 else 2_000_000_000    # a hub referenced more often than there are columns (far more: comparison-sort path)
         check(cnt.astype(np.uint32), (trial, kind))
     gomp = C.CDLL("libgomp.so.1", mode=C.RTLD_GLOBAL)
     before = gomp.omp_get_max_threads()
