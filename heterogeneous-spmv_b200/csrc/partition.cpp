@@ -103,12 +103,10 @@ void bin_rows(int64_t m, const int32_t *rp, std::vector<int32_t> &rows, int64_t 
 #endif
   // cnt[t][b] = rows of bin b in thread t's contiguous row range
   std::vector<int64_t> cnt((size_t)nt * NUM_BINS, 0);
-#pragma omp parallel num_threads(nt)
-  {
-    int t = 0;
-#ifdef _OPENMP
-    t = omp_get_thread_num();
-#endif
+  // (a loop over the nt row ranges, not "one range per thread of the team": inside a caller's parallel region the team
+  // may be smaller than requested, and every range must still be walked)
+#pragma omp parallel for schedule(static, 1) num_threads(nt)
+  for (int t = 0; t < nt; ++t) {
     const int64_t lo = m * t / nt, hi = m * (t + 1) / nt;
     int64_t *c = &cnt[(size_t)t * NUM_BINS];
     for (int64_t r = lo; r < hi; ++r) ++c[bin_of_len((int64_t)rp[r + 1] - rp[r])];
@@ -120,12 +118,8 @@ void bin_rows(int64_t m, const int32_t *rp, std::vector<int32_t> &rows, int64_t 
     bin_ptr[b + 1] = bin_ptr[b] + tot;
   }
   rows.resize((size_t)m);
-#pragma omp parallel num_threads(nt)
-  {
-    int t = 0;
-#ifdef _OPENMP
-    t = omp_get_thread_num();
-#endif
+#pragma omp parallel for schedule(static, 1) num_threads(nt)
+  for (int t = 0; t < nt; ++t) {
     int64_t cur[NUM_BINS];
     for (int b = 0; b < NUM_BINS; ++b) {
       cur[b] = bin_ptr[b];
@@ -221,12 +215,8 @@ void hub_order(int64_t n, const u32 *cnt, uvec &perm, uvec &inv) {
   }
   if (keys * nt > n) nt = 1; // histograms larger than the data: one core, one histogram
   std::vector<int64_t> slot((size_t)(keys * nt), 0); // slot[t * keys + k]: first count, then first output position
-#pragma omp parallel num_threads(nt)
-  {
-    int t = 0;
-#ifdef _OPENMP
-    t = omp_get_thread_num();
-#endif
+#pragma omp parallel for schedule(static, 1) num_threads(nt)
+  for (int t = 0; t < nt; ++t) {
     int64_t *h = &slot[(size_t)t * (size_t)keys];
     const int64_t lo = n * t / nt, hi = n * (t + 1) / nt;
     for (int64_t c = lo; c < hi; ++c) ++h[mx - cnt[c]];
@@ -239,12 +229,8 @@ void hub_order(int64_t n, const u32 *cnt, uvec &perm, uvec &inv) {
       v = run;
       run += c;
     }
-#pragma omp parallel num_threads(nt)
-  {
-    int t = 0;
-#ifdef _OPENMP
-    t = omp_get_thread_num();
-#endif
+#pragma omp parallel for schedule(static, 1) num_threads(nt)
+  for (int t = 0; t < nt; ++t) {
     int64_t *h = &slot[(size_t)t * (size_t)keys];
     const int64_t lo = n * t / nt, hi = n * (t + 1) / nt;
     for (int64_t c = lo; c < hi; ++c) perm[(size_t)h[mx - cnt[c]]++] = (u32)c;

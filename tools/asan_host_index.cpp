@@ -46,5 +46,22 @@ int main(int argc, char **argv) {
     for (size_t c = 0; c + 1 < rl.size(); ++c) cm[c] = std::min<int64_t>(m - 1, rl[c + 1] + 1000);
     pipe_pieces(m, cm, xl, need);
   }
+  { // called from inside a caller's parallel region (the inner teams then have ONE thread): same answers
+    const int64_t m = 200000;
+    std::vector<int32_t> rp((size_t)m + 1, 0);
+    uvec cnt((size_t)m);
+    for (int64_t i = 0; i < m; ++i) { rp[(size_t)i + 1] = rp[(size_t)i] + (int32_t)(rng() % 70); cnt[(size_t)i] = (u32)(rng() % 1000); }
+    std::vector<int32_t> rows0; int64_t bp0[NUM_BINS + 1]; bin_rows(m, rp.data(), rows0, bp0);
+    uvec p0, i0; hub_order(m, cnt.data(), p0, i0);
+    int bad = 0;
+#pragma omp parallel num_threads(2) reduction(+ : bad)
+    {
+      std::vector<int32_t> rows1; int64_t bp1[NUM_BINS + 1]; bin_rows(m, rp.data(), rows1, bp1);
+      uvec p1, i1; hub_order(m, cnt.data(), p1, i1);
+      if (rows1 != rows0 || p1 != p0 || i1 != i0) bad = 1;
+      for (int b = 0; b <= NUM_BINS; ++b) if (bp1[b] != bp0[b]) bad = 1;
+    }
+    if (bad) { printf("nested call fail\n"); return 1; }
+  }
   printf("ok\n");
 }
