@@ -175,3 +175,42 @@ def test_direct_level_computation_equals_the_literal_search(hs, oracle, monkeypa
         for key in ("perm", "pack_ptr"):
             assert np.array_equal(got[key], want[key]), (trial, key, "direct")
             assert np.array_equal(lit[key], want[key]), (trial, key, "literal")
+
+
+def test_sts_golden_vectors_from_the_compiled_reference(hs, oracle, gen):
+    """tests/golden/sts/*.npz were produced by the compiled reference's STS path (tests/golden/make_golden_sts.py): level
+    permutation, pack bounds, L, b and the solution for a right-hand side that is not L * 1.  The oracle restatement
+    reproduces all of it bit for bit, and the product's level finder (both forms) the permutation and the packs --
+    without /root/reference or oracle/_ref."""
+    import glob
+    import importlib.util
+    import os
+    import zlib
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    spec = importlib.util.spec_from_file_location("mgs", os.path.join(gold, "make_golden_sts.py"))
+    mgs = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mgs)
+    paths = sorted(glob.glob(os.path.join(gold, "sts", "*.npz")))
+    assert len(paths) == len(mgs.CASES) >= 4
+
+    def crc(a):
+        return np.uint32(zlib.crc32(np.ascontiguousarray(a).tobytes()))
+
+    for path in paths:
+        g = np.load(path)
+        fn, kw = mgs.CASES[os.path.basename(path)[:-4]]
+        for dt, tag in ((np.float32, "f32"), (np.float64, "f64")):
+            rp, ci, v = getattr(gen, fn)(dtype=dt, **kw)
+            assert crc(rp) == g["crc_in_row_ptr"] and crc(ci) == g["crc_in_col"], "generator drifted from the golden inputs"
+            lv = oracle.sts_levels(rp, ci)
+            assert np.array_equal(lv["perm"], g["perm"]) and np.array_equal(lv["pack_ptr"], g["pack_ptr"]), path
+            got = hs.sts_levels_host(rp, ci)
+            assert np.array_equal(got["perm"], g["perm"]) and np.array_equal(got["pack_ptr"], g["pack_ptr"]), path
+            r2, c2, v2 = oracle.bandk_reorder(lv["perm"], rp, ci, v)
+            l_rp, l_ci, l_val = oracle.sts_lower(r2, c2, v2)
+            assert crc(l_rp) == g["crc_l_rp"] and crc(l_ci) == g["crc_l_ci"] and crc(l_val) == g["crc_l_val_" + tag], (path, tag)
+            b = oracle.sts_b(l_rp, l_ci, l_val)
+            assert crc(b) == g["crc_b_" + tag], (path, tag)
+            assert bool(np.all(oracle.sts_solve(lv["pack_ptr"], l_rp, l_ci, l_val, b) == 1)) == bool(g["x_ones_is_exact_" + tag])
+            x = oracle.sts_solve(lv["pack_ptr"], l_rp, l_ci, l_val, mgs.rhs(len(rp) - 1, dt))
+            assert np.array_equal(x, g["x_" + tag]), (path, tag)
