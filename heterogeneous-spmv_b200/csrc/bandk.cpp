@@ -113,8 +113,13 @@ void group_rows(const u32 *rp, int64_t n, u32 T, uvec &start, uvec &grp) {
   }
 }
 
+// (rp, adj): the graph to coarsen; start / grp: the groups.  With new2old / old2new the graph is still stored in its
+// OLD numbering while start / grp (and the result) are in the new one: vertex u is row new2old[u] and its neighbours
+// are old2new[adj[..]] -- renumberGraphUsingReorderedVertices (csrk.cpp:3012-3115) applied on the fly.  The result
+// does not depend on the order of a row's entries (they are collected, sorted and run-length encoded), so it equals
+// coarsening the relabelled graph of relabel() below, without copying and re-sorting its 100 M entries at config 5.
 int build_coarse(const u32 *rp, const u32 *adj, const uvec &start,
-                 const uvec &grp, Coarse &out) {
+                 const uvec &grp, Coarse &out, const u32 *new2old = nullptr, const u32 *old2new = nullptr) {
   const int64_t nc = (int64_t)start.size() - 1;
   out.n = nc;
   uvec up_cnt((size_t)nc + 1, 0);
@@ -139,9 +144,19 @@ int build_coarse(const u32 *rp, const u32 *adj, const uvec &start,
     for (int64_t cv = lo; cv < hi; ++cv) {
       scratch.clear();
       const u32 gs = start[(size_t)cv];
-      for (u32 u = gs; u < start[(size_t)cv + 1]; ++u)
-        for (u32 j = rp[u]; j < rp[u + 1]; ++j)
-          if (adj[j] >= gs) scratch.push_back(grp[adj[j]]);
+      if (new2old) {
+        for (u32 u = gs; u < start[(size_t)cv + 1]; ++u) {
+          const u32 o = new2old[u];
+          for (u32 j = rp[o]; j < rp[o + 1]; ++j) {
+            const u32 w = old2new[adj[j]];
+            if (w >= gs) scratch.push_back(grp[w]);
+          }
+        }
+      } else {
+        for (u32 u = gs; u < start[(size_t)cv + 1]; ++u)
+          for (u32 j = rp[u]; j < rp[u + 1]; ++j)
+            if (adj[j] >= gs) scratch.push_back(grp[adj[j]]);
+      }
       std::sort(scratch.begin(), scratch.end());
       u32 distinct = 0;
       for (size_t i = 0; i < scratch.size();) {
@@ -690,6 +705,7 @@ static int bandk_levels(int64_t n, int64_t nnz, const u32 *rp, const u32 *adj, i
                         uvec &sr_ptr, uvec &ssr_ptr) {
   std::vector<uvec> perms((size_t)k), maps((size_t)k);
   Coarse level[3];
+  uvec fused_n2o, fused_o2n, fused_rp; // level l in its old numbering + the renumbering, while level l+1 is coarsened
 
   const u32 *cur_rp = rp, *cur_adj = adj;
   int64_t cur_n = n, cur_nnz = nnz;
@@ -708,7 +724,14 @@ static int bandk_levels(int64_t n, int64_t nnz, const u32 *rp, const u32 *adj, i
         group_rows(cur_rp, cur_n, T, maps[(size_t)lvl], grp);
       }
       Phase ph("coarse graph (host)");
-      int rc = build_coarse(cur_rp, cur_adj, maps[(size_t)lvl], grp, level[lvl]);
+      int rc;
+      if (lvl > 1 && !fused_n2o.empty()) {
+        rc = build_coarse(level[lvl - 1].rp.data(), level[lvl - 1].adj.data(), maps[(size_t)lvl], grp, level[lvl], fused_n2o.data(),
+                          fused_o2n.data());
+        perms[(size_t)lvl - 1].swap(fused_n2o); // back where the uncoarsening expects it
+      } else {
+        rc = build_coarse(cur_rp, cur_adj, maps[(size_t)lvl], grp, level[lvl]);
+      }
       if (rc) return rc;
     }
     uvec o2n;
@@ -717,12 +740,28 @@ static int bandk_levels(int64_t n, int64_t nnz, const u32 *rp, const u32 *adj, i
       rcm_order_auto(level[lvl], perms[(size_t)lvl], o2n);
     }
     if (lvl + 1 < k) { // the next level coarsens the renumbered graph
-      Phase ph("relabel");
-      relabel(level[lvl], perms[(size_t)lvl], o2n);
-      cur_rp = level[lvl].rp.data();
-      cur_adj = level[lvl].adj.data();
       cur_n = level[lvl].n;
       cur_nnz = (int64_t)level[lvl].adj.size();
+      const char *lit = std::getenv("HSPMV_BANDK_RELABEL"); // "1": relabel first, then coarsen (the literal two steps; tests)
+      if (lit && lit[0] == '1') {
+        Phase ph("relabel");
+        relabel(level[lvl], perms[(size_t)lvl], o2n);
+        cur_rp = level[lvl].rp.data();
+        cur_adj = level[lvl].adj.data();
+        fused_n2o.clear();
+      } else { // renumbering applied on the fly by build_coarse: only the row pointer of the new order is built
+        Phase ph("row pointer in the new order");
+        fused_n2o.swap(perms[(size_t)lvl]);
+        fused_o2n.swap(o2n);
+        fused_rp.resize((size_t)cur_n + 1);
+        fused_rp[0] = 0;
+        for (int64_t i = 0; i < cur_n; ++i) {
+          const u32 o = fused_n2o[(size_t)i];
+          fused_rp[(size_t)i + 1] = fused_rp[(size_t)i] + (level[lvl].rp[o + 1] - level[lvl].rp[o]);
+        }
+        cur_rp = fused_rp.data();
+        cur_adj = nullptr; // (not addressable in the new order; build_coarse goes through new2old / old2new)
+      }
     }
   }
 

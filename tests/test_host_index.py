@@ -54,12 +54,16 @@ CASES = [
 # synchronous one that large graphs get.  HSPMV_RCM / HSPMV_RCM_CUTOFF force either on any graph, so every Band-k test
 # below runs as "auto" (serial at these sizes), with the level-synchronous walk forking on every level (cutoff 1), and
 # with it forking only on levels of >= 7 vertices (mixed serial / forked levels inside one search).
-RCM_MODES = [None, ("parallel", 1), ("parallel", 7)]
+RCM_MODES = [None, ("parallel", 1), ("parallel", 7), "relabel"]
 
 
-@pytest.fixture(params=RCM_MODES, ids=["rcm-auto", "rcm-levelsync-cut1", "rcm-levelsync-cut7"])
+@pytest.fixture(params=RCM_MODES, ids=["rcm-auto", "rcm-levelsync-cut1", "rcm-levelsync-cut7", "relabel-then-coarsen"])
 def rcm_mode(request, monkeypatch):
-    if request.param is not None:
+    """... and the k = 3 builder has two forms of "coarsen the renumbered level-1 graph": the renumbering applied on the
+    fly (default) and the literal two steps, relabel() then coarsen (HSPMV_BANDK_RELABEL=1)."""
+    if request.param == "relabel":
+        monkeypatch.setenv("HSPMV_BANDK_RELABEL", "1")
+    elif request.param is not None:
         monkeypatch.setenv("HSPMV_RCM", request.param[0])
         monkeypatch.setenv("HSPMV_RCM_CUTOFF", str(request.param[1]))
     return request.param
